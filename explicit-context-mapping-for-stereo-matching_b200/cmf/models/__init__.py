@@ -1,0 +1,26 @@
+"""Model registry with the reference's entry point (reference cmf/models/__init__.py:19-41).
+
+`get_model(name)` instantiates the class with NO arguments, exactly like the reference.  Scope of this
+build: `cmfsm` is the B200-native hot path.  The other nine registered names of the
+reference (baselines / ablations / the 1/8 and 1/16 variants) are listed so that a typo and an
+out-of-scope name produce different, explicit errors instead of the reference's bare `print`.
+"""
+from cmf.models.cmfsm import cmfsm
+
+_IMPLEMENTED = {"cmfsm": cmfsm}
+_REFERENCE_NAMES = ("cmf", "cmfsm", "bilinear_cmf", "cmfsm_sub_8", "cmfsm_sub_16", "bilinear_cmf_sub_8",
+                    "bilinear_cmf_sub_16", "cm_sub_16", "cm_sub_8", "cm_sub_4")
+
+
+def _get_model_instance(name):
+    if name in _IMPLEMENTED:
+        return _IMPLEMENTED[name]
+    if name in _REFERENCE_NAMES:
+        raise NotImplementedError(
+            "model '%s' is registered by the reference but not yet built in the B200-native package "
+            "(SURVEY.md section 8f); available: %s" % (name, sorted(_IMPLEMENTED)))
+    raise KeyError("Model {} not available".format(name))
+
+
+def get_model(name):
+    return _get_model_instance(name)()

@@ -1,0 +1,255 @@
+"""`cmfsm` -- the Explicit-Context-Mapping stereo network, B200-native hot path.
+
+Drop-in for the reference class `cmf.models.cmfsm.cmfsm` (reference file cmf/models/cmfsm.py:594-775):
+same constructor (`cmfsm(maxdisp=192)`), same `forward(left, right) -> (disp1, disp2, disp3)`, same
+parameter tree / `state_dict` keys and the same seeded initialisation, so
+checkpoints and the reference drivers (train.py, test.py, eval_kitti.py) work unchanged.
+
+What differs underneath: cost volume, 3-D aggregation (conv/deconv + GroupNorm + residual + ReLU),
+context-mapping weights and the soft-argmin/upsample/mapping epilogue run as hand-written sm_100a kernels
+from libcmfb200.so (`cmf_b200.ops`); the 2-D feature extractor is still dispatched to cuDNN in strict
+fp32.  Output semantics are per-sample `[B,1,H,W]` (the reference
+broadcasts to `[B,B,H,W]` for B>1).  There is no CPU path: CPU inputs raise.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from cmf_b200 import ops
+from cmf_b200 import autograd_ops as aops
+
+GN_GROUPS = 32  # cmfsm.py:33
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers (module tree == reference tree, so state_dict keys and RNG order match)
+# ------------------------------------------------------------------------------------------------
+def _conv_gn_2d(cin, cout, k, stride, pad, dilation):
+    # reference convbn(), cmfsm.py:36-46
+    return nn.Sequential(
+        nn.Conv2d(cin, cout, k, stride, dilation if dilation > 1 else pad, dilation, bias=False),
+        nn.GroupNorm(GN_GROUPS, cout))
+
+
+def _conv_gn_3d(cin, cout, stride=1):
+    # reference convbn_3d(), cmfsm.py:49-58
+    return nn.Sequential(nn.Conv3d(cin, cout, 3, stride, 1, bias=False), nn.GroupNorm(GN_GROUPS, cout))
+
+
+def _deconv_gn_3d(cin, cout):
+    # cmfsm.py:261-281
+    return nn.Sequential(nn.ConvTranspose3d(cin, cout, 3, stride=2, padding=1, output_padding=1, bias=False),
+                         nn.GroupNorm(GN_GROUPS, cout))
+
+
+class ResidualUnit(nn.Module):
+    """Reference BasicBlock (cmfsm.py:61-85): conv-GN-ReLU, conv-GN, + skip, no ReLU after the add."""
+
+    def __init__(self, cin, cout, stride, downsample, pad, dilation):
+        super().__init__()
+        self.conv1 = nn.Sequential(_conv_gn_2d(cin, cout, 3, stride, pad, dilation), nn.ReLU(inplace=True))
+        self.conv2 = _conv_gn_2d(cout, cout, 3, 1, pad, dilation)
+        self.downsample = downsample
+
+    def forward(self, x):
+        y = self.conv2(self.conv1(x))
+        return y + (x if self.downsample is None else self.downsample(x))
+
+
+class feature_extraction(nn.Module):
+    """2-D SPP feature extractor (reference cmfsm.py:126-236); cuDNN fp32 for now."""
+
+    def __init__(self):
+        super().__init__()
+        self._width = 32
+        relu = lambda: nn.ReLU(inplace=True)  # noqa: E731
+        self.firstconv = nn.Sequential(_conv_gn_2d(3, 32, 3, 1, 1, 1), relu(), _conv_gn_2d(32, 32, 3, 1, 1, 1), relu(),
+                                       _conv_gn_2d(32, 32, 3, 1, 1, 1), relu(),
+                                       nn.Conv2d(32, 32, 3, 1, 1, bias=False))
+        self.secondconv = nn.Sequential(nn.GroupNorm(GN_GROUPS, 32), relu(), _conv_gn_2d(32, 32, 3, 2, 1, 1), relu(),
+                                        _conv_gn_2d(32, 32, 3, 1, 1, 1), relu())
+        self.layer1 = self._stack(32, 3, 1, 1, 1)
+        self.layer2 = self._stack(64, 16, 2, 1, 1)
+        self.layer3 = self._stack(128, 3, 1, 1, 1)
+        self.layer4 = self._stack(128, 3, 1, 1, 2)
+        for i, k in enumerate((64, 32, 16, 8), 1):
+            setattr(self, "branch%d" % i,
+                    nn.Sequential(nn.AvgPool2d((k, k), stride=(k, k)), _conv_gn_2d(128, 32, 1, 1, 0, 1), relu()))
+        self.lastconv = nn.Sequential(_conv_gn_2d(320, 128, 3, 1, 1, 1), relu(), nn.Conv2d(128, 32, 1, bias=False))
+
+    def _stack(self, width, n, stride, pad, dilation):
+        down = None
+        if stride != 1 or self._width != width:
+            down = nn.Sequential(nn.Conv2d(self._width, width, 1, stride, bias=False), nn.GroupNorm(GN_GROUPS, width))
+        units = [ResidualUnit(self._width, width, stride, down, pad, dilation)]
+        self._width = width
+        units += [ResidualUnit(width, width, 1, None, pad, dilation) for _ in range(1, n)]
+        return nn.Sequential(*units)
+
+    def forward(self, x):
+        full = self.firstconv(x)  # [B,32,H,W], pre-GN / pre-ReLU: the context-mapping "hr" feature
+        half = self.layer1(self.secondconv(full))
+        raw = self.layer2(half)
+        skip = self.layer4(self.layer3(raw))
+        size = skip.shape[2:]
+        pyramid = [F.interpolate(getattr(self, "branch%d" % i)(skip), size, mode="bilinear", align_corners=False)
+                   for i in (4, 3, 2, 1)]
+        feat = self.lastconv(torch.cat([raw, skip] + pyramid, 1))
+        return feat, half, full
+
+
+class hourglass(nn.Module):
+    """Parameter container of one 3-D hourglass (reference cmfsm.py:240-303); run by cmfsm._hourglass."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Sequential(_conv_gn_3d(c, 2 * c, 2), nn.ReLU(inplace=True))
+        self.conv2 = _conv_gn_3d(2 * c, 2 * c, 1)
+        self.conv3 = nn.Sequential(_conv_gn_3d(2 * c, 2 * c, 2), nn.ReLU(inplace=True))
+        self.conv4 = nn.Sequential(_conv_gn_3d(2 * c, 2 * c, 1), nn.ReLU(inplace=True))
+        self.conv5 = _deconv_gn_3d(2 * c, 2 * c)
+        self.conv6 = _deconv_gn_3d(2 * c, c)
+
+
+class similarity_measure1(nn.Module):
+    """Weights of the similarity MLP 66-32-16-8-1 (reference cmfsm.py:304-358)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv0 = nn.Conv2d(66, 32, 1, bias=False)
+        self.conv1 = nn.Conv2d(32, 16, 1, bias=False)
+        self.conv2 = nn.Conv2d(16, 8, 1, bias=False)
+        self.conv3 = nn.Conv2d(8, 1, 1, bias=False)
+        for m in (self.conv0, self.conv1, self.conv2, self.conv3):  # cmfsm.py:328-330 (consumes RNG)
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+
+class eight_related_context_mapping(nn.Module):
+    """Holds `similarity1`; the 9-neighbour weights are produced by kernel K5 (reference cmfsm.py:431-593)."""
+
+    def __init__(self):
+        super().__init__()
+        self.similarity1 = similarity_measure1()
+
+
+class cmfsm(nn.Module):
+    def __init__(self, maxdisp=192):
+        super().__init__()
+        self.maxdisp = maxdisp
+        self.feature_extraction = feature_extraction()
+        relu = lambda: nn.ReLU(inplace=True)  # noqa: E731
+        self.dres0 = nn.Sequential(_conv_gn_3d(64, 32), relu(), _conv_gn_3d(32, 32), relu())
+        self.dres1 = nn.Sequential(_conv_gn_3d(32, 32), relu(), _conv_gn_3d(32, 32))
+        self.dres2 = hourglass(32)
+        self.dres3 = hourglass(32)
+        self.dres4 = hourglass(32)
+        for i in (1, 2, 3):
+            setattr(self, "classif%d" % i,
+                    nn.Sequential(_conv_gn_3d(32, 32), relu(), nn.Conv3d(32, 1, 3, 1, 1, bias=False)))
+        self.mapping_matrix = eight_related_context_mapping()
+        # reference initialisation, cmfsm.py:638-645: N(0, sqrt(2/(k*...*Cout))) for Conv2d/Conv3d;
+        # ConvTranspose3d keeps the PyTorch default (it is not matched by the isinstance chain).
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Conv3d)):
+                n = m.out_channels
+                for k in m.kernel_size:
+                    n *= k
+                m.weight.data.normal_(0, math.sqrt(2.0 / n))
+        # packed-weight cache: stable per-layer name (survives DataParallel's shallow replicas) + device
+        for name, m in self.named_modules():
+            if isinstance(m, (nn.Conv3d, nn.ConvTranspose3d)):
+                m._cmf_name = name
+        self._packed = {}  # (layer name, device index) -> (version, data_ptr, packed weight)
+
+    # -------------------------------------------------------------------------------- helpers
+    def _pack(self, conv):
+        w = conv.weight
+        key = (conv._cmf_name, w.device.index)
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+            return hit[2]
+        packed = ops.pack_conv3d_weight(w, transposed=isinstance(conv, nn.ConvTranspose3d))
+        self._packed[key] = (w._version, w.data_ptr(), packed)
+        return packed
+
+    def _cg(self, block, x, stride=1, residual=None, relu=False):
+        """conv/deconv + GroupNorm (+residual) (+ReLU) with the parameters of a [conv, GroupNorm] pair."""
+        conv, gn = block[0], block[1]
+        transposed = isinstance(conv, nn.ConvTranspose3d)
+        if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+            return aops.conv3d_gn(x, conv.weight, gn.weight, gn.bias, stride, transposed, residual, relu)
+        return ops.conv3d_gn(x, self._pack(conv), gn.weight, gn.bias, stride, transposed, residual, relu)
+
+    def _hourglass(self, hg, x, presqu, postsqu, out_residual):
+        # reference hourglass.forward, cmfsm.py:283-303 (+ the caller's `out + cost0`, :687,690,693)
+        out = self._cg(hg.conv1[0], x, 2, relu=True)
+        pre = self._cg(hg.conv2, out, 1, residual=postsqu, relu=True)
+        out = self._cg(hg.conv3[0], pre, 2, relu=True)
+        out = self._cg(hg.conv4[0], out, 1, relu=True)
+        post = self._cg(hg.conv5, out, residual=presqu if presqu is not None else pre, relu=True)
+        out = self._cg(hg.conv6, post, residual=out_residual, relu=False)
+        return out, pre, post
+
+    def _classify(self, head, x):
+        t = self._cg(head[0], x, 1, relu=True)
+        last = head[2]
+        if torch.is_grad_enabled() and (t.requires_grad or last.weight.requires_grad):
+            return aops.conv3d_plain(t, last.weight).squeeze(1)
+        y, _ = ops.conv3d_k3(t, self._pack(last), 1)
+        return y.squeeze(1)
+
+    @staticmethod
+    def _check(left, right, maxdisp):
+        if left.shape != right.shape or left.dim() != 4 or left.shape[1] != 3:
+            raise ValueError("expected two [B,3,H,W] images, got %s and %s" % (tuple(left.shape), tuple(right.shape)))
+        B, _, H, W = left.shape
+        if H % 16 or W % 16:
+            raise ValueError("H and W must be multiples of 16 (got %dx%d)" % (H, W))
+        if maxdisp % 16:
+            raise ValueError("maxdisp must be a multiple of 16 (got %d)" % maxdisp)
+        if H < 256 or W < 256 or B * (H // 256) * (W // 256) < 2:
+            raise ValueError("image %dx%d (B=%d) is too small for the 64x64 SPP branch + GroupNorm" % (H, W, B))
+        if not left.is_cuda:
+            raise ops._lib.CmfB200Error("cmfsm runs on CUDA (sm_100a) only; there is no CPU path")
+
+    # -------------------------------------------------------------------------------- forward
+    def forward(self, left, right):
+        self._check(left, right, self.maxdisp)
+        B = left.shape[0]
+        left, right = left.float(), right.float()
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            feat, _half, full = self.feature_extraction(torch.cat([left, right], 0))
+        feat = feat.contiguous()
+        lfeat, rfeat = feat[:B], feat[B:]
+        hr = full[:B].contiguous()
+        scale = hr.shape[-1] // lfeat.shape[-1]
+        D = self.maxdisp // scale
+        sim = self.mapping_matrix.similarity1
+        training = torch.is_grad_enabled() and (feat.requires_grad or sim.conv0.weight.requires_grad)
+
+        if training:
+            weights9 = aops.ctxmap_weights(lfeat, hr, sim.conv0.weight, sim.conv1.weight, sim.conv2.weight,
+                                           sim.conv3.weight)
+            cost = aops.cost_volume_concat(lfeat, rfeat, D)
+        else:
+            weights9 = ops.ctxmap_weights(lfeat, hr, sim.conv0.weight, sim.conv1.weight, sim.conv2.weight,
+                                          sim.conv3.weight)
+            cost = ops.cost_volume_concat(lfeat, rfeat, D)
+
+        cost0 = self._cg(self.dres0[0], cost, relu=True)
+        del cost
+        cost0 = self._cg(self.dres0[2], cost0, relu=True)
+        t = self._cg(self.dres1[0], cost0, relu=True)
+        cost0 = self._cg(self.dres1[2], t, residual=cost0)
+        del t
+        out1, pre1, post1 = self._hourglass(self.dres2, cost0, None, None, cost0)
+        out2, _pre2, post2 = self._hourglass(self.dres3, out1, pre1, post1, cost0)
+        out3, _pre3, _post3 = self._hourglass(self.dres4, out2, pre1, post2, cost0)  # pre1: cmfsm.py:692
+        c1 = self._classify(self.classif1, out1)
+        c2 = self._classify(self.classif2, out2)
+        c3 = self._classify(self.classif3, out3)
+        if training:
+            return aops.softargmin_ctxmap(c1, c2, c3, weights9, scale)
+        return ops.softargmin_ctxmap(c1, c2, c3, weights9, scale)

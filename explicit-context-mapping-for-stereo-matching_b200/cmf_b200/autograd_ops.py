@@ -1,0 +1,205 @@
+"""Differentiable wrappers used when `cmfsm.forward` runs under autograd (training, train.py:166-181).
+
+FORWARD always runs the libcmfb200 kernels.  BACKWARD status (round 1):
+  * cost volume           -- own kernel (`cmfb200_cost_volume_concat_bwd`);
+  * conv/deconv+GroupNorm -- interim: ATen `convolution_backward` / `native_group_norm_backward` on the
+    tensors saved by our forward (SURVEY.md section 7 step 5 allows this while dgrad/wgrad kernels are written);
+  * K5 / K4               -- interim: the closed forms below are re-evaluated with PyTorch CUDA ops inside
+    `backward` only and differentiated by autograd.
+None of this is reachable on CPU tensors (the forward kernels raise first).
+"""
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import ops
+
+_NEIGHBOURS = ((0, 0), (0, -1), (0, 1), (-1, 0), (1, 0), (-1, -1), (-1, 1), (1, -1), (1, 1))
+_aten = torch.ops.aten
+
+
+class _CostVolume(Function):
+    @staticmethod
+    def forward(ctx, L, R, D):
+        ctx.C = L.shape[1]
+        return ops.cost_volume_concat(L.contiguous(), R.contiguous(), D)
+
+    @staticmethod
+    def backward(ctx, g):
+        dL, dR = ops.cost_volume_concat_bwd(g.contiguous(), ctx.C)
+        return dL, dR, None
+
+
+def cost_volume_concat(L, R, D):
+    return _CostVolume.apply(L, R, D)
+
+
+def _mean_rstd(sums, cpg, spatial, eps=ops.GN_EPS):
+    B, C, _ = sums.shape
+    s = sums.view(B, C // cpg, cpg, 2).sum(2)
+    n = float(cpg * spatial)
+    mean = s[..., 0] / n
+    var = (s[..., 1] / n - mean * mean).clamp_min(0)
+    return mean.float(), torch.rsqrt(var + eps).float()
+
+
+class _ConvGN3d(Function):
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, residual, stride, transposed, relu):
+        x = x.contiguous()
+        packed = ops.pack_conv3d_weight(weight, transposed)
+        raw, sums = ops.conv3d_k3(x, packed, stride, transposed, want_stats=True)
+        res = residual.contiguous() if residual is not None else None
+        out = ops.gn_apply(raw, sums, gamma, beta, res, relu)
+        ctx.cfg = (stride, transposed, relu, residual is not None)
+        ctx.save_for_backward(x, weight, gamma, raw, sums, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        stride, transposed, relu, has_res = ctx.cfg
+        x, weight, gamma, raw, sums, out = ctx.saved_tensors
+        g = g.contiguous()
+        if relu:
+            g = g * (out > 0)
+        B, C = raw.shape[:2]
+        spatial = raw[0, 0].numel()
+        cpg = C // ops.GN_GROUPS
+        mean, rstd = _mean_rstd(sums, cpg, spatial)
+        d_raw, d_gamma, d_beta = _aten.native_group_norm_backward(g, raw, mean, rstd, gamma, B, C, spatial,
+                                                                   ops.GN_GROUPS, [True, True, True])
+        s3, one, zero = [stride] * 3, [1, 1, 1], [0, 0, 0]
+        if transposed:
+            dx, dw, _ = _aten.convolution_backward(d_raw, x, weight, None, [2, 2, 2], one, one, True, one, 1,
+                                                   [True, True, False])
+        else:
+            dx, dw, _ = _aten.convolution_backward(d_raw, x, weight, None, s3, one, one, False, zero, 1,
+                                                   [True, True, False])
+        return dx, dw, d_gamma, d_beta, (g if has_res else None), None, None, None
+
+
+def conv3d_gn(x, weight, gamma, beta, stride=1, transposed=False, residual=None, relu=False):
+    return _ConvGN3d.apply(x, weight, gamma, beta, residual, stride, transposed, relu)
+
+
+class _ConvPlain3d(Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        x = x.contiguous()
+        y, _ = ops.conv3d_k3(x, ops.pack_conv3d_weight(weight, False), 1)
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        one, zero = [1, 1, 1], [0, 0, 0]
+        dx, dw, _ = _aten.convolution_backward(g.contiguous(), x, weight, None, one, one, one, False, zero, 1,
+                                               [True, True, False])
+        return dx, dw
+
+
+def conv3d_plain(x, weight):
+    return _ConvPlain3d.apply(x, weight)
+
+
+# ---- backward-only closed forms (PyTorch CUDA ops; differentiated by autograd inside backward) -------
+def _position_code(scale, device):
+    half = scale // 2
+    off = torch.tensor([float(v) for v in list(range(-half, 0)) + list(range(1, half + 1))], device=device)
+    inc = torch.arange(1, scale + 1, device=device, dtype=torch.float32)
+    dec = scale - inc + 1
+    rowv = {"off": off, "inc": inc, "dec": dec}
+    kinds = (("off", "off"), ("dec", "off"), ("inc", "off"), ("off", "dec"), ("off", "inc"),
+             ("dec", "off"), ("inc", "off"), ("off", "dec"), ("off", "inc"))
+    return torch.stack([torch.stack((rowv[a].view(1, scale).expand(scale, scale),
+                                     rowv[b].view(scale, 1).expand(scale, scale))) for a, b in kinds])
+
+
+def _ctxmap_weights_torch(lr, hr, w0, w1, w2, w3):
+    B, C, h, w = lr.shape
+    H, W = hr.shape[2:]
+    s = W // w
+    codes = _position_code(s, lr.device)
+    lr_up = lr.repeat_interleave(s, 2).repeat_interleave(s, 3)
+    logits = []
+    for k, (dy, dx) in enumerate(_NEIGHBOURS):
+        code = codes[k].repeat(1, h, w).unsqueeze(0).expand(B, -1, -1, -1)
+        shifted = torch.roll(lr_up, shifts=(-dy * s, -dx * s), dims=(2, 3))
+        t = torch.cat([shifted, hr, code], 1)
+        t = F.leaky_relu(F.conv2d(t, w0), 0.01)
+        t = F.leaky_relu(F.conv2d(t, w1), 0.01)
+        t = F.leaky_relu(F.conv2d(t, w2), 0.01)
+        t = F.conv2d(t, w3)
+        valid = torch.ones((1, 1, H, W), device=lr.device, dtype=torch.bool)
+        if dy < 0:
+            valid[:, :, :s] = False
+        if dy > 0:
+            valid[:, :, H - s:] = False
+        if dx < 0:
+            valid[:, :, :, :s] = False
+        if dx > 0:
+            valid[:, :, :, W - s:] = False
+        logits.append(torch.where(valid, t, torch.full_like(t, -100.0)))
+    return F.softmax(torch.cat(logits, 1), dim=1)
+
+
+def _softargmin_ctxmap_torch(c1, c2, c3, weights9, scale):
+    s = scale
+    outs = []
+    cost = None
+    for c in (c1, c2, c3):
+        cost = c if cost is None else c + cost
+        D = cost.shape[1]
+        disp = torch.arange(D, device=cost.device, dtype=cost.dtype).view(1, D, 1, 1)
+        p = (F.softmax(cost, 1) * disp).sum(1)
+        up = s * p.repeat_interleave(s, 1).repeat_interleave(s, 2)
+        H, W = up.shape[1:]
+        out = up * weights9[:, 0]
+        for k in range(1, 9):
+            dy, dx = _NEIGHBOURS[k]
+            y0, y1 = max(0, -dy) * s, H - max(0, dy) * s
+            x0, x1 = max(0, -dx) * s, W - max(0, dx) * s
+            pad = torch.zeros_like(up)
+            pad[:, y0:y1, x0:x1] = up[:, y0 + dy * s:y1 + dy * s, x0 + dx * s:x1 + dx * s]
+            out = out + pad * weights9[:, k]
+        outs.append(out.unsqueeze(1))
+    return tuple(outs)
+
+
+class _CtxmapWeights(Function):
+    @staticmethod
+    def forward(ctx, lr, hr, w0, w1, w2, w3):
+        ctx.save_for_backward(lr, hr, w0, w1, w2, w3)
+        return ops.ctxmap_weights(lr.contiguous(), hr.contiguous(), w0, w1, w2, w3)
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = [t.detach().requires_grad_(True) for t in ctx.saved_tensors]
+        with torch.enable_grad():
+            out = _ctxmap_weights_torch(*saved)
+        return torch.autograd.grad(out, saved, g, allow_unused=True)
+
+
+def ctxmap_weights(lr, hr, w0, w1, w2, w3):
+    return _CtxmapWeights.apply(lr, hr, w0, w1, w2, w3)
+
+
+class _SoftargminCtxmap(Function):
+    @staticmethod
+    def forward(ctx, c1, c2, c3, weights9, scale):
+        ctx.scale = scale
+        ctx.save_for_backward(c1, c2, c3, weights9)
+        return ops.softargmin_ctxmap(c1.contiguous(), c2.contiguous(), c3.contiguous(), weights9.contiguous(), scale)
+
+    @staticmethod
+    def backward(ctx, g1, g2, g3):
+        saved = [t.detach().requires_grad_(True) for t in ctx.saved_tensors]
+        with torch.enable_grad():
+            outs = _softargmin_ctxmap_torch(*saved, ctx.scale)
+        grads = torch.autograd.grad(outs, saved, (g1, g2, g3), allow_unused=True)
+        return grads + (None,)
+
+
+def softargmin_ctxmap(c1, c2, c3, weights9, scale):
+    return _SoftargminCtxmap.apply(c1, c2, c3, weights9, scale)

@@ -1,0 +1,165 @@
+"""Torch-facing wrappers of the libcmfb200 kernels (device memory, streams: PyTorch; compute: ours).
+
+Every function takes/returns CUDA fp32 tensors, enqueues on the current stream of the tensor's device and
+never synchronises.  Nothing here has a CPU or eager-PyTorch fallback: a CPU tensor or a missing
+library raises.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _lib
+
+GN_GROUPS = 32  # group_norm_group_num, cmf/models/cmfsm.py:33
+GN_EPS = 1e-5
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.CmfB200Error("cmf_b200 kernels need CUDA tensors (no CPU fallback); got device %s" % t.device)
+        if t.dtype != torch.float32:
+            raise _lib.CmfB200Error("cmf_b200 fp32 kernels got dtype %s" % t.dtype)
+        if not t.is_contiguous():
+            raise _lib.CmfB200Error("cmf_b200 kernels need contiguous tensors")
+
+
+# ------------------------------------------------------------------------------------------ K1
+def cost_volume_concat(L, R, D):
+    """[B,C,h,w] x2 -> [B,2C,D,h,w]; cmf/models/cmfsm.py:667-682."""
+    _req(L, R)
+    if L.shape != R.shape:
+        raise ValueError("left/right feature shapes differ: %s vs %s" % (tuple(L.shape), tuple(R.shape)))
+    B, C, h, w = L.shape
+    cost = torch.empty((B, 2 * C, D, h, w), device=L.device, dtype=torch.float32)
+    with torch.cuda.device(L.device):
+        _lib.check(_lib.load().cmfb200_cost_volume_concat_fwd(_p(L), _p(R), _p(cost), B, C, h, w, D, _stream()),
+                   "cost_volume_concat_fwd")
+    return cost
+
+
+def cost_volume_concat_bwd(g, C):
+    _req(g)
+    B, C2, D, h, w = g.shape
+    dL = torch.empty((B, C, h, w), device=g.device, dtype=torch.float32)
+    dR = torch.empty_like(dL)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.load().cmfb200_cost_volume_concat_bwd(_p(g), _p(dL), _p(dR), B, C, h, w, D, _stream()),
+                   "cost_volume_concat_bwd")
+    return dL, dR
+
+
+# ------------------------------------------------------------------------------------------ K2 / K3
+def pack_conv3d_weight(weight, transposed=False):
+    """nn.Conv3d [Cout,Cin,3,3,3] (or nn.ConvTranspose3d [Cin,Cout,3,3,3]) -> packed [Cin,27,Cout]."""
+    weight = weight.detach()
+    _req(weight)
+    if transposed:
+        Cin, Cout = weight.shape[:2]
+    else:
+        Cout, Cin = weight.shape[:2]
+    if tuple(weight.shape[2:]) != (3, 3, 3):
+        raise ValueError("expected a 3x3x3 kernel, got %s" % (tuple(weight.shape),))
+    packed = torch.empty((Cin, 27, Cout), device=weight.device, dtype=torch.float32)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.load().cmfb200_pack_conv3d_weight(_p(weight), _p(packed), Cout, Cin, int(transposed), _stream()),
+                   "pack_conv3d_weight")
+    return packed
+
+
+def conv3d_k3(x, packed, stride=1, transposed=False, want_stats=False):
+    """3x3x3 conv (pad 1) or transposed conv (s2,p1,op1).  Returns (y, gn_sums or None)."""
+    _req(x, packed)
+    B, Cin, D, H, W = x.shape
+    if packed.shape[0] != Cin:
+        raise ValueError("weight Cin %d != input channels %d" % (packed.shape[0], Cin))
+    Cout = packed.shape[2]
+    sums = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    L = _lib.load()
+    with torch.cuda.device(x.device):
+        if transposed:
+            y = torch.empty((B, Cout, 2 * D, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
+            _lib.check(L.cmfb200_deconv3d_k3s2_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W, _stream()),
+                       "deconv3d_k3s2_fwd")
+        else:
+            Do, Ho, Wo = (D - 1) // stride + 1, (H - 1) // stride + 1, (W - 1) // stride + 1
+            y = torch.empty((B, Cout, Do, Ho, Wo), device=x.device, dtype=torch.float32)
+            _lib.check(L.cmfb200_conv3d_k3_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W, stride,
+                                               _stream()), "conv3d_k3_fwd")
+    return y, sums
+
+
+def gn_stats(x):
+    _req(x)
+    B, C = x.shape[:2]
+    spatial = x[0, 0].numel()
+    sums = torch.zeros((B, C, 2), device=x.device, dtype=torch.float64)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().cmfb200_gn_stats(_p(x), _p(sums), B, C, spatial, _stream()), "gn_stats")
+    return sums
+
+
+def gn_apply(x, sums, gamma, beta, residual=None, relu=False, out=None, groups=GN_GROUPS, eps=GN_EPS):
+    """y = GroupNorm(x) (+residual) (ReLU).  `out` may be x itself (in place)."""
+    gamma, beta = gamma.detach(), beta.detach()
+    _req(x, gamma, beta, residual)
+    B, C = x.shape[:2]
+    spatial = x[0, 0].numel()
+    if residual is not None and residual.shape != x.shape:
+        raise ValueError("residual shape %s != %s" % (tuple(residual.shape), tuple(x.shape)))
+    y = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().cmfb200_gn_apply(_p(x), _p(sums), _p(gamma), _p(beta), _p(residual), _p(y), B, C, groups,
+                                                spatial, eps, int(relu), _stream()), "gn_apply")
+    return y
+
+
+def conv3d_gn(x, packed, gamma, beta, stride=1, transposed=False, residual=None, relu=False):
+    """convbn_3d (+residual) (+ReLU): conv with fused statistics, then one normalise pass in place."""
+    y, sums = conv3d_k3(x, packed, stride, transposed, want_stats=True)
+    return gn_apply(y, sums, gamma, beta, residual, relu, out=y)
+
+
+# ------------------------------------------------------------------------------------------ K5 / K4
+def ctxmap_weights(lr, hr, w0, w1, w2, w3):
+    """eight_related_context_mapping: [B,32,h,w],[B,32,H,W] -> [B,9,H,W] (cmf/models/cmfsm.py:443-593)."""
+    ws = [w.detach().reshape(w.shape[0], w.shape[1]).contiguous() for w in (w0, w1, w2, w3)]
+    _req(lr, hr, *ws)
+    B, C, h, w = lr.shape
+    H, W = hr.shape[2:]
+    if C != 32 or hr.shape[1] != 32 or tuple(ws[0].shape) != (32, 66):
+        raise ValueError("context mapping expects 32-channel features and a 66-input similarity MLP")
+    scale = W // w
+    if H != h * scale or W != w * scale:
+        raise ValueError("hr %dx%d is not an integer multiple of lr %dx%d" % (H, W, h, w))
+    out = torch.empty((B, 9, H, W), device=lr.device, dtype=torch.float32)
+    with torch.cuda.device(lr.device):
+        _lib.check(_lib.load().cmfb200_ctxmap_weights_fwd(_p(lr), _p(hr), _p(ws[0]), _p(ws[1]), _p(ws[2]), _p(ws[3]),
+                                                          _p(out), B, h, w, scale, _stream()), "ctxmap_weights_fwd")
+    return out
+
+
+def softargmin_ctxmap(c1, c2, c3, weights9, scale, want_lowres=False):
+    """cmf/models/cmfsm.py:703-769.  c_i [B,D,h,w], weights9 [B,9,H,W] -> 3 x [B,1,H,W] (+ [3,B,h,w])."""
+    _req(c1, c2, c3, weights9)
+    B, D, h, w = c1.shape
+    H, W = h * scale, w * scale
+    if tuple(weights9.shape) != (B, 9, H, W):
+        raise ValueError("weights9 shape %s != %s" % (tuple(weights9.shape), (B, 9, H, W)))
+    outs = [torch.empty((B, 1, H, W), device=c1.device, dtype=torch.float32) for _ in range(3)]
+    low = torch.empty((3, B, h, w), device=c1.device, dtype=torch.float32) if want_lowres else None
+    with torch.cuda.device(c1.device):
+        _lib.check(_lib.load().cmfb200_softargmin_ctxmap_fwd(_p(c1), _p(c2), _p(c3), _p(weights9), _p(outs[0]),
+                                                             _p(outs[1]), _p(outs[2]), _p(low), B, D, h, w, scale,
+                                                             _stream()), "softargmin_ctxmap_fwd")
+    return (tuple(outs), low) if want_lowres else tuple(outs)

@@ -1,0 +1,426 @@
+// K2 (fp32 parity path) -- 3x3x3 convolutions / transposed convolutions of the aggregation network on the
+// CUDA cores with exact fp32 FMA accumulation, NCDHW.  Replaces nn.Conv3d / nn.ConvTranspose3d inside
+// convbn_3d, hourglass and classif (cmf/models/cmfsm.py:49-58, 240-303, 604-634).  This is the mode the
+// fp32 parity gate runs in (the reference's fp32 result moves by 2e-3 px between thread counts, SURVEY.md
+// section 0.7, so tensor-core operand rounding is not an option here); the bf16 tcgen05 implicit GEMM in
+// conv3d_igemm.cu is the throughput mode.
+//
+// Register-tiled direct convolution: a CTA owns a TD x TH x 32 block of output voxels and ALL output
+// channels; per chunk of CC input channels the halo'd input patch and the [CC][27][COUT] weight slice
+// are staged in shared memory; a thread owns CPT output channels x 4 consecutive-w voxels (32 fp32
+// accumulators for CPT=8).  Per (ci,kd,kh) it issues 2 vector loads of input + 6 broadcast loads of weights
+// for 96 FMAs, i.e. the inner loop is FMA-issue bound, not shared-memory bound.
+// GroupNorm statistics (sum, sum of squares per (b,channel)) are reduced in the epilogue.
+#include "common.cuh"
+
+namespace cmfb200 {
+
+constexpr int kConvThreads = 256;
+constexpr int kTW = 32;  // output voxels along w per CTA
+constexpr int kVPT = 4;  // consecutive-w output voxels per thread
+
+template <int COUT, int CPT>
+struct ConvTile {
+    static constexpr int NCG = COUT / CPT;               // channel groups
+    static constexpr int NQ = kConvThreads / NCG;        // voxel quads per CTA
+    static constexpr int ROWS = NQ / (kTW / kVPT);       // (d,h) rows of 32 voxels
+    static constexpr int TD = (COUT == 1) ? 4 : 1;
+    static constexpr int TH = ROWS / TD;
+    static_assert(NCG * NQ == kConvThreads && TD * TH * (kTW / kVPT) == NQ, "bad tile");
+};
+
+// epilogue helper: block-level reduction of per-thread channel sums into gn_sums[b][co][2] (double atomics)
+template <int COUT, int CPT>
+__device__ __forceinline__ void gn_epilogue(const float (&s)[CPT], const float (&ss)[CPT], int cg, float* sred,
+                                            double* __restrict__ gn_sums, int b) {
+    using T = ConvTile<COUT, CPT>;
+    constexpr int WPG = T::NQ / 32;  // warps per channel group
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();  // sred aliases the operand buffers: everyone must be done with them
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const float a = warp_sum(s[c]), q = warp_sum(ss[c]);
+        if (lane == 0) {
+            sred[(warp * CPT + c) * 2 + 0] = a;
+            sred[(warp * CPT + c) * 2 + 1] = q;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < COUT * 2) {
+        const int co = threadIdx.x >> 1, which = threadIdx.x & 1;
+        const int g = co / CPT, c = co % CPT;
+        double acc = 0.0;
+        for (int wgi = 0; wgi < WPG; ++wgi) acc += (double)sred[((g * WPG + wgi) * CPT + c) * 2 + which];
+        atomicAdd(gn_sums + ((size_t)b * COUT + co) * 2 + which, acc);
+    }
+    (void)cg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward convolution, stride S in {1,2}
+// ------------------------------------------------------------------------------------------------
+template <int COUT, int CPT, int S, int CC>
+__global__ void __launch_bounds__(kConvThreads, (COUT == 64 && S == 2) ? 1 : 2)
+    conv3d_k3_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
+                     double* __restrict__ gn_sums, int Cin, int D, int H, int W, int Do, int Ho, int Wo, int tiles_w) {
+    using T = ConvTile<COUT, CPT>;
+    constexpr int PD = (T::TD - 1) * S + 3, PH = (T::TH - 1) * S + 3, PW = (kTW - 1) * S + 3;
+    constexpr int PWP = (PW + 3) & ~3;
+    constexpr int PATCH = PD * PH * PWP;  // floats per input channel
+    constexpr int WSL = 27 * COUT;        // weight floats per input channel
+    constexpr int NI = (kVPT - 1) * S + 3;
+
+    extern __shared__ __align__(16) float smem[];
+    float* sIn = smem;               // [CC][PD][PH][PWP]
+    float* sW = smem + CC * PATCH;   // [CC][27][COUT]
+
+    const int tile_x = blockIdx.x % tiles_w, tile_y = blockIdx.x / tiles_w;
+    const int w0 = tile_x * kTW, h0 = tile_y * T::TH, d0 = blockIdx.y * T::TD;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int cg = tid / T::NQ;
+    const int q = tid % T::NQ;
+    const int qx = q % (kTW / kVPT);
+    const int row = q / (kTW / kVPT);
+    const int th = row % T::TH, td = row / T::TH;
+
+    float acc[CPT][kVPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+#pragma unroll
+        for (int v = 0; v < kVPT; ++v) acc[c][v] = 0.f;
+
+    const size_t in_plane = (size_t)H * W;
+    const size_t in_vol = (size_t)D * in_plane;
+    const float* xb = x + (size_t)b * Cin * in_vol;
+    const int di0 = d0 * S - 1, hi0 = h0 * S - 1, wi0 = w0 * S - 1;
+
+    for (int c0 = 0; c0 < Cin; c0 += CC) {
+        __syncthreads();  // previous chunk fully consumed
+        // ---- stage input patch (zero padded)
+        for (int i = tid; i < CC * PD * PH * PW; i += kConvThreads) {
+            const int pw = i % PW;
+            int r = i / PW;
+            const int ph = r % PH;
+            r /= PH;
+            const int pd = r % PD, ci = r / PD;
+            const int di = di0 + pd, hi = hi0 + ph, wi = wi0 + pw;
+            float v = 0.f;
+            if ((unsigned)di < (unsigned)D && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W)
+                v = __ldg(xb + (size_t)(c0 + ci) * in_vol + (size_t)di * in_plane + (size_t)hi * W + wi);
+            sIn[((ci * PD + pd) * PH + ph) * PWP + pw] = v;
+        }
+        // ---- stage weights: contiguous [CC][27][COUT] slice
+        {
+            const float* wsrc = wp + (size_t)c0 * WSL;
+            if constexpr ((WSL * CC) % 4 == 0) {
+                for (int i = tid * 4; i < CC * WSL; i += kConvThreads * 4)
+                    *reinterpret_cast<float4*>(sW + i) = __ldg(reinterpret_cast<const float4*>(wsrc + i));
+            } else {
+                for (int i = tid; i < CC * WSL; i += kConvThreads) sW[i] = __ldg(wsrc + i);
+            }
+        }
+        __syncthreads();
+        // ---- FMA loop
+#pragma unroll 1
+        for (int ci = 0; ci < CC; ++ci) {
+            const float* pin = sIn + ci * PATCH + (td * S * PH + th * S) * PWP + qx * kVPT * S;
+            const float* pw_ = sW + ci * WSL + cg * CPT;
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const float* prow = pin + (kd * PH + kh) * PWP;
+                    float in[NI];
+                    if constexpr (S == 1) {
+                        const float4 a = *reinterpret_cast<const float4*>(prow);
+                        const float2 c2 = *reinterpret_cast<const float2*>(prow + 4);
+                        in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w; in[4] = c2.x; in[5] = c2.y;
+                    } else {
+                        const float4 a = *reinterpret_cast<const float4*>(prow);
+                        const float4 c4 = *reinterpret_cast<const float4*>(prow + 4);
+                        in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w;
+                        in[4] = c4.x; in[5] = c4.y; in[6] = c4.z; in[7] = c4.w;
+                        in[8] = prow[8];
+                    }
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float* wt = pw_ + ((kd * 3 + kh) * 3 + kw) * COUT;
+                        float wv[CPT];
+                        if constexpr (CPT == 8) {
+                            const float4 w0v = *reinterpret_cast<const float4*>(wt);
+                            const float4 w1v = *reinterpret_cast<const float4*>(wt + 4);
+                            wv[0] = w0v.x; wv[1] = w0v.y; wv[2] = w0v.z; wv[3] = w0v.w;
+                            wv[4] = w1v.x; wv[5] = w1v.y; wv[6] = w1v.z; wv[7] = w1v.w;
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < CPT; ++c) wv[c] = wt[c];
+                        }
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c)
+#pragma unroll
+                            for (int v = 0; v < kVPT; ++v) acc[c][v] = fmaf(wv[c], in[v * S + kw], acc[c][v]);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: store + GroupNorm partial sums
+    const int od = d0 + td, oh = h0 + th, ow = w0 + qx * kVPT;
+    const bool row_ok = (od < Do) && (oh < Ho);
+    const size_t out_plane = (size_t)Ho * Wo;
+    float s[CPT], ss[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        s[c] = 0.f;
+        ss[c] = 0.f;
+    }
+    if (row_ok && ow < Wo) {
+        const bool vec = ((Wo & 3) == 0);  // then ow+3 < Wo and the address is 16-byte aligned
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int co = cg * CPT + c;
+            float* py = y + (((size_t)b * COUT + co) * Do + od) * out_plane + (size_t)oh * Wo + ow;
+            if (vec) {
+                *reinterpret_cast<float4*>(py) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+#pragma unroll
+                for (int v = 0; v < kVPT; ++v) {
+                    s[c] += acc[c][v];
+                    ss[c] = fmaf(acc[c][v], acc[c][v], ss[c]);
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < kVPT; ++v)
+                    if (ow + v < Wo) {
+                        py[v] = acc[c][v];
+                        s[c] += acc[c][v];
+                        ss[c] = fmaf(acc[c][v], acc[c][v], ss[c]);
+                    }
+            }
+        }
+    }
+    if (gn_sums != nullptr) gn_epilogue<COUT, CPT>(s, ss, cg, smem, gn_sums, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// transposed convolution k3 s2 p1 op1 (output = 2x input).  od = 2*id - 1 + kd.
+// A CTA owns one (pd,ph) output-parity class of a TH x 32 block of INPUT positions at one input depth:
+// outputs (od,oh) = (2*id+pd, 2*ih+ph), ow = 2*iw .. 2*iw+1.  Along each of d,h: parity 0 uses tap k=1 of
+// input i; parity 1 uses tap k=2 of input i and tap k=0 of input i+1.  A thread owns CPT channels x 8
+// consecutive output columns (4 input columns).
+// ------------------------------------------------------------------------------------------------
+template <int COUT, int CPT, int CC>
+__global__ void __launch_bounds__(kConvThreads, 1)
+    deconv3d_k3s2_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
+                         double* __restrict__ gn_sums, int Cin, int D, int H, int W, int tiles_w) {
+    using T = ConvTile<COUT, CPT>;
+    static_assert(T::TD == 1, "deconv tile is one depth slice");
+    constexpr int PD = 2, PH = T::TH + 1, PW = kTW + 1;
+    constexpr int PWP = (PW + 3) & ~3;  // 36
+    constexpr int PATCH = PD * PH * PWP;
+    constexpr int WSL = 27 * COUT;
+    constexpr int NO = 2 * kVPT;  // output columns per thread
+
+    extern __shared__ __align__(16) float smem[];
+    float* sIn = smem;
+    float* sW = smem + CC * PATCH;
+
+    const int tile_x = blockIdx.x % tiles_w, tile_y = blockIdx.x / tiles_w;
+    const int iw0 = tile_x * kTW, ih0 = tile_y * T::TH;
+    const int id = blockIdx.y >> 2;
+    const int pd = (blockIdx.y >> 1) & 1, ph = blockIdx.y & 1;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int cg = tid / T::NQ;
+    const int q = tid % T::NQ;
+    const int qx = q % (kTW / kVPT);
+    const int th = q / (kTW / kVPT);
+
+    float acc[CPT][NO];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+#pragma unroll
+        for (int v = 0; v < NO; ++v) acc[c][v] = 0.f;
+
+    const size_t in_plane = (size_t)H * W;
+    const size_t in_vol = (size_t)D * in_plane;
+    const float* xb = x + (size_t)b * Cin * in_vol;
+    const int nd = pd ? 2 : 1, nh = ph ? 2 : 1;
+
+    for (int c0 = 0; c0 < Cin; c0 += CC) {
+        __syncthreads();
+        for (int i = tid; i < CC * PD * PH * PW; i += kConvThreads) {
+            const int pw = i % PW;
+            int r = i / PW;
+            const int phh = r % PH;
+            r /= PH;
+            const int pdd = r % PD, ci = r / PD;
+            const int di = id + pdd, hi = ih0 + phh, wi = iw0 + pw;
+            float v = 0.f;
+            if (di < D && hi < H && wi < W)
+                v = __ldg(xb + (size_t)(c0 + ci) * in_vol + (size_t)di * in_plane + (size_t)hi * W + wi);
+            sIn[((ci * PD + pdd) * PH + phh) * PWP + pw] = v;
+        }
+        {
+            const float* wsrc = wp + (size_t)c0 * WSL;
+            for (int i = tid * 4; i < CC * WSL; i += kConvThreads * 4)
+                *reinterpret_cast<float4*>(sW + i) = __ldg(reinterpret_cast<const float4*>(wsrc + i));
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int ci = 0; ci < CC; ++ci) {
+            const float* pin = sIn + ci * PATCH + th * PWP + qx * kVPT;
+            const float* pw_ = sW + ci * WSL + cg * CPT;
+#pragma unroll 1
+            for (int jd = 0; jd < nd; ++jd) {
+                // parity 0: (k=1, +0) ; parity 1: jd=0 -> (k=2, +0), jd=1 -> (k=0, +1)
+                const int kd = pd ? (jd == 0 ? 2 : 0) : 1;
+#pragma unroll 1
+                for (int jh = 0; jh < nh; ++jh) {
+                    const int kh = ph ? (jh == 0 ? 2 : 0) : 1;
+                    const float* prow = pin + (jd * PH + jh) * PWP;
+                    const float4 a = *reinterpret_cast<const float4*>(prow);
+                    const float in[5] = {a.x, a.y, a.z, a.w, prow[4]};
+                    const float* wt = pw_ + (kd * 3 + kh) * 3 * COUT;
+                    float wk[3][CPT];
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float4 w0v = *reinterpret_cast<const float4*>(wt + kw * COUT);
+                        const float4 w1v = *reinterpret_cast<const float4*>(wt + kw * COUT + 4);
+                        wk[kw][0] = w0v.x; wk[kw][1] = w0v.y; wk[kw][2] = w0v.z; wk[kw][3] = w0v.w;
+                        wk[kw][4] = w1v.x; wk[kw][5] = w1v.y; wk[kw][6] = w1v.z; wk[kw][7] = w1v.w;
+                    }
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c)
+#pragma unroll
+                        for (int v = 0; v < kVPT; ++v) {
+                            // even column 2*(i+v): tap kw=1 of input v ; odd column: kw=2 of v, kw=0 of v+1
+                            acc[c][2 * v] = fmaf(wk[1][c], in[v], acc[c][2 * v]);
+                            acc[c][2 * v + 1] = fmaf(wk[2][c], in[v], acc[c][2 * v + 1]);
+                            acc[c][2 * v + 1] = fmaf(wk[0][c], in[v + 1], acc[c][2 * v + 1]);
+                        }
+                }
+            }
+        }
+    }
+
+    const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+    const int od = 2 * id + pd, oh = 2 * (ih0 + th) + ph, ow = 2 * (iw0 + qx * kVPT);
+    const size_t out_plane = (size_t)Ho * Wo;
+    float s[CPT], ss[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        s[c] = 0.f;
+        ss[c] = 0.f;
+    }
+    if (oh < Ho && ow < Wo) {
+        const bool vec = ((Wo & 3) == 0) && (ow + NO <= Wo);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int co = cg * CPT + c;
+            float* py = y + (((size_t)b * COUT + co) * Do + od) * out_plane + (size_t)oh * Wo + ow;
+            if (vec) {
+                *reinterpret_cast<float4*>(py) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                *reinterpret_cast<float4*>(py + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+            }
+#pragma unroll
+            for (int v = 0; v < NO; ++v)
+                if (ow + v < Wo) {
+                    if (!vec) py[v] = acc[c][v];
+                    s[c] += acc[c][v];
+                    ss[c] = fmaf(acc[c][v], acc[c][v], ss[c]);
+                }
+        }
+    }
+    if (gn_sums != nullptr) gn_epilogue<COUT, CPT>(s, ss, cg, smem, gn_sums, b);
+}
+
+// weight packing: conv [Cout][Cin][27] -> [Cin][27][Cout];  deconv [Cin][Cout][27] -> [Cin][27][Cout]
+__global__ void pack_conv3d_weight_kernel(const float* __restrict__ w, float* __restrict__ p, int Cout, int Cin,
+                                          int transposed) {
+    const int n = Cout * Cin * 27;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int co = i % Cout;
+        const int t = (i / Cout) % 27;
+        const int ci = i / (Cout * 27);
+        const size_t src = transposed ? ((size_t)ci * Cout + co) * 27 + t : ((size_t)co * Cin + ci) * 27 + t;
+        p[i] = w[src];
+    }
+}
+
+template <int COUT, int CPT, int S, int CC>
+static int launch_conv(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
+                       cudaStream_t st) {
+    using T = ConvTile<COUT, CPT>;
+    constexpr int PD = (T::TD - 1) * S + 3, PH = (T::TH - 1) * S + 3, PW = (kTW - 1) * S + 3;
+    constexpr int PWP = (PW + 3) & ~3;
+    constexpr size_t smem = (size_t)CC * (PD * PH * PWP + 27 * COUT) * sizeof(float);
+    static_assert(smem <= 220 * 1024, "tile does not fit");
+    const int Do = (D - 1) / S + 1, Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+    const int tiles_w = (int)cdiv(Wo, kTW), tiles_h = (int)cdiv(Ho, T::TH);
+    auto kern = conv3d_k3_kernel<COUT, CPT, S, CC>;
+    CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)cdiv(Do, T::TD), (unsigned)B);
+    CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d: grid too large");
+    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, D, H, W, Do, Ho, Wo, tiles_w);
+    CMF_LAUNCH_CHECK("conv3d_k3_kernel");
+    return CMFB200_OK;
+}
+
+template <int COUT, int CPT, int CC>
+static int launch_deconv(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
+                         cudaStream_t st) {
+    using T = ConvTile<COUT, CPT>;
+    constexpr size_t smem = (size_t)CC * (2 * (T::TH + 1) * 36 + 27 * COUT) * sizeof(float);
+    const int tiles_w = (int)cdiv(W, kTW), tiles_h = (int)cdiv(H, T::TH);
+    auto kern = deconv3d_k3s2_kernel<COUT, CPT, CC>;
+    CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(D * 4), (unsigned)B);
+    CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "deconv3d: grid too large");
+    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, D, H, W, tiles_w);
+    CMF_LAUNCH_CHECK("deconv3d_k3s2_kernel");
+    return CMFB200_OK;
+}
+
+}  // namespace cmfb200
+
+using namespace cmfb200;
+
+extern "C" int cmfb200_pack_conv3d_weight(const float* weight, float* packed, int Cout, int Cin, int transposed,
+                                          void* stream) {
+    CMF_REQUIRE(weight && packed, "pack_conv3d_weight: null pointer");
+    CMF_REQUIRE(Cout > 0 && Cin > 0, "pack_conv3d_weight: non-positive dimension");
+    const int n = Cout * Cin * 27;
+    pack_conv3d_weight_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(weight, packed, Cout, Cin,
+                                                                                          transposed);
+    CMF_LAUNCH_CHECK("pack_conv3d_weight_kernel");
+    return CMFB200_OK;
+}
+
+extern "C" int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B, int Cin,
+                                     int Cout, int D, int H, int W, int stride, void* stream) {
+    CMF_REQUIRE(x && packed_w && y, "conv3d_k3_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && Cin > 0 && D > 0 && H > 0 && W > 0, "conv3d_k3_fwd: non-positive dimension");
+    CMF_REQUIRE(Cin % 8 == 0, "conv3d_k3_fwd: Cin=%d must be a multiple of 8", Cin);
+    CMF_REQUIRE(stride == 1 || stride == 2, "conv3d_k3_fwd: stride=%d not in {1,2}", stride);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cout == 32 && stride == 1) return launch_conv<32, 8, 1, 8>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 64 && stride == 1) return launch_conv<64, 8, 1, 8>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 64 && stride == 2) return launch_conv<64, 8, 2, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 1 && stride == 1) return launch_conv<1, 1, 1, 8>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    CMF_REQUIRE(false, "conv3d_k3_fwd: unsupported (Cout=%d, stride=%d); Cout in {1,32,64}", Cout, stride);
+}
+
+extern "C" int cmfb200_deconv3d_k3s2_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B,
+                                         int Cin, int Cout, int D, int H, int W, void* stream) {
+    CMF_REQUIRE(x && packed_w && y, "deconv3d_k3s2_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && Cin > 0 && D > 0 && H > 0 && W > 0, "deconv3d_k3s2_fwd: non-positive dimension");
+    CMF_REQUIRE(Cin % 8 == 0, "deconv3d_k3s2_fwd: Cin=%d must be a multiple of 8", Cin);
+    CMF_REQUIRE(D * 4 <= 65535, "deconv3d_k3s2_fwd: depth too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cout == 32) return launch_deconv<32, 8, 8>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 64) return launch_deconv<64, 8, 8>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    CMF_REQUIRE(false, "deconv3d_k3s2_fwd: unsupported Cout=%d (32 or 64)", Cout);
+}

@@ -1,0 +1,107 @@
+/*
+ * cmfb200.h -- C ABI of libcmfb200.so: sm_100a kernels for the `cmfsm` stereo hot path.
+ *
+ * The reference (lidongyv/Explicit-Context-Mapping-for-Stereo-Matching) is pure PyTorch and has no
+ * FFI of its own; each entry point below replaces the block of ATen calls cited next to it
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (plain cudaMalloc / torch allocations), 16-byte aligned;
+ *   - tensors are dense, row-major in the layout named in the comment;
+ *   - the last argument is the CUDA stream (cudaStream_t passed as void*), work is enqueued
+ *     asynchronously: no allocation, no host synchronisation, no global mutable state;
+ *   - return value: 0 = ok, <0 = error; `cmfb200_last_error()` returns a thread-local message.
+ *   - fp32 arithmetic unless the name says otherwise.
+ */
+#ifndef CMFB200_H_
+#define CMFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMFB200_OK 0
+#define CMFB200_ERR_INVALID (-1) /* bad shape / null pointer / unsupported configuration */
+#define CMFB200_ERR_CUDA (-2)    /* a CUDA runtime call failed (message has the cudaError string) */
+
+#define CMFB200_ABI_VERSION 1
+
+/* ABI version of the loaded library (== CMFB200_ABI_VERSION of the header it was built from). */
+int cmfb200_abi_version(void);
+/* Thread-local, NUL-terminated description of the last error returned on this thread. */
+const char* cmfb200_last_error(void);
+/* Number of kernel launches enqueued by this library since load (all threads); bench.py reports it. */
+unsigned long long cmfb200_launch_count(void);
+
+/* ---- K1: concat cost volume ----------------------------------------------------------------
+ * Replaces cmf/models/cmfsm.py:667-682 (CPU zeros + H2D copy + 2*D slice copies).
+ *   cost[b, c,   d, y, x] = L[b,c,y,x]     if x >= d else +0.0
+ *   cost[b, C+c, d, y, x] = R[b,c,y,x-d]   if x >= d else +0.0
+ * L, R: [B,C,h,w] fp32 NCHW.  cost: [B,2C,D,h,w] fp32 NCDHW (every element written). w % 4 == 0. */
+int cmfb200_cost_volume_concat_fwd(const float* L, const float* R, float* cost,
+                                   int B, int C, int h, int w, int D, void* stream);
+/* Adjoint (autograd of the slice copies): dL[b,c,y,x] = sum_{d<=x} g[b,c,d,y,x],
+ * dR[b,c,y,x] = sum_{d, x+d<w} g[b,C+c,d,y,x+d].  g: [B,2C,D,h,w]; dL,dR: [B,C,h,w] (overwritten). */
+int cmfb200_cost_volume_concat_bwd(const float* g, float* dL, float* dR,
+                                   int B, int C, int h, int w, int D, void* stream);
+
+/* ---- K2: 3-D convolutions of the aggregation network ------------------------------------------
+ * Replace nn.Conv3d(k=3,pad=1,bias=False) in convbn_3d (cmfsm.py:49-58; dres0/1 :604-613, hourglass
+ * :244-259, classif :621-634) and nn.ConvTranspose3d(k=3,s=2,p=1,op=1) (hourglass conv5/conv6 :261-281).
+ *
+ * Weights are consumed in the packed layout  wp[Cin][27][Cout]  (tap = kd*9+kh*3+kw):
+ *   conv   : wp[ci][t][co] = weight[co][ci][t]      (nn.Conv3d layout          [Cout,Cin,3,3,3])
+ *   deconv : wp[ci][t][co] = weight[ci][co][t]      (nn.ConvTranspose3d layout [Cin,Cout,3,3,3]) */
+int cmfb200_pack_conv3d_weight(const float* weight, float* packed, int Cout, int Cin,
+                               int transposed, void* stream);
+
+/* x: [B,Cin,D,H,W] NCDHW; y: [B,Cout,Do,Ho,Wo], Xo = (X-1)/stride + 1; stride in {1,2};
+ * Cin % 4 == 0; Cout in {1, 32, 64}.
+ * If gn_sums != NULL it must be a ZEROED [B,Cout,2] double buffer: the kernel accumulates per
+ * (b,channel) sum and sum-of-squares of y into it (GroupNorm statistics fused into the epilogue). */
+int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
+                          int B, int Cin, int Cout, int D, int H, int W, int stride, void* stream);
+/* Transposed conv k3 s2 p1 op1: y: [B,Cout,2D,2H,2W].  Cout in {32,64}; same gn_sums contract. */
+int cmfb200_deconv3d_k3s2_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
+                              int B, int Cin, int Cout, int D, int H, int W, void* stream);
+
+/* ---- K3: GroupNorm (+ residual add) (+ ReLU) ---------------------------------------------------
+ * Replaces nn.GroupNorm(32,C) (cmfsm.py:58,269,280), the residual adds (:288,297,299,685,687,690,693)
+ * and nn.ReLU / F.relu around them.
+ * gn_stats: per-(b,channel) sum / sum of squares of x [B,C,spatial] into a ZEROED [B,C,2] double buffer
+ * (only needed when the producer did not fuse them). */
+int cmfb200_gn_stats(const float* x, double* gn_sums, int B, int C, long long spatial, void* stream);
+/* y = ((x - mean_g) * rstd_g) * gamma[c] + beta[c]  (+ residual)  (then max(.,0) if relu)
+ * mean/rstd per (b, group of C/G consecutive channels) from gn_sums; biased variance, eps inside sqrt.
+ * y may alias x.  residual may be NULL. */
+int cmfb200_gn_apply(const float* x, const double* gn_sums, const float* gamma, const float* beta,
+                     const float* residual, float* y, int B, int C, int G, long long spatial,
+                     float eps, int relu, void* stream);
+
+/* ---- K5: context-mapping weights -----------------------------------------------------------------
+ * Replaces eight_related_context_mapping.forward + similarity_measure1 (cmfsm.py:443-593, 304-358).
+ * lr: [B,32,h,w] (1/scale-res features), hr: [B,32,H,W] (full-res firstconv output), H=h*scale, W=w*scale,
+ * scale in {4} (even).  w0:[32,66] w1:[16,32] w2:[8,16] w3:[1,8] (1x1 conv weights, no bias).
+ * weights9: [B,9,H,W] softmax over the 9 neighbours (order c,l,r,t,b,lt,rt,lb,rb); out-of-image
+ * neighbours take the constant logit -100. */
+int cmfb200_ctxmap_weights_fwd(const float* lr, const float* hr, const float* w0, const float* w1,
+                               const float* w2, const float* w3, float* weights9,
+                               int B, int h, int w, int scale, void* stream);
+
+/* ---- K4: soft-argmin + x scale upsample + 9-neighbour context mapping ---------------------------
+ * Replaces cmfsm.py:703-769 (3x softmax, disparityregression :111-123, ~60 slice kernels).
+ * c1,c2,c3: raw classifier volumes [B,D,h,w]; cost1=c1, cost2=c2+cost1, cost3=c3+cost2.
+ * p_i[b,cy,cx] = sum_d d*softmax_d(cost_i);  out_i[b,0,y,x] = sum_k w_k[b,y,x]*scale*p_i[b,y/s+dy_k,x/s+dx_k]
+ * over in-image neighbours.  weights9: [B,9,H,W]; out1..3: [B,1,H,W]; pred_lr (optional, may be NULL):
+ * [3,B,h,w] receives p_i.  D <= 128. */
+int cmfb200_softargmin_ctxmap_fwd(const float* c1, const float* c2, const float* c3,
+                                  const float* weights9, float* out1, float* out2, float* out3,
+                                  float* pred_lr, int B, int D, int h, int w, int scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMFB200_H_ */
