@@ -14,6 +14,46 @@ GN_GROUPS = 32  # group_norm_group_num, cmf/models/cmfsm.py:33
 GN_EPS = 1e-5
 
 
+# ---- optional per-kernel CUDA-event timing (bench.py / profiling only; off by default) ------------
+_TIMING = None  # None, or a list receiving (kernel name, start event, end event)
+
+
+def enable_event_timing(on=True):
+    """When on, every kernel wrapper records a CUDA event pair on the launching stream."""
+    global _TIMING
+    _TIMING = [] if on else None
+
+
+def drain_event_timing():
+    """Synchronise and return {name: (launches, total ms)}; clears the record."""
+    global _TIMING
+    out = {}
+    if _TIMING:
+        torch.cuda.synchronize()
+        for name, a, b in _TIMING:
+            n, ms = out.get(name, (0, 0.0))
+            out[name] = (n + 1, ms + a.elapsed_time(b))
+        _TIMING = []
+    return out
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if _TIMING is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _TIMING.append((self.name, self.a, b))
+        return False
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -42,7 +82,7 @@ def cost_volume_concat(L, R, D):
         raise ValueError("left/right feature shapes differ: %s vs %s" % (tuple(L.shape), tuple(R.shape)))
     B, C, h, w = L.shape
     cost = torch.empty((B, 2 * C, D, h, w), device=L.device, dtype=torch.float32)
-    with torch.cuda.device(L.device):
+    with torch.cuda.device(L.device), _timed("cost_volume_concat_fwd"):
         _lib.check(_lib.load().cmfb200_cost_volume_concat_fwd(_p(L), _p(R), _p(cost), B, C, h, w, D, _stream()),
                    "cost_volume_concat_fwd")
     return cost
@@ -86,7 +126,7 @@ def conv3d_k3(x, packed, stride=1, transposed=False, want_stats=False):
     Cout = packed.shape[2]
     sums = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
     L = _lib.load()
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("deconv3d_k3s2_fwd" if transposed else "conv3d_k3_fwd"):
         if transposed:
             y = torch.empty((B, Cout, 2 * D, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
             _lib.check(L.cmfb200_deconv3d_k3s2_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W, _stream()),
@@ -118,7 +158,7 @@ def gn_apply(x, sums, gamma, beta, residual=None, relu=False, out=None, groups=G
     if residual is not None and residual.shape != x.shape:
         raise ValueError("residual shape %s != %s" % (tuple(residual.shape), tuple(x.shape)))
     y = torch.empty_like(x) if out is None else out
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("gn_apply"):
         _lib.check(_lib.load().cmfb200_gn_apply(_p(x), _p(sums), _p(gamma), _p(beta), _p(residual), _p(y), B, C, groups,
                                                 spatial, eps, int(relu), _stream()), "gn_apply")
     return y
@@ -143,7 +183,7 @@ def ctxmap_weights(lr, hr, w0, w1, w2, w3):
     if H != h * scale or W != w * scale:
         raise ValueError("hr %dx%d is not an integer multiple of lr %dx%d" % (H, W, h, w))
     out = torch.empty((B, 9, H, W), device=lr.device, dtype=torch.float32)
-    with torch.cuda.device(lr.device):
+    with torch.cuda.device(lr.device), _timed("ctxmap_weights_fwd"):
         _lib.check(_lib.load().cmfb200_ctxmap_weights_fwd(_p(lr), _p(hr), _p(ws[0]), _p(ws[1]), _p(ws[2]), _p(ws[3]),
                                                           _p(out), B, h, w, scale, _stream()), "ctxmap_weights_fwd")
     return out
@@ -158,7 +198,7 @@ def softargmin_ctxmap(c1, c2, c3, weights9, scale, want_lowres=False):
         raise ValueError("weights9 shape %s != %s" % (tuple(weights9.shape), (B, 9, H, W)))
     outs = [torch.empty((B, 1, H, W), device=c1.device, dtype=torch.float32) for _ in range(3)]
     low = torch.empty((3, B, h, w), device=c1.device, dtype=torch.float32) if want_lowres else None
-    with torch.cuda.device(c1.device):
+    with torch.cuda.device(c1.device), _timed("softargmin_ctxmap_fwd"):
         _lib.check(_lib.load().cmfb200_softargmin_ctxmap_fwd(_p(c1), _p(c2), _p(c3), _p(weights9), _p(outs[0]),
                                                              _p(outs[1]), _p(outs[2]), _p(low), B, D, h, w, scale,
                                                              _stream()), "softargmin_ctxmap_fwd")

@@ -1,0 +1,240 @@
+"""GPU parity tests: every libcmfb200 kernel (through the C ABI via cmf_b200.ops) against the CPU oracle
+on the same seeded inputs, against fixtures produced by the real reference, and -- at BASELINE sizes --
+through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cmfsm_oracle as orc
+import golden_common as gc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _npz(golden_dir, name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def _rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _rand(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("B,C,h,w,D", [(1, 32, 64, 128, 48), (2, 32, 7, 20, 12), (1, 4, 3, 8, 12), (1, 32, 5, 36, 1),
+                                       (3, 2, 9, 4, 3)])
+def test_k1_bit_exact_vs_oracle(B, C, h, w, D):
+    from cmf_b200 import ops
+
+    L, R = _rand(B, C, h, w, seed=1), _rand(B, C, h, w, seed=2)
+    want = orc.cost_volume_concat(L, R, D)
+    got = ops.cost_volume_concat(L.to(DEV), R.to(DEV), D).cpu()
+    assert torch.equal(got, want)
+    assert not torch.signbit(got[got == 0]).any()  # +0.0 everywhere in the masked triangle
+
+
+def test_k1_golden_crop_from_reference(golden_dir):
+    from cmf_b200 import ops
+
+    g = _npz(golden_dir, "cmfsm_c1_full.npz")
+    L, R = g["k1_L_crop"].unsqueeze(0), g["k1_R_crop"].unsqueeze(0)
+    got = ops.cost_volume_concat(L.to(DEV).contiguous(), R.to(DEV).contiguous(), 48).cpu()
+    assert torch.equal(got[0], g["k1_cost_crop"])
+
+
+def test_k1_full_size_properties():
+    """BASELINE config 2 (576x960 -> 144x240, D'=48): slice identities of SURVEY.md A.1, checked on device."""
+    from cmf_b200 import ops
+
+    B, C, h, w, D = 1, 32, 144, 240, 48
+    L = torch.randn(B, C, h, w, device=DEV)
+    R = torch.randn(B, C, h, w, device=DEV)
+    cost = ops.cost_volume_concat(L, R, D)
+    assert cost.shape == (B, 2 * C, D, h, w)
+    for d in (0, 1, 7, 47):
+        assert torch.equal(cost[:, :C, d, :, d:], L[..., d:])
+        assert torch.equal(cost[:, C:, d, :, d:], R[..., :w - d])
+        assert int(cost[:, :, d, :, :d].count_nonzero()) == 0
+    # checksum of checksums: every L element appears min(x+1, D) times
+    mult = torch.clamp(torch.arange(w, device=DEV) + 1, max=D).double()
+    assert abs(float(cost[:, :C].double().sum()) - float((L.double() * mult).sum())) < 1e-6 * cost[:, :C].numel()
+
+
+def test_k1_backward_vs_oracle():
+    from cmf_b200 import ops
+
+    g = _rand(2, 8, 6, 5, 16, seed=3)
+    dL, dR = ops.cost_volume_concat_bwd(g.to(DEV), 4)
+    wL, wR = orc.cost_volume_concat_bwd(g, 4)
+    torch.testing.assert_close(dL.cpu(), wL, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(dR.cpu(), wR, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ K2 / K3
+CONV_CASES = [  # B, Cin, Cout, D, H, W, stride
+    (1, 64, 32, 6, 8, 20, 1), (2, 32, 32, 5, 9, 36, 1), (1, 32, 64, 8, 8, 16, 2), (1, 32, 64, 7, 9, 18, 2),
+    (1, 64, 64, 6, 10, 40, 2), (1, 64, 64, 3, 5, 34, 1), (2, 32, 1, 6, 8, 12, 1), (1, 32, 1, 9, 17, 70, 1),
+    (1, 32, 32, 4, 16, 64, 1),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,D,H,W,stride", CONV_CASES)
+def test_conv3d_vs_fp64_oracle(B, Cin, Cout, D, H, W, stride):
+    from cmf_b200 import ops
+
+    x = _rand(B, Cin, D, H, W, seed=10)
+    wgt = _rand(Cout, Cin, 3, 3, 3, seed=11) * (2.0 / (27 * Cin)) ** 0.5
+    want = F.conv3d(x.double(), wgt.double(), None, stride, 1)
+    y, sums = ops.conv3d_k3(x.to(DEV), ops.pack_conv3d_weight(wgt.to(DEV)), stride, want_stats=Cout > 1)
+    assert y.shape == want.shape
+    assert _rel_l2(y, want) < 1e-5  # fp32 FMA accumulation vs fp64 (tolerance: SURVEY.md 8c, K2 fp32 mode)
+    if sums is not None:
+        s = sums.cpu()
+        torch.testing.assert_close(s[..., 0], want.sum((2, 3, 4)), rtol=1e-5, atol=1e-3)
+        torch.testing.assert_close(s[..., 1], (want * want).sum((2, 3, 4)), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,D,H,W", [(1, 64, 64, 3, 4, 6), (1, 64, 32, 4, 5, 34), (2, 64, 32, 2, 8, 32)])
+def test_deconv3d_vs_fp64_oracle(B, Cin, Cout, D, H, W):
+    from cmf_b200 import ops
+
+    x = _rand(B, Cin, D, H, W, seed=12)
+    wgt = _rand(Cin, Cout, 3, 3, 3, seed=13) * 0.05
+    want = F.conv_transpose3d(x.double(), wgt.double(), None, stride=2, padding=1, output_padding=1)
+    y, sums = ops.conv3d_k3(x.to(DEV), ops.pack_conv3d_weight(wgt.to(DEV), transposed=True), transposed=True,
+                            want_stats=True)
+    assert y.shape == want.shape
+    assert _rel_l2(y, want) < 1e-5
+    torch.testing.assert_close(sums.cpu()[..., 0], want.sum((2, 3, 4)), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("C,relu,res", [(32, True, False), (64, True, True), (64, False, True), (32, False, False)])
+def test_groupnorm_apply_vs_oracle(C, relu, res):
+    from cmf_b200 import ops
+
+    x = _rand(2, C, 5, 6, 12, seed=20) * 3 + 0.5
+    gamma, beta = _rand(C, seed=21), _rand(C, seed=22)
+    r = _rand(2, C, 5, 6, 12, seed=23) if res else None
+    want = F.group_norm(x.double(), 32, gamma.double(), beta.double(), 1e-5)
+    if res:
+        want = want + r.double()
+    if relu:
+        want = want.relu()
+    xs = x.to(DEV)
+    got = ops.gn_apply(xs, ops.gn_stats(xs), gamma.to(DEV), beta.to(DEV), r.to(DEV) if res else None, relu)
+    torch.testing.assert_close(got.cpu().double(), want, rtol=1e-5, atol=1e-5)
+
+
+def test_groupnorm_odd_spatial():
+    from cmf_b200 import ops
+
+    x = _rand(1, 32, 3, 5, 7, seed=24)
+    ones, zeros = torch.ones(32), torch.zeros(32)
+    xs = x.to(DEV)
+    got = ops.gn_apply(xs, ops.gn_stats(xs), ones.to(DEV), zeros.to(DEV))
+    torch.testing.assert_close(got.cpu(), F.group_norm(x, 32, ones, zeros, 1e-5), rtol=1e-5, atol=1e-5)
+
+
+def _model_with(sub, weights):
+    from cmf.models import get_model
+
+    model = get_model("cmfsm")
+    getattr(model, sub).load_state_dict(weights)
+    return model.to(DEV).eval()
+
+
+def test_hourglass_golden_from_reference_module(golden_dir):
+    """Product hourglass (conv/deconv + GN + skip + ReLU kernels) vs the reference module's outputs."""
+    from test_oracle_golden import _hourglass_sd
+
+    g = _npz(golden_dir, "cmfsm_modules.npz")
+    model = _model_with("dres2", gc.seeded_weights(_hourglass_sd(), gc.SEED_HG_W, gn_affine=True))
+    x, presqu, postsqu = (t.to(DEV) for t in gc.hourglass_inputs())
+    with torch.no_grad():
+        a = model._hourglass(model.dres2, x, None, None, None)
+        b = model._hourglass(model.dres2, x, presqu, postsqu, None)
+    for got, key in zip(a + b, ("hg_out_a", "hg_pre_a", "hg_post_a", "hg_out_b", "hg_pre_b", "hg_post_b")):
+        assert _rel_l2(got, g[key]) < 2e-5, key
+        torch.testing.assert_close(got.cpu(), g[key], rtol=1e-3, atol=2e-4)
+
+
+def test_head_and_classifier_golden_from_reference_modules(golden_dir):
+    g = _npz(golden_dir, "cmfsm_modules.npz")
+    from cmf.models import get_model
+
+    model = get_model("cmfsm")
+    w = gc.seeded_weights(model.dres0.state_dict(), gc.SEED_HEAD_W, gn_affine=True)
+    model.dres0.load_state_dict(w)
+    w = gc.seeded_weights(model.classif1.state_dict(), gc.SEED_CLS_W, gn_affine=True)
+    model.classif1.load_state_dict(w)
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        t = model._cg(model.dres0[0], gc.head_input().to(DEV), relu=True)
+        head = model._cg(model.dres0[2], t, relu=True)
+        cls = model._classify(model.classif1, gc.classif_input().to(DEV))
+    assert _rel_l2(head, g["head_out"]) < 2e-5
+    assert _rel_l2(cls, g["cls_out"].squeeze(1)) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------ K5 / K4
+def test_k5_golden_from_reference_module(golden_dir):
+    from cmf_b200 import ops
+
+    g = _npz(golden_dir, "cmfsm_modules.npz")
+    proto = {"conv0.weight": torch.empty(32, 66, 1, 1), "conv1.weight": torch.empty(16, 32, 1, 1),
+             "conv2.weight": torch.empty(8, 16, 1, 1), "conv3.weight": torch.empty(1, 8, 1, 1)}
+    w = gc.seeded_weights({"similarity1." + k: v for k, v in proto.items()}, gc.SEED_K5_W)
+    lr, hr = gc.k5_inputs()
+    got = ops.ctxmap_weights(lr.to(DEV), hr.to(DEV), *[w["similarity1.conv%d.weight" % i].to(DEV) for i in range(4)])
+    # first layer is evaluated as lr-part + hr-part + code-part: summation order differs from the
+    # reference's single 66-wide dot product -> tolerance 1e-5 absolute on softmax weights
+    torch.testing.assert_close(got.cpu(), g["k5_weights"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 3, 5), (2, 8, 16), (1, 9, 21)])
+def test_k5_vs_oracle_ragged(B, h, w):
+    from cmf_b200 import ops
+
+    proto = {"mapping_matrix.similarity1.conv0.weight": torch.empty(32, 66, 1, 1),
+             "mapping_matrix.similarity1.conv1.weight": torch.empty(16, 32, 1, 1),
+             "mapping_matrix.similarity1.conv2.weight": torch.empty(8, 16, 1, 1),
+             "mapping_matrix.similarity1.conv3.weight": torch.empty(1, 8, 1, 1)}
+    sd = gc.seeded_weights(proto, 77)
+    lr, hr = _rand(B, 32, h, w, seed=30), _rand(B, 32, 4 * h, 4 * w, seed=31)
+    want = orc.context_mapping_weights(sd, lr, hr)
+    got = ops.ctxmap_weights(lr.to(DEV), hr.to(DEV), *[sd["mapping_matrix.similarity1.conv%d.weight" % i].to(DEV)
+                                                        for i in range(4)])
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+
+
+def test_k4_golden_interior_from_reference(golden_dir):
+    from cmf_b200 import ops
+
+    g = _npz(golden_dir, "cmfsm_c1_full.npz")
+    args = [g[k][None].contiguous().to(DEV) for k in ("k4_c1", "k4_c2", "k4_c3", "k4_w")]
+    outs = ops.softargmin_ctxmap(*args, 4)
+    for i, o in enumerate(outs, 1):
+        torch.testing.assert_close(o[0, 0, 4:-4, 4:-4].cpu(), g["k4_out%d_interior" % i], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,D,h,w", [(1, 48, 8, 16), (2, 48, 11, 19), (1, 24, 3, 5), (1, 96, 17, 33)])
+def test_k4_vs_oracle(B, D, h, w):
+    from cmf_b200 import ops
+
+    c = [_rand(B, D, h, w, seed=40 + i) * 4 for i in range(3)]
+    wts = torch.softmax(_rand(B, 9, 4 * h, 4 * w, seed=44) * 2, 1)
+    want = orc.softargmin_ctxmap(*c, wts, 4)
+    got, low = ops.softargmin_ctxmap(*[t.to(DEV) for t in c], wts.to(DEV), 4, want_lowres=True)
+    for a, b in zip(got, want):
+        torch.testing.assert_close(a.cpu(), b, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(low[2].cpu(), orc.softargmin(c[0] + c[1] + c[2]), rtol=1e-5, atol=1e-4)
+    # outputs are convex combinations of scale*p: bounded by scale*(D-1)
+    assert float(got[2].max()) <= 4 * (D - 1) + 1e-3 and float(got[2].min()) >= -1e-3
