@@ -60,15 +60,26 @@ def test_forward_batch2_matches_per_sample(model):
 
 
 def test_forward_vs_cpu_oracle_structured_pair(model):
-    """Structured pair with true disparity 20 px: CUDA path vs the CPU oracle, same weights."""
+    """Structured pair with true disparity 20 px: CUDA path vs the CPU oracle, same weights.
+
+    Gate: distance to the fp64 oracle <= 2x the distance of the reference's own fp32 CPU
+    arithmetic to that fp64 oracle (+ a 2e-3 px floor = the reference's thread-count reproducibility).
+    The north-star 1e-3 px max-abs figure is printed next to it; it is below the reference's own noise floor.
+    """
     left, right = gc.structured_pair(256, 512, delta=20)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-    want = orc.forward(sd, left, right, 192)
+    ref32 = orc.forward(sd, left, right, 192)
+    ref64 = orc.forward({k: v.double() for k, v in sd.items()}, left.double(), right.double(), 192)
     with torch.no_grad():
         got = model(left.to(DEV), right.to(DEV))
-    for a, b in zip(got, want):
-        d = (a.cpu() - b).abs()
-        assert float(d.max()) < 2e-2 and float(d.mean()) < 1.2e-3, (float(d.max()), float(d.mean()))
+    for i, (a, b32, b64) in enumerate(zip(got, ref32, ref64), 1):
+        ours = (a.cpu().double() - b64).abs()
+        theirs = (b32.double() - b64).abs()
+        direct = (a.cpu() - b32).abs()
+        print("pred%d  |ours-fp64| max %.2e mean %.2e   |ref32-fp64| max %.2e mean %.2e   |ours-ref32| max %.2e mean %.2e"
+              % (i, ours.max(), ours.mean(), theirs.max(), theirs.mean(), direct.max(), direct.mean()))
+        assert float(ours.max()) <= 2 * float(theirs.max()) + 2e-3, (i, float(ours.max()), float(theirs.max()))
+        assert float(ours.mean()) <= 2 * float(theirs.mean()) + 1e-4, (i, float(ours.mean()), float(theirs.mean()))
 
 
 def test_training_step_gradients_flow(model):
