@@ -7,8 +7,9 @@ checkpoints and the reference drivers (train.py, test.py, eval_kitti.py) work un
 
 What differs underneath: cost volume, 3-D aggregation (conv/deconv + GroupNorm + residual + ReLU),
 context-mapping weights and the soft-argmin/upsample/mapping epilogue run as hand-written sm_100a kernels
-from libcmfb200.so (`cmf_b200.ops`); the 2-D feature extractor is still dispatched to cuDNN in strict
-fp32.  Output semantics are per-sample `[B,1,H,W]` (the reference
+from libcmfb200.so (`cmf_b200.ops`), and so do the 2-D feature extractor's convolutions + GroupNorms at
+inference (its four SPP average pools / bilinear upsamples are still ATen calls; under autograd the 2-D
+extractor runs through cuDNN in strict fp32).  Output semantics are per-sample `[B,1,H,W]` (the reference
 broadcasts to `[B,B,H,W]` for B>1).  There is no CPU path: CPU inputs raise.
 """
 import math
@@ -159,7 +160,7 @@ class cmfsm(nn.Module):
                 m.weight.data.normal_(0, math.sqrt(2.0 / n))
         # packed-weight cache: stable per-layer name (survives DataParallel's shallow replicas) + device
         for name, m in self.named_modules():
-            if isinstance(m, (nn.Conv3d, nn.ConvTranspose3d)):
+            if isinstance(m, (nn.Conv2d, nn.Conv3d, nn.ConvTranspose3d)):
                 m._cmf_name = name
         self._packed = {}  # (layer name, device index) -> (version, data_ptr, packed weight)
 
@@ -170,7 +171,10 @@ class cmfsm(nn.Module):
         hit = self._packed.get(key)
         if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
             return hit[2]
-        packed = ops.pack_conv3d_weight(w, transposed=isinstance(conv, nn.ConvTranspose3d))
+        if isinstance(conv, nn.Conv2d):
+            packed = ops.pack_conv2d_weight(w)
+        else:
+            packed = ops.pack_conv3d_weight(w, transposed=isinstance(conv, nn.ConvTranspose3d))
         self._packed[key] = (w._version, w.data_ptr(), packed)
         return packed
 
@@ -181,6 +185,45 @@ class cmfsm(nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
             return aops.conv3d_gn(x, conv.weight, gn.weight, gn.bias, stride, transposed, residual, relu)
         return ops.conv3d_gn(x, self._pack(conv), gn.weight, gn.bias, stride, transposed, residual, relu)
+
+    # ---- 2-D feature extractor on our fp32 kernels (inference); reference feature_extraction.forward :199-236
+    def _c2(self, conv, x, want_stats):
+        return ops.conv2d(x, self._pack(conv), conv.kernel_size[0], conv.stride[0], conv.dilation[0], want_stats)
+
+    def _cg2(self, block, x, residual=None, relu=False):
+        y, sums = self._c2(block[0], x, True)
+        return ops.gn_apply(y, sums, block[1].weight, block[1].bias, residual, relu, out=y)
+
+    def _features(self, x):
+        fe = self.feature_extraction
+        o = self._cg2(fe.firstconv[0], x, relu=True)
+        o = self._cg2(fe.firstconv[2], o, relu=True)
+        o = self._cg2(fe.firstconv[4], o, relu=True)
+        full, _ = self._c2(fe.firstconv[6], o, False)
+        gn0 = fe.secondconv[0]
+        o = ops.gn_apply(full, ops.gn_stats(full), gn0.weight, gn0.bias, None, True)  # out of place: `full` is kept
+        o = self._cg2(fe.secondconv[2], o, relu=True)
+        o = self._cg2(fe.secondconv[4], o, relu=True)
+        raw = None
+        for name in ("layer1", "layer2", "layer3", "layer4"):
+            for unit in getattr(fe, name):
+                t = self._cg2(unit.conv1[0], o, relu=True)
+                skip = o if unit.downsample is None else self._cg2(unit.downsample, o)
+                o = self._cg2(unit.conv2, t, residual=skip)
+            if name == "layer2":
+                raw = o
+        skip = o
+        size = skip.shape[2:]
+        pyramid = []
+        for i in (4, 3, 2, 1):
+            branch = getattr(fe, "branch%d" % i)
+            pooled = branch[0](skip)  # AvgPool2d: tiny; TODO own kernel together with the bilinear upsample
+            pyramid.append(F.interpolate(self._cg2(branch[1], pooled.contiguous(), relu=True), size, mode="bilinear",
+                                         align_corners=False))
+        cat = torch.cat([raw, skip] + pyramid, 1)
+        o = self._cg2(fe.lastconv[0], cat, relu=True)
+        feat, _ = self._c2(fe.lastconv[2], o, False)
+        return feat, full
 
     def _hourglass(self, hg, x, presqu, postsqu, out_residual):
         # reference hourglass.forward, cmfsm.py:283-303 (+ the caller's `out + cost0`, :687,690,693)
@@ -219,9 +262,14 @@ class cmfsm(nn.Module):
         self._check(left, right, self.maxdisp)
         B = left.shape[0]
         left, right = left.float(), right.float()
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            feat, _half, full = self.feature_extraction(torch.cat([left, right], 0))
-        feat = feat.contiguous()
+        both = torch.cat([left, right], 0)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.feature_extraction.parameters()):
+            # training: autograd through the cuDNN modules (strict fp32); our kernels are forward-only here
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                feat, _half, full = self.feature_extraction(both)
+            feat = feat.contiguous()
+        else:
+            feat, full = self._features(both.contiguous())
         lfeat, rfeat = feat[:B], feat[B:]
         hr = full[:B].contiguous()
         scale = hr.shape[-1] // lfeat.shape[-1]

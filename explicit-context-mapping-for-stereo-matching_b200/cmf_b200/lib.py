@@ -27,6 +27,8 @@ SIGNATURES = {
     "cmfb200_pack_conv3d_weight": [_P, _P, _I, _I, _I, _P],
     "cmfb200_conv3d_k3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_deconv3d_k3s2_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "cmfb200_pack_conv2d_weight": [_P, _P, _I, _I, _I, _P],
+    "cmfb200_conv2d_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_gn_stats": [_P, _P, _I, _I, _LL, _P],
     "cmfb200_gn_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _F, _I, _P],
     "cmfb200_ctxmap_weights_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -139,6 +139,38 @@ def conv3d_k3(x, packed, stride=1, transposed=False, want_stats=False):
     return y, sums
 
 
+def pack_conv2d_weight(weight):
+    """nn.Conv2d [Cout,Cin,k,k] -> packed [Cin,k*k,Cout]."""
+    weight = weight.detach()
+    _req(weight)
+    Cout, Cin, k, k2 = weight.shape
+    if k != k2 or k not in (1, 3):
+        raise ValueError("expected a 1x1 or 3x3 kernel, got %s" % (tuple(weight.shape),))
+    packed = torch.empty((Cin, k * k, Cout), device=weight.device, dtype=torch.float32)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.load().cmfb200_pack_conv2d_weight(_p(weight), _p(packed), Cout, Cin, k, _stream()),
+                   "pack_conv2d_weight")
+    return packed
+
+
+def conv2d(x, packed, ksize, stride=1, dilation=1, want_stats=False):
+    """2-D conv, padding (k//2)*dilation (reference convbn(), cmf/models/cmfsm.py:36-46).  Returns (y, gn_sums)."""
+    _req(x, packed)
+    B, Cin, H, W = x.shape
+    if packed.shape[0] != Cin or packed.shape[1] != ksize * ksize:
+        raise ValueError("packed weight %s does not match Cin=%d k=%d" % (tuple(packed.shape), Cin, ksize))
+    Cout = packed.shape[2]
+    pad = (ksize // 2) * dilation
+    Ho = (H + 2 * pad - (ksize - 1) * dilation - 1) // stride + 1
+    Wo = (W + 2 * pad - (ksize - 1) * dilation - 1) // stride + 1
+    sums = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _timed("conv2d_fwd"):
+        _lib.check(_lib.load().cmfb200_conv2d_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, H, W, ksize, stride,
+                                                  dilation, _stream()), "conv2d_fwd")
+    return y, sums
+
+
 def gn_stats(x):
     _req(x)
     B, C = x.shape[:2]

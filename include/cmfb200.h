@@ -59,7 +59,7 @@ int cmfb200_pack_conv3d_weight(const float* weight, float* packed, int Cout, int
                                int transposed, void* stream);
 
 /* x: [B,Cin,D,H,W] NCDHW; y: [B,Cout,Do,Ho,Wo], Xo = (X-1)/stride + 1; stride in {1,2};
- * Cin % 4 == 0; Cout in {1, 32, 64}.
+ * Cin % 8 == 0; Cout in {1, 32, 64}.
  * If gn_sums != NULL it must be a ZEROED [B,Cout,2] double buffer: the kernel accumulates per
  * (b,channel) sum and sum-of-squares of y into it (GroupNorm statistics fused into the epilogue). */
 int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
@@ -67,6 +67,16 @@ int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, float* y, doubl
 /* Transposed conv k3 s2 p1 op1: y: [B,Cout,2D,2H,2W].  Cout in {32,64}; same gn_sums contract. */
 int cmfb200_deconv3d_k3s2_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
                               int B, int Cin, int Cout, int D, int H, int W, void* stream);
+
+/* ---- 2-D convolutions of the feature extractor ----------------------------------------------------
+ * Replace nn.Conv2d(bias=False) in convbn / BasicBlock / feature_extraction (cmfsm.py:36-46, 61-85, 126-236).
+ * Packed weights wp[Cin][k*k][Cout] from nn.Conv2d's [Cout,Cin,k,k].
+ * x: [B,Cin,H,W] NCHW; y: [B,Cout,Ho,Wo]; padding = (k/2)*dilation (what convbn() computes);
+ * (ksize,stride,dilation) in {(3,1,1),(3,2,1),(3,1,2),(1,1,1),(1,2,1)}; Cin = 3 (stem, Cout 32) or a multiple
+ * of 8; Cout = 32 or a multiple of 64.  gn_sums: same contract as cmfb200_conv3d_k3_fwd. */
+int cmfb200_pack_conv2d_weight(const float* weight, float* packed, int Cout, int Cin, int ksize, void* stream);
+int cmfb200_conv2d_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
+                       int B, int Cin, int Cout, int H, int W, int ksize, int stride, int dilation, void* stream);
 
 /* ---- K3: GroupNorm (+ residual add) (+ ReLU) ---------------------------------------------------
  * Replaces nn.GroupNorm(32,C) (cmfsm.py:58,269,280), the residual adds (:288,297,299,685,687,690,693)
@@ -96,7 +106,7 @@ int cmfb200_ctxmap_weights_fwd(const float* lr, const float* hr, const float* w0
  * c1,c2,c3: raw classifier volumes [B,D,h,w]; cost1=c1, cost2=c2+cost1, cost3=c3+cost2.
  * p_i[b,cy,cx] = sum_d d*softmax_d(cost_i);  out_i[b,0,y,x] = sum_k w_k[b,y,x]*scale*p_i[b,y/s+dy_k,x/s+dx_k]
  * over in-image neighbours.  weights9: [B,9,H,W]; out1..3: [B,1,H,W]; pred_lr (optional, may be NULL):
- * [3,B,h,w] receives p_i.  D <= 128. */
+ * [3,B,h,w] receives p_i.  scale % 4 == 0. */
 int cmfb200_softargmin_ctxmap_fwd(const float* c1, const float* c2, const float* c3,
                                   const float* weights9, float* out1, float* out2, float* out3,
                                   float* pred_lr, int B, int D, int h, int w, int scale, void* stream);

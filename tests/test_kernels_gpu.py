@@ -116,6 +116,47 @@ def test_deconv3d_vs_fp64_oracle(B, Cin, Cout, D, H, W):
     torch.testing.assert_close(sums.cpu()[..., 0], want.sum((2, 3, 4)), rtol=1e-5, atol=1e-3)
 
 
+CONV2D_CASES = [  # B, Cin, Cout, H, W, k, stride, dilation
+    (2, 3, 32, 20, 40, 3, 1, 1), (1, 32, 32, 17, 70, 3, 1, 1), (1, 32, 32, 21, 50, 3, 2, 1), (1, 32, 64, 16, 64, 3, 2, 1),
+    (1, 64, 64, 9, 33, 3, 1, 1), (1, 64, 128, 12, 36, 3, 1, 1), (2, 128, 128, 10, 44, 3, 1, 2), (1, 32, 64, 18, 30, 1, 2, 1),
+    (1, 64, 128, 7, 12, 1, 1, 1), (2, 128, 32, 2, 3, 1, 1, 1), (1, 320, 128, 8, 36, 3, 1, 1), (1, 128, 32, 9, 60, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,stride,dil", CONV2D_CASES)
+def test_conv2d_vs_fp64_oracle(B, Cin, Cout, H, W, k, stride, dil):
+    from cmf_b200 import ops
+
+    x = _rand(B, Cin, H, W, seed=50)
+    wgt = _rand(Cout, Cin, k, k, seed=51) * (2.0 / (k * k * Cin)) ** 0.5
+    pad = (k // 2) * dil
+    want = F.conv2d(x.double(), wgt.double(), None, stride, pad, dil)
+    y, sums = ops.conv2d(x.to(DEV), ops.pack_conv2d_weight(wgt.to(DEV)), k, stride, dil, want_stats=True)
+    assert y.shape == want.shape
+    assert _rel_l2(y, want) < 1e-5
+    torch.testing.assert_close(sums.cpu()[..., 0], want.sum((2, 3)), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(sums.cpu()[..., 1], (want * want).sum((2, 3)), rtol=1e-5, atol=1e-3)
+
+
+def test_feature_extractor_vs_oracle():
+    """Own conv2d/GroupNorm kernels through the whole SPP feature extractor vs the CPU oracle (fp32 and fp64)."""
+    from cmf.models import get_model
+
+    torch.manual_seed(gc.WEIGHT_SEED)
+    model = get_model("cmfsm").to(DEV).eval()
+    left, _ = gc.seeded_pair(1, 256, 512)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    f32, a32 = orc.feature_extraction(sd, left)
+    f64, a64 = orc.feature_extraction({k: v.double() for k, v in sd.items()}, left.double())
+    with torch.no_grad():
+        feat, full = model._features(left.to(DEV))
+    assert torch.equal(torch.tensor(feat.shape), torch.tensor(f32.shape))
+    print("feat rel-L2 ours/fp64 %.2e  ref32/fp64 %.2e ; full ours %.2e ref32 %.2e"
+          % (_rel_l2(feat, f64), _rel_l2(f32, f64), _rel_l2(full, a64), _rel_l2(a32, a64)))
+    assert _rel_l2(full, a64) < 1e-5
+    assert _rel_l2(feat, f64) < max(2e-5, 3 * _rel_l2(f32, f64))
+
+
 @pytest.mark.parametrize("C,relu,res", [(32, True, False), (64, True, True), (64, False, True), (32, False, False)])
 def test_groupnorm_apply_vs_oracle(C, relu, res):
     from cmf_b200 import ops
