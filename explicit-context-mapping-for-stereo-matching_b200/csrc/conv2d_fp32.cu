@@ -172,28 +172,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
                 }
         }
     }
-    if (gn_sums != nullptr) {
-        constexpr int WPG = G::NQ / 32;
-        float* sred = smem;
-        const int warp = tid >> 5, lane = tid & 31;
-        // (the loop's trailing __syncthreads already fenced the operand buffers)
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const float a = warp_sum(s[c]), qq = warp_sum(ss[c]);
-            if (lane == 0) {
-                sred[(warp * CPT + c) * 2 + 0] = a;
-                sred[(warp * CPT + c) * 2 + 1] = qq;
-            }
-        }
-        __syncthreads();
-        if (tid < COUT_TILE * 2) {
-            const int col = tid >> 1, which = tid & 1;
-            const int g = col / CPT, c = col % CPT;
-            double a = 0.0;
-            for (int wi = 0; wi < WPG; ++wi) a += (double)sred[((g * WPG + wi) * CPT + c) * 2 + which];
-            atomicAdd(gn_sums + ((size_t)b * Cout + cb + col) * 2 + which, a);
-        }
-    }
+    if (gn_sums != nullptr) gn_epilogue<COUT_TILE, CPT>(s, ss, cg, smem, gn_sums, b, Cout, cb);
 }
 
 // weight packing: [Cout][Cin][KS*KS] -> [Cin][KS*KS][Cout]

@@ -38,21 +38,22 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __res
     const float* p = x + bc * spatial;
     const long long beg = (long long)blockIdx.x * kGnChunk;
     const long long end = min(spatial, beg + kGnChunk);
-    float s = 0.f, ss = 0.f;
+    // 4-element fp32 partials, everything above that in double (see gn_epilogue in conv_common.cuh)
+    double s = 0.0, ss = 0.0;
     if ((spatial & 3) == 0) {
         for (long long i = beg + threadIdx.x * 4; i < end; i += kGnThreads * 4) {
             const float4 v = ld_streaming_f4(p + i);
-            s += (v.x + v.y) + (v.z + v.w);
-            ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            s += (double)((v.x + v.y) + (v.z + v.w));
+            ss += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
         }
     } else {
         for (long long i = beg + threadIdx.x; i < end; i += kGnThreads) {
             const float v = p[i];
-            s += v;
-            ss += v * v;
+            s += (double)v;
+            ss += (double)v * (double)v;
         }
     }
-    block_reduce_add2((double)s, (double)ss, sums + 2 * bc);
+    block_reduce_add2(s, ss, sums + 2 * bc);
 }
 
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const float* __restrict__ x,

@@ -69,7 +69,7 @@ def _layer(sd, key, x, blocks, stride, dilation):
 # ----------------------------------------------------------------------------------------------
 # a2: 2D feature extraction  (cmfsm.py:126-236)
 # ----------------------------------------------------------------------------------------------
-def feature_extraction(sd, x, prefix="feature_extraction"):
+def feature_extraction(sd, x, prefix="feature_extraction", stages=None):
     """Returns (feature [B,32,H/4,W/4], all_feature [B,32,H,W]).  cmfsm.py:199-236.
 
     `all_feature` is the output of firstconv (pre-GN, pre-ReLU) -- cmfsm.py:138,200.
@@ -83,10 +83,11 @@ def feature_extraction(sd, x, prefix="feature_extraction"):
     o = F.relu(_gn(sd, p + ".secondconv.0", all_feature))
     o = F.relu(_convgn2d(sd, p + ".secondconv.2", o, stride=2))
     o = F.relu(_convgn2d(sd, p + ".secondconv.4", o))
-    o = _layer(sd, p + ".layer1", o, 3, 1, 1)
-    raw = _layer(sd, p + ".layer2", o, 16, 2, 1)
-    o = _layer(sd, p + ".layer3", raw, 3, 1, 1)
-    skip = _layer(sd, p + ".layer4", o, 3, 1, 2)
+    second = o
+    l1 = _layer(sd, p + ".layer1", o, 3, 1, 1)
+    raw = _layer(sd, p + ".layer2", l1, 16, 2, 1)
+    l3 = _layer(sd, p + ".layer3", raw, 3, 1, 1)
+    skip = _layer(sd, p + ".layer4", l3, 3, 1, 2)
     size = skip.shape[2:]
     branches = []
     for name, k in (("branch1", 64), ("branch2", 32), ("branch3", 16), ("branch4", 8)):
@@ -97,6 +98,9 @@ def feature_extraction(sd, x, prefix="feature_extraction"):
     cat = torch.cat((raw, skip, b4, b3, b2, b1), 1)  # cmfsm.py:231-233
     o = F.relu(_convgn2d(sd, p + ".lastconv.0", cat))
     feat = F.conv2d(o, sd[p + ".lastconv.2.weight"])
+    if stages is not None:
+        stages.update(full=all_feature, second=second, layer1=l1, layer2=raw, layer3=l3, layer4=skip, b1=b1, b2=b2,
+                      b3=b3, b4=b4, last0=o, feat=feat)
     return feat, all_feature
 
 
