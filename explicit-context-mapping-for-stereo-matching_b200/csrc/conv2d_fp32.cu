@@ -150,11 +150,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     // ---- epilogue
     const int oh = h0 + th, ow = w0 + qx * kVPT;
     const size_t out_plane = (size_t)Ho * Wo;
-    float s[CPT], ss[CPT];
+    double s[CPT], ss[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-        s[c] = 0.f;
-        ss[c] = 0.f;
+        s[c] = 0.0;
+        ss[c] = 0.0;
     }
     if (oh < Ho && ow < Wo) {
         const bool vec = ((Wo & 3) == 0);
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(kConvThreads, 2)
             for (int v = 0; v < kVPT; ++v)
                 if (vec || ow + v < Wo) {
                     if (!vec) py[v] = acc[c][v];
-                    s[c] += acc[c][v];
-                    ss[c] = fmaf(acc[c][v], acc[c][v], ss[c]);
+                    s[c] += (double)acc[c][v];
+                    ss[c] = fma((double)acc[c][v], (double)acc[c][v], ss[c]);
                 }
         }
     }

@@ -7,7 +7,8 @@
 //
 // Register-tiled direct convolution: a CTA owns a TD x TH x 32 block of output voxels and ALL output
 // channels; per chunk of CC input channels the halo'd input patch and the [CC][27][COUT] weight slice
-// are staged in shared memory; a thread owns CPT output channels x 4 consecutive-w voxels (32 fp32
+// are staged in shared memory (cp.async, 2-stage ring: chunk i+1 is prefetched while chunk i is consumed;
+// per-thread staging slots computed once); a thread owns CPT output channels x 4 consecutive-w voxels (32 fp32
 // accumulators for CPT=8).  Per (ci,kd,kh) it issues 2 vector loads of input + 6 broadcast loads of weights
 // for 96 FMAs, i.e. the inner loop is FMA-issue bound, not shared-memory bound.
 // GroupNorm statistics (sum, sum of squares per (b,channel)) are reduced in the epilogue.
@@ -20,7 +21,7 @@ namespace cmfb200 {
 // forward convolution, stride S in {1,2}
 // ------------------------------------------------------------------------------------------------
 template <int COUT, int CPT, int S, int CC>
-__global__ void __launch_bounds__(kConvThreads, (COUT == 64 && S == 2) ? 1 : 2)
+__global__ void __launch_bounds__(kConvThreads, 2)
     conv3d_k3_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
                      double* __restrict__ gn_sums, int Cin, int D, int H, int W, int Do, int Ho, int Wo, int tiles_w) {
     using T = ConvTile<COUT, CPT>;
@@ -29,10 +30,13 @@ __global__ void __launch_bounds__(kConvThreads, (COUT == 64 && S == 2) ? 1 : 2)
     constexpr int PATCH = PD * PH * PWP;  // floats per input channel
     constexpr int WSL = 27 * COUT;        // weight floats per input channel
     constexpr int NI = (kVPT - 1) * S + 3;
+    constexpr int NI4 = (NI + 3) / 4;
+    constexpr int NSLOT = (PD * PH * PW + kConvThreads - 1) / kConvThreads;
+    constexpr int STAGE = CC * (PATCH + WSL);  // floats per pipeline stage
+    static_assert((kTW / kVPT - 1) * kVPT * S + NI4 * 4 <= PWP, "vector over-read leaves the patch row");
+    static_assert((CC * WSL) % 4 == 0 && (CC * PATCH) % 4 == 0, "stage slices must stay 16-byte aligned");
 
-    extern __shared__ __align__(16) float smem[];
-    float* sIn = smem;               // [CC][PD][PH][PWP]
-    float* sW = smem + CC * PATCH;   // [CC][27][COUT]
+    extern __shared__ __align__(16) float smem[];  // 2 stages of [CC][PD][PH][PWP] + [CC][27][COUT]
 
     const int tile_x = blockIdx.x % tiles_w, tile_y = blockIdx.x / tiles_w;
     const int w0 = tile_x * kTW, h0 = tile_y * T::TH, d0 = blockIdx.y * T::TD;
@@ -55,33 +59,60 @@ __global__ void __launch_bounds__(kConvThreads, (COUT == 64 && S == 2) ? 1 : 2)
     const float* xb = x + (size_t)b * Cin * in_vol;
     const int di0 = d0 * S - 1, hi0 = h0 * S - 1, wi0 = w0 * S - 1;
 
-    for (int c0 = 0; c0 < Cin; c0 += CC) {
-        __syncthreads();  // previous chunk fully consumed
-        // ---- stage input patch (zero padded)
-        for (int i = tid; i < CC * PD * PH * PW; i += kConvThreads) {
-            const int pw = i % PW;
-            int r = i / PW;
-            const int ph = r % PH;
-            r /= PH;
-            const int pd = r % PD, ci = r / PD;
-            const int di = di0 + pd, hi = hi0 + ph, wi = wi0 + pw;
-            float v = 0.f;
-            if ((unsigned)di < (unsigned)D && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W)
-                v = __ldg(xb + (size_t)(c0 + ci) * in_vol + (size_t)di * in_plane + (size_t)hi * W + wi);
-            sIn[((ci * PD + pd) * PH + ph) * PWP + pw] = v;
+    // ---- staging slots of this thread (identical for every input channel): computed once
+    int goff[NSLOT], soff[NSLOT];
+    bool ok[NSLOT];
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) {
+        const int e = tid + j * kConvThreads;
+        const int pw = e % PW;
+        const int r = e / PW;
+        const int ph = r % PH, pd = r / PH;
+        const int di = di0 + pd, hi = hi0 + ph, wi = wi0 + pw;
+        const bool in_patch = e < PD * PH * PW;
+        ok[j] = in_patch && (unsigned)di < (unsigned)D && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
+        goff[j] = ok[j] ? (di * H + hi) * W + wi : 0;
+        soff[j] = in_patch ? (pd * PH + ph) * PWP + pw : -1;
+    }
+
+    auto stage = [&](int c0, int buf) {
+        float* sIn = smem + buf * STAGE;
+        float* sW = sIn + CC * PATCH;
+#pragma unroll
+        for (int ci = 0; ci < CC; ++ci) {
+            const float* src = xb + (size_t)(c0 + ci) * in_vol;
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j)
+                if (soff[j] >= 0) cp_async_4_zfill(sIn + ci * PATCH + soff[j], src + goff[j], ok[j]);
         }
-        // ---- stage weights: contiguous [CC][27][COUT] slice
-        {
-            const float* wsrc = wp + (size_t)c0 * WSL;
-            if constexpr ((WSL * CC) % 4 == 0) {
-                for (int i = tid * 4; i < CC * WSL; i += kConvThreads * 4)
-                    *reinterpret_cast<float4*>(sW + i) = __ldg(reinterpret_cast<const float4*>(wsrc + i));
-            } else {
-                for (int i = tid; i < CC * WSL; i += kConvThreads) sW[i] = __ldg(wsrc + i);
-            }
+        const float* wsrc = wp + (size_t)c0 * WSL;  // contiguous [CC][27][COUT] slice
+        for (int i = tid * 4; i < CC * WSL; i += kConvThreads * 4) cp_async_16(sW + i, wsrc + i);
+        cp_async_commit();
+    };
+
+    // zero the alignment tail of every patch row once (never written by cp.async, read by the vector loads)
+    if constexpr (PWP > PW) {
+        for (int i = tid; i < 2 * CC * PD * PH * (PWP - PW); i += kConvThreads) {
+            const int t = i % (PWP - PW);
+            const int r = i / (PWP - PW);  // (buf, ci, pd*PH+ph) flattened
+            const int prow = r % (PD * PH), ci = (r / (PD * PH)) % CC, buf = r / (PD * PH * CC);
+            smem[buf * STAGE + ci * PATCH + prow * PWP + PW + t] = 0.f;
+        }
+    }
+
+    const int nchunks = Cin / CC;
+    stage(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) {
+            stage((ch + 1) * CC, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
-        // ---- FMA loop
+        const float* sIn = smem + buf * STAGE;
+        const float* sW = sIn + CC * PATCH;
 #pragma unroll 1
         for (int ci = 0; ci < CC; ++ci) {
             const float* pin = sIn + ci * PATCH + (td * S * PH + th * S) * PWP + qx * kVPT * S;
@@ -91,17 +122,11 @@ __global__ void __launch_bounds__(kConvThreads, (COUT == 64 && S == 2) ? 1 : 2)
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     const float* prow = pin + (kd * PH + kh) * PWP;
-                    float in[NI];
-                    if constexpr (S == 1) {
-                        const float4 a = *reinterpret_cast<const float4*>(prow);
-                        const float2 c2 = *reinterpret_cast<const float2*>(prow + 4);
-                        in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w; in[4] = c2.x; in[5] = c2.y;
-                    } else {
-                        const float4 a = *reinterpret_cast<const float4*>(prow);
-                        const float4 c4 = *reinterpret_cast<const float4*>(prow + 4);
-                        in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w;
-                        in[4] = c4.x; in[5] = c4.y; in[6] = c4.z; in[7] = c4.w;
-                        in[8] = prow[8];
+                    float in[NI4 * 4];
+#pragma unroll
+                    for (int j = 0; j < NI4; ++j) {
+                        const float4 a = *reinterpret_cast<const float4*>(prow + 4 * j);
+                        in[4 * j + 0] = a.x; in[4 * j + 1] = a.y; in[4 * j + 2] = a.z; in[4 * j + 3] = a.w;
                     }
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
@@ -124,17 +149,18 @@ __global__ void __launch_bounds__(kConvThreads, (COUT == 64 && S == 2) ? 1 : 2)
                 }
             }
         }
+        __syncthreads();  // everyone done with `buf` before the next prefetch overwrites it
     }
 
     // ---- epilogue: store + GroupNorm partial sums
     const int od = d0 + td, oh = h0 + th, ow = w0 + qx * kVPT;
     const bool row_ok = (od < Do) && (oh < Ho);
     const size_t out_plane = (size_t)Ho * Wo;
-    float s[CPT], ss[CPT];
+    double s[CPT], ss[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-        s[c] = 0.f;
-        ss[c] = 0.f;
+        s[c] = 0.0;
+        ss[c] = 0.0;
     }
     if (row_ok && ow < Wo) {
         const bool vec = ((Wo & 3) == 0);  // then ow+3 < Wo and the address is 16-byte aligned
@@ -146,16 +172,16 @@ __global__ void __launch_bounds__(kConvThreads, (COUT == 64 && S == 2) ? 1 : 2)
                 *reinterpret_cast<float4*>(py) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
 #pragma unroll
                 for (int v = 0; v < kVPT; ++v) {
-                    s[c] += acc[c][v];
-                    ss[c] = fmaf(acc[c][v], acc[c][v], ss[c]);
+                    s[c] += (double)acc[c][v];
+                    ss[c] = fma((double)acc[c][v], (double)acc[c][v], ss[c]);
                 }
             } else {
 #pragma unroll
                 for (int v = 0; v < kVPT; ++v)
                     if (ow + v < Wo) {
                         py[v] = acc[c][v];
-                        s[c] += acc[c][v];
-                        ss[c] = fmaf(acc[c][v], acc[c][v], ss[c]);
+                        s[c] += (double)acc[c][v];
+                        ss[c] = fma((double)acc[c][v], (double)acc[c][v], ss[c]);
                     }
             }
         }
@@ -268,11 +294,11 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
     const int od = 2 * id + pd, oh = 2 * (ih0 + th) + ph, ow = 2 * (iw0 + qx * kVPT);
     const size_t out_plane = (size_t)Ho * Wo;
-    float s[CPT], ss[CPT];
+    double s[CPT], ss[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-        s[c] = 0.f;
-        ss[c] = 0.f;
+        s[c] = 0.0;
+        ss[c] = 0.0;
     }
     if (oh < Ho && ow < Wo) {
         const bool vec = ((Wo & 3) == 0) && (ow + NO <= Wo);
@@ -288,8 +314,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
             for (int v = 0; v < NO; ++v)
                 if (ow + v < Wo) {
                     if (!vec) py[v] = acc[c][v];
-                    s[c] += acc[c][v];
-                    ss[c] = fmaf(acc[c][v], acc[c][v], ss[c]);
+                    s[c] += (double)acc[c][v];
+                    ss[c] = fma((double)acc[c][v], (double)acc[c][v], ss[c]);
                 }
         }
     }
@@ -315,8 +341,8 @@ static int launch_conv(const float* x, const float* wp, float* y, double* gn, in
     using T = ConvTile<COUT, CPT>;
     constexpr int PD = (T::TD - 1) * S + 3, PH = (T::TH - 1) * S + 3, PW = (kTW - 1) * S + 3;
     constexpr int PWP = (PW + 3) & ~3;
-    constexpr size_t smem = (size_t)CC * (PD * PH * PWP + 27 * COUT) * sizeof(float);
-    static_assert(smem <= 220 * 1024, "tile does not fit");
+    constexpr size_t smem = 2 * (size_t)CC * (PD * PH * PWP + 27 * COUT) * sizeof(float);
+    static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
     const int Do = (D - 1) / S + 1, Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
     const int tiles_w = (int)cdiv(Wo, kTW), tiles_h = (int)cdiv(Ho, T::TH);
     auto kern = conv3d_k3_kernel<COUT, CPT, S, CC>;
@@ -365,11 +391,11 @@ extern "C" int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, floa
     CMF_REQUIRE(Cin % 8 == 0, "conv3d_k3_fwd: Cin=%d must be a multiple of 8", Cin);
     CMF_REQUIRE(stride == 1 || stride == 2, "conv3d_k3_fwd: stride=%d not in {1,2}", stride);
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cout == 32 && stride == 1) return launch_conv<32, 8, 1, 8>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 64 && stride == 1) return launch_conv<64, 8, 1, 8>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 64 && stride == 2) return launch_conv<64, 8, 2, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 1 && stride == 1) return launch_conv<1, 1, 1, 8>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 32 && stride == 1) return launch_conv<32, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 64 && stride == 1) return launch_conv<64, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 2>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 64 && stride == 2) return launch_conv<64, 8, 2, 2>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 1 && stride == 1) return launch_conv<1, 1, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
     CMF_REQUIRE(false, "conv3d_k3_fwd: unsupported (Cout=%d, stride=%d); Cout in {1,32,64}", Cout, stride);
 }
 

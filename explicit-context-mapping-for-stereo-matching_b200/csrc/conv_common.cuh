@@ -19,11 +19,12 @@ struct ConvTile {
 };
 
 // epilogue helper: block-level reduction of per-thread channel sums into gn_sums[b][co][2] (double atomics).
-// Per-thread partials (a handful of fp32 adds) are widened to double BEFORE any cross-thread reduction: the
-// variance is formed as E[x^2]-mean^2, so fp32 rounding in the reduction tree is amplified by E[x^2]/var
-// (measured: 3e-5 relative feature error -> 1 px disparity error on random-init weights).
+// Sums and sums of squares are accumulated in DOUBLE from the first element on: the variance is formed as
+// E[x^2]-mean^2, so any fp32 rounding of a partial sum is amplified by E[x^2]/var.  Measured on the SPP branch
+// (GroupNorm over 2 pooled values per channel): fp32 4-element partials gave 6.5e-4 relative error there and
+// 1 px disparity error end to end on random-init weights.
 template <int COUT, int CPT>
-__device__ __forceinline__ void gn_epilogue(const float (&s)[CPT], const float (&ss)[CPT], int cg, void* sred_raw,
+__device__ __forceinline__ void gn_epilogue(const double (&s)[CPT], const double (&ss)[CPT], int cg, void* sred_raw,
                                             double* __restrict__ gn_sums, int b, int c_total = COUT, int c_base = 0) {
     using T = ConvTile<COUT, CPT>;
     constexpr int WPG = T::NQ / 32;  // warps per channel group
@@ -32,7 +33,7 @@ __device__ __forceinline__ void gn_epilogue(const float (&s)[CPT], const float (
     __syncthreads();  // sred aliases the operand buffers: everyone must be done with them
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-        const double a = warp_sum((double)s[c]), q = warp_sum((double)ss[c]);
+        const double a = warp_sum(s[c]), q = warp_sum(ss[c]);
         if (lane == 0) {
             sred[(warp * CPT + c) * 2 + 0] = a;
             sred[(warp * CPT + c) * 2 + 1] = q;

@@ -38,13 +38,14 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __res
     const float* p = x + bc * spatial;
     const long long beg = (long long)blockIdx.x * kGnChunk;
     const long long end = min(spatial, beg + kGnChunk);
-    // 4-element fp32 partials, everything above that in double (see gn_epilogue in conv_common.cuh)
+    // double from the first element on (see gn_epilogue in conv_common.cuh)
     double s = 0.0, ss = 0.0;
     if ((spatial & 3) == 0) {
         for (long long i = beg + threadIdx.x * 4; i < end; i += kGnThreads * 4) {
             const float4 v = ld_streaming_f4(p + i);
-            s += (double)((v.x + v.y) + (v.z + v.w));
-            ss += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+            const double a = v.x, b = v.y, c = v.z, d = v.w;
+            s += (a + b) + (c + d);
+            ss += (a * a + b * b) + (c * c + d * d);
         }
     } else {
         for (long long i = beg + threadIdx.x; i < end; i += kGnThreads) {
