@@ -62,14 +62,14 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _req(*tensors):
+def _req(*tensors, dtype=torch.float32):
     for t in tensors:
         if t is None:
             continue
         if not t.is_cuda:
             raise _lib.CmfB200Error("cmf_b200 kernels need CUDA tensors (no CPU fallback); got device %s" % t.device)
-        if t.dtype != torch.float32:
-            raise _lib.CmfB200Error("cmf_b200 fp32 kernels got dtype %s" % t.dtype)
+        if t.dtype != dtype:
+            raise _lib.CmfB200Error("cmf_b200 kernel expected dtype %s, got %s" % (dtype, t.dtype))
         if not t.is_contiguous():
             raise _lib.CmfB200Error("cmf_b200 kernels need contiguous tensors")
 
@@ -235,3 +235,83 @@ def softargmin_ctxmap(c1, c2, c3, weights9, scale, want_lowres=False):
                                                              _p(outs[1]), _p(outs[2]), _p(low), B, D, h, w, scale,
                                                              _stream()), "softargmin_ctxmap_fwd")
     return (tuple(outs), low) if want_lowres else tuple(outs)
+
+
+# ------------------------------------------------------------------------------------------ bf16 / C8 path
+# C8 layout: bf16 [B, C/8, D, H, W, 8] (include/cmfb200.h); tensors below carry that 6-D shape.
+BF16 = torch.bfloat16
+
+
+def pack_igemm_weight(weight, transposed=False):
+    """nn.Conv3d weight (fp32) -> bf16 [27, Cin/8, Cout, 8] for the tcgen05 implicit GEMM."""
+    weight = weight.detach()
+    _req(weight)
+    Cin, Cout = (weight.shape[0], weight.shape[1]) if transposed else (weight.shape[1], weight.shape[0])
+    packed = torch.empty((27, Cin // 8, Cout, 8), device=weight.device, dtype=BF16)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.load().cmfb200_pack_igemm_weight_bf16(_p(weight), _p(packed), Cout, Cin, int(transposed),
+                                                              _stream()), "pack_igemm_weight_bf16")
+    return packed
+
+
+def f32_to_c8(x):
+    """[B,C,D,H,W] fp32 -> C8 bf16."""
+    _req(x)
+    B, C = x.shape[:2]
+    sp = tuple(x.shape[2:])
+    y = torch.empty((B, C // 8) + sp + (8,), device=x.device, dtype=BF16)
+    with torch.cuda.device(x.device), _timed("f32_to_c8_bf16"):
+        _lib.check(_lib.load().cmfb200_f32_to_c8_bf16(_p(x), _p(y), B, C, x[0, 0].numel(), _stream()), "f32_to_c8_bf16")
+    return y
+
+
+def c8_to_f32(x):
+    """C8 bf16 -> [B,C,D,H,W] fp32."""
+    _req(x, dtype=BF16)
+    B, NC = x.shape[:2]
+    sp = tuple(x.shape[2:-1])
+    y = torch.empty((B, NC * 8) + sp, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _timed("c8_bf16_to_f32"):
+        _lib.check(_lib.load().cmfb200_c8_bf16_to_f32(_p(x), _p(y), B, NC * 8, y[0, 0].numel(), _stream()),
+                   "c8_bf16_to_f32")
+    return y
+
+
+def cost_volume_concat_c8(L, R, D):
+    """K1 in C8/bf16: [B,C,h,w] fp32 x2 -> [B, 2C/8, D, h, w, 8] bf16."""
+    _req(L, R)
+    B, C, h, w = L.shape
+    cost = torch.empty((B, 2 * C // 8, D, h, w, 8), device=L.device, dtype=BF16)
+    with torch.cuda.device(L.device), _timed("cost_volume_concat_c8_bf16"):
+        _lib.check(_lib.load().cmfb200_cost_volume_concat_c8_bf16(_p(L), _p(R), _p(cost), B, C, h, w, D, _stream()),
+                   "cost_volume_concat_c8_bf16")
+    return cost
+
+
+def conv3d_igemm(x, packed, want_stats=True):
+    """tcgen05 implicit-GEMM 3x3x3 s1 conv on C8/bf16.  Returns (raw y C8 bf16, gn_sums or None)."""
+    _req(x, packed, dtype=BF16)
+    B, NC, D, H, W, _ = x.shape
+    Cin, Cout = NC * 8, packed.shape[2]
+    if packed.shape[1] != NC:
+        raise ValueError("weight Cin %d != input channels %d" % (packed.shape[1] * 8, Cin))
+    y = torch.empty((B, Cout // 8, D, H, W, 8), device=x.device, dtype=BF16)
+    sums = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    with torch.cuda.device(x.device), _timed("conv3d_igemm_bf16_fwd"):
+        _lib.check(_lib.load().cmfb200_conv3d_igemm_bf16_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W,
+                                                             _stream()), "conv3d_igemm_bf16_fwd")
+    return y, sums
+
+
+def gn_apply_c8(x, sums, gamma, beta, residual=None, relu=False, out=None, groups=GN_GROUPS, eps=GN_EPS):
+    gamma, beta = gamma.detach(), beta.detach()
+    _req(gamma, beta)
+    _req(x, residual, dtype=BF16)
+    B, NC = x.shape[:2]
+    spatial = x[0, 0].numel() // 8
+    y = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device), _timed("gn_apply_c8_bf16"):
+        _lib.check(_lib.load().cmfb200_gn_apply_c8_bf16(_p(x), _p(sums), _p(gamma), _p(beta), _p(residual), _p(y), B,
+                                                        NC * 8, groups, spatial, eps, int(relu), _stream()),
+                   "gn_apply_c8_bf16")
+    return y

@@ -68,6 +68,29 @@ int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, float* y, doubl
 int cmfb200_deconv3d_k3s2_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
                               int B, int Cin, int Cout, int D, int H, int W, void* stream);
 
+/* ---- K2 throughput path: bf16 tcgen05/TMEM/TMA implicit GEMM on the "C8" layout -------------------------
+ * C8 layout: bf16 [B][C/8][D][H][W][8] (a voxel's 8-channel group is one 16-byte unit).  All *_c8 pointers
+ * below are bf16 device buffers in that layout (void* in the ABI: no CUDA types in the header).
+ * pack: nn.Conv3d [Cout,Cin,3,3,3] (transposed=0) fp32 -> bf16 [27][Cin/8][Cout][8]. */
+int cmfb200_pack_igemm_weight_bf16(const float* weight, void* packed, int Cout, int Cin, int transposed,
+                                   void* stream);
+/* 3x3x3 stride-1 pad-1 conv, bf16 operands, fp32 accumulation (tcgen05.mma, accumulators in TMEM); output =
+ * RAW conv result rounded to bf16, C8.  (Cin,Cout) in {(32,32),(64,32),(64,64)}.  gn_sums: ZEROED [B,Cout,2]
+ * double buffer receiving sum / sum of squares of the stored (rounded) values, or NULL. */
+int cmfb200_conv3d_igemm_bf16_fwd(const void* x_c8, const void* packed_w, void* y_c8, double* gn_sums,
+                                  int B, int Cin, int Cout, int D, int H, int W, void* stream);
+/* K1 in C8/bf16: same contract as cmfb200_cost_volume_concat_fwd, output [B][2C/8][D][h][w][8] bf16
+ * (channel groups 0..C/8-1 = masked left features, C/8.. = shifted right features). */
+int cmfb200_cost_volume_concat_c8_bf16(const float* L, const float* R, void* cost_c8,
+                                       int B, int C, int h, int w, int D, void* stream);
+/* K3 on C8/bf16: y = GroupNorm(x) (+residual) (ReLU), fp32 math, bf16 in/out; y may alias x. */
+int cmfb200_gn_apply_c8_bf16(const void* x_c8, const double* gn_sums, const float* gamma, const float* beta,
+                             const void* residual_c8, void* y_c8, int B, int C, int G, long long spatial,
+                             float eps, int relu, void* stream);
+/* layout/dtype converters between C8/bf16 and dense fp32 [B,C,spatial] (NCDHW). */
+int cmfb200_c8_bf16_to_f32(const void* x_c8, float* y, int B, int C, long long spatial, void* stream);
+int cmfb200_f32_to_c8_bf16(const float* x, void* y_c8, int B, int C, long long spatial, void* stream);
+
 /* ---- 2-D convolutions of the feature extractor ----------------------------------------------------
  * Replace nn.Conv2d(bias=False) in convbn / BasicBlock / feature_extraction (cmfsm.py:36-46, 61-85, 126-236).
  * Packed weights wp[Cin][k*k][Cout] from nn.Conv2d's [Cout,Cin,k,k].

@@ -279,3 +279,67 @@ def test_k4_vs_oracle(B, D, h, w):
     torch.testing.assert_close(low[2].cpu(), orc.softargmin(c[0] + c[1] + c[2]), rtol=1e-5, atol=1e-4)
     # outputs are convex combinations of scale*p: bounded by scale*(D-1)
     assert float(got[2].max()) <= 4 * (D - 1) + 1e-3 and float(got[2].min()) >= -1e-3
+
+
+# ------------------------------------------------------------------------------------------ bf16 / C8 / tcgen05
+def _to_c8_ref(x):
+    """torch reference of the C8 layout: [B,C,D,H,W] -> [B,C/8,D,H,W,8] bf16."""
+    B, C, D, H, W = x.shape
+    return x.view(B, C // 8, 8, D, H, W).permute(0, 1, 3, 4, 5, 2).contiguous().to(torch.bfloat16)
+
+
+def test_c8_layout_converters_bit_exact():
+    from cmf_b200 import ops
+
+    x = _rand(2, 32, 3, 5, 12, seed=60)
+    c8 = ops.f32_to_c8(x.to(DEV))
+    assert torch.equal(c8.cpu(), _to_c8_ref(x))
+    back = ops.c8_to_f32(c8)
+    assert torch.equal(back.cpu(), x.to(torch.bfloat16).float())
+
+
+def test_k1_c8_bf16_matches_fp32_cost_volume():
+    from cmf_b200 import ops
+
+    L, R = _rand(2, 32, 6, 20, seed=61), _rand(2, 32, 6, 20, seed=62)
+    want = _to_c8_ref(orc.cost_volume_concat(L, R, 12))
+    got = ops.cost_volume_concat_c8(L.to(DEV), R.to(DEV), 12)
+    assert torch.equal(got.cpu(), want)
+
+
+IGEMM_CASES = [  # B, Cin, Cout, D, H, W
+    (1, 32, 32, 4, 16, 8), (1, 32, 32, 6, 20, 12), (2, 64, 32, 5, 16, 8), (1, 64, 64, 4, 18, 24), (1, 32, 32, 9, 37, 29),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,D,H,W", IGEMM_CASES)
+def test_conv3d_igemm_tcgen05_vs_oracle(B, Cin, Cout, D, H, W):
+    """tcgen05/TMEM/TMA implicit GEMM vs fp64 conv of the SAME bf16-rounded operands; the only differences are
+    fp32 accumulation order and the final bf16 rounding of the output (2^-9 relative per element)."""
+    from cmf_b200 import ops
+
+    x = _rand(B, Cin, D, H, W, seed=70)
+    wgt = _rand(Cout, Cin, 3, 3, 3, seed=71) * (2.0 / (27 * Cin)) ** 0.5
+    xq, wq = x.to(torch.bfloat16).double(), wgt.to(torch.bfloat16).double()
+    want = F.conv3d(xq, wq, None, 1, 1)
+    y, sums = ops.conv3d_igemm(ops.f32_to_c8(x.to(DEV)), ops.pack_igemm_weight(wgt.to(DEV)))
+    torch.cuda.synchronize()
+    got = ops.c8_to_f32(y).cpu().double()
+    err = _rel_l2(got, want)
+    print("igemm %s rel-L2 %.3e  max|d| %.3e" % ((B, Cin, Cout, D, H, W), err, float((got - want).abs().max())))
+    assert err < 3e-3
+    torch.testing.assert_close(sums.cpu()[..., 0], got.sum((2, 3, 4)), rtol=1e-6, atol=1e-3)
+    torch.testing.assert_close(sums.cpu()[..., 1], (got * got).sum((2, 3, 4)), rtol=1e-6, atol=1e-3)
+
+
+def test_gn_apply_c8_vs_oracle():
+    from cmf_b200 import ops
+
+    x = _rand(2, 64, 3, 6, 10, seed=80) * 2 + 0.3
+    r = _rand(2, 64, 3, 6, 10, seed=81)
+    gamma, beta = _rand(64, seed=82), _rand(64, seed=83)
+    xq, rq = x.to(torch.bfloat16).float(), r.to(torch.bfloat16).float()
+    want = (F.group_norm(xq.double(), 32, gamma.double(), beta.double(), 1e-5) + rq.double()).relu()
+    xs = xq.to(DEV)
+    got = ops.gn_apply_c8(ops.f32_to_c8(xs), ops.gn_stats(xs), gamma.to(DEV), beta.to(DEV), ops.f32_to_c8(rq.to(DEV)), True)
+    assert _rel_l2(ops.c8_to_f32(got), want) < 3e-3
