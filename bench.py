@@ -155,6 +155,7 @@ def run_ours(args, rank, world, local_rank):
 
     torch.manual_seed(0)
     model = get_model("cmfsm").to(dev).eval()
+    model.aggregation = args.aggregation
     left_h, right_h = (t.pin_memory() for t in synthetic_pair(1 + rank))
     left_d, right_d = left_h.to(dev), right_h.to(dev)
 
@@ -211,26 +212,45 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         hbm_peak, peak_src = peaks()
         h, w, D = H_PAD // 4, W_IMG // 4, MAXDISP // 4
-        k1_bytes = 2 * 32 * h * w * 4 + 64 * D * h * w * 4  # read both feature maps + write every voxel
-        k1_n, k1_ms = kernels.get("cost_volume_concat_fwd", (0, 0.0))
+        # read both fp32 feature maps once + write every voxel (4 B fp32 NCDHW, or 2 B in the C8/bf16 mode)
+        s_out = 4 if args.aggregation == "fp32" else 2
+        k1_name = "cost_volume_concat_fwd" if args.aggregation == "fp32" else "cost_volume_concat_c8_bf16"
+        k1_bytes = 2 * 32 * h * w * 4 + 64 * D * h * w * s_out
+        k1_n, k1_ms = kernels.get(k1_name, (0, 0.0))
         k1_gbs = (k1_bytes * k1_n / (k1_ms * 1e-3) / 1e9) if k1_ms > 0 else None
         share = {k: {"launches": n // args.steps, "ms_per_step": ms / args.steps,
                      "share": ms / ms_total} for k, (n, ms) in sorted(kernels.items())}
+        precision = ("fp32 FMA 3-D aggregation (parity mode)" if args.aggregation == "fp32" else
+                     "bf16-operand/fp32-accumulate tcgen05 implicit-GEMM 3-D aggregation (stride-1 convs)")
+        ig_n, ig_ms = kernels.get("conv3d_igemm_bf16_fwd", (0, 0.0))
+        vox = D * h * w
+        ig_macs = 27 * (vox * (64 * 32 + 6 * 32 * 32) + 3 * (vox // 8) * 64 * 64 + 3 * (vox // 64) * 64 * 64)
         line = {"metric": METRIC, "value": world * args.steps / (ms_total * 1e-3), "unit": "pairs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.aggregation == "fp32" else "bf16",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "parallelism": "independent pairs, %d rank(s), no collective" % world,
                            "l2": "working set per step (425 MB cost volume, 212 MB activations) exceeds the 126 MB L2",
-                           "precision": "fp32 FMA 3-D aggregation (parity mode), cuDNN fp32 (TF32 off) 2-D features"},
+                           "precision": precision + "; fp32 FMA 2-D features, K1/K4/K5 fp32"},
                 "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "pairs/s",
                         "h2d_bytes_per_step": 2 * 3 * H_PAD * W_IMG * 4, "d2h_bytes_per_step": H_IMG * W_IMG * 4},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "cost_volume_concat_fwd_kernel (K1)", "bound": "hbm", "achieved": k1_gbs,
+                "roofline": {"kernel": k1_name + " (K1)", "bound": "hbm", "achieved": k1_gbs,
                              "peak": hbm_peak, "unit": "GB/s", "frac": (k1_gbs / hbm_peak) if k1_gbs else None,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
                              "us_per_launch": (k1_ms / k1_n * 1e3) if k1_n else None},
                 "kernels": share, "clocks": sampler.summary()}
+        if ig_n:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+                os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            tpeak = float(pk.get("bf16_tflops_sustained", 1400.0))
+            tf = 2.0 * ig_macs * args.steps / (ig_ms * 1e-3) / 1e12
+            line["roofline_k2"] = {"kernel": "conv3d_igemm_bf16_kernel (K2, %d launches/step)" % (ig_n // args.steps),
+                                   "bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
+                                   "frac": tf / tpeak, "traffic": None,
+                                   "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json" if pk else "fallback",
+                                   "algorithmic_flops_per_step": 2.0 * ig_macs}
         if world == 1 and not args.no_cpu_baseline:
             times, cores = time_cpu_oracle(3)
             sec = statistics.median(times[1:]) if len(times) > 1 else times[0]
@@ -249,6 +269,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--aggregation", default="fp32", choices=("fp32", "bf16"),
+                    help="3-D aggregation arithmetic: fp32 FMA (BASELINE config 2, default) or bf16 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~30 s CPU oracle timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -13,6 +13,7 @@ extractor runs through cuDNN in strict fp32).  Output semantics are per-sample `
 broadcasts to `[B,B,H,W]` for B>1).  There is no CPU path: CPU inputs raise.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -162,7 +163,10 @@ class cmfsm(nn.Module):
         for name, m in self.named_modules():
             if isinstance(m, (nn.Conv2d, nn.Conv3d, nn.ConvTranspose3d)):
                 m._cmf_name = name
-        self._packed = {}  # (layer name, device index) -> (version, data_ptr, packed weight)
+        self._packed = {}  # (layer name, device index[, "ig"]) -> (version, data_ptr, packed weight)
+        # 3-D aggregation arithmetic: "fp32" (CUDA-core FMA, the parity mode BASELINE config 2 is quoted in) or
+        # "bf16" (tcgen05 implicit GEMM, bf16 operands / fp32 accumulate, BASELINE config 4)
+        self.aggregation = os.environ.get("CMF_B200_AGGREGATION", "fp32")
 
     # -------------------------------------------------------------------------------- helpers
     def _pack(self, conv):
@@ -225,6 +229,52 @@ class cmfsm(nn.Module):
         feat, _ = self._c2(fe.lastconv[2], o, False)
         return feat, full
 
+    # ---- bf16 aggregation: tcgen05 implicit GEMM on the C8 layout (stride-1 convs); the stride-2 convs and the
+    # transposed convs (16 % of the MACs) still run on the fp32 kernels through layout converters (round 1).
+    def _pack_ig(self, conv):
+        w = conv.weight
+        key = (conv._cmf_name, w.device.index, "ig")
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+            return hit[2]
+        packed = ops.pack_igemm_weight(w)
+        self._packed[key] = (w._version, w.data_ptr(), packed)
+        return packed
+
+    def _ig(self, block, x, residual=None, relu=False):
+        y, sums = ops.conv3d_igemm(x, self._pack_ig(block[0]))
+        return ops.gn_apply_c8(y, sums, block[1].weight, block[1].bias, residual, relu, out=y)
+
+    def _hourglass_bf16(self, hg, x, x32, presqu, postsqu, resid32):
+        o = ops.f32_to_c8(self._cg(hg.conv1[0], x32, 2, relu=True))
+        pre = self._ig(hg.conv2, o, residual=postsqu, relu=True)
+        pre32 = ops.c8_to_f32(pre)
+        o = ops.f32_to_c8(self._cg(hg.conv3[0], pre32, 2, relu=True))
+        o32 = ops.c8_to_f32(self._ig(hg.conv4[0], o, relu=True))
+        skip32 = ops.c8_to_f32(presqu) if presqu is not None else pre32
+        post32 = self._cg(hg.conv5, o32, residual=skip32, relu=True)
+        out32 = self._cg(hg.conv6, post32, residual=resid32, relu=False)
+        return ops.f32_to_c8(out32), out32, pre, ops.f32_to_c8(post32)
+
+    def _classify_bf16(self, head, x):
+        t32 = ops.c8_to_f32(self._ig(head[0], x, relu=True))
+        y, _ = ops.conv3d_k3(t32, self._pack(head[2]), 1)
+        return y.squeeze(1)
+
+    def _aggregate_bf16(self, lfeat, rfeat, D):
+        cost = ops.cost_volume_concat_c8(lfeat, rfeat, D)
+        cost0 = self._ig(self.dres0[0], cost, relu=True)
+        del cost
+        cost0 = self._ig(self.dres0[2], cost0, relu=True)
+        t = self._ig(self.dres1[0], cost0, relu=True)
+        cost0 = self._ig(self.dres1[2], t, residual=cost0)
+        cost0_32 = ops.c8_to_f32(cost0)
+        out1, out1_32, pre1, post1 = self._hourglass_bf16(self.dres2, cost0, cost0_32, None, None, cost0_32)
+        out2, out2_32, _pre2, post2 = self._hourglass_bf16(self.dres3, out1, out1_32, pre1, post1, cost0_32)
+        out3, _o3, _pre3, _post3 = self._hourglass_bf16(self.dres4, out2, out2_32, pre1, post2, cost0_32)
+        return (self._classify_bf16(self.classif1, out1), self._classify_bf16(self.classif2, out2),
+                self._classify_bf16(self.classif3, out3))
+
     def _hourglass(self, hg, x, presqu, postsqu, out_residual):
         # reference hourglass.forward, cmfsm.py:283-303 (+ the caller's `out + cost0`, :687,690,693)
         out = self._cg(hg.conv1[0], x, 2, relu=True)
@@ -284,6 +334,11 @@ class cmfsm(nn.Module):
         else:
             weights9 = ops.ctxmap_weights(lfeat, hr, sim.conv0.weight, sim.conv1.weight, sim.conv2.weight,
                                           sim.conv3.weight)
+            if self.aggregation == "bf16":
+                c1, c2, c3 = self._aggregate_bf16(lfeat, rfeat, D)
+                return ops.softargmin_ctxmap(c1, c2, c3, weights9, scale)
+            if self.aggregation != "fp32":
+                raise ValueError("aggregation must be 'fp32' or 'bf16', got %r" % (self.aggregation,))
             cost = ops.cost_volume_concat(lfeat, rfeat, D)
 
         cost0 = self._cg(self.dres0[0], cost, relu=True)
