@@ -90,7 +90,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 
 // ---- the kernel -------------------------------------------------------------------------------------
 template <int CIN, int COUT, int BD, int NS>
-__global__ void __launch_bounds__(kIgThreads, 1)
+__global__ void __launch_bounds__(kIgThreads, 2)
     conv3d_igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ wpk,
                              __nv_bfloat16* __restrict__ y, double* __restrict__ gn_sums, int D, int H, int W,
                              int tiles_w) {
