@@ -156,6 +156,8 @@ def run_ours(args, rank, world, local_rank):
     torch.manual_seed(0)
     model = get_model("cmfsm").to(dev).eval()
     model.aggregation = args.aggregation
+    if args.cuda_graph:
+        model.enable_cuda_graph(True)
     left_h, right_h = (t.pin_memory() for t in synthetic_pair(1 + rank))
     left_d, right_d = left_h.to(dev), right_h.to(dev)
 
@@ -271,6 +273,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--aggregation", default="fp32", choices=("fp32", "bf16"),
                     help="3-D aggregation arithmetic: fp32 FMA (BASELINE config 2, default) or bf16 tcgen05")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay the forward as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~30 s CPU oracle timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -42,12 +42,13 @@ class _timed:
         self.name = name
 
     def __enter__(self):
-        if _TIMING is not None:
+        self.on = _TIMING is not None and not torch.cuda.is_current_stream_capturing()
+        if self.on:
             self.a = torch.cuda.Event(enable_timing=True)
             self.a.record()
 
     def __exit__(self, *exc):
-        if _TIMING is not None:
+        if self.on:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
             _TIMING.append((self.name, self.a, b))

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 // consecutive output columns (4 input columns).
 // ------------------------------------------------------------------------------------------------
 template <int COUT, int CPT, int CC>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
     deconv3d_k3s2_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
                          double* __restrict__ gn_sums, int Cin, int D, int H, int W, int tiles_w) {
     using T = ConvTile<COUT, CPT>;
@@ -205,12 +205,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     constexpr int PD = 2, PH = T::TH + 1, PW = kTW + 1;
     constexpr int PWP = (PW + 3) & ~3;  // 36
     constexpr int PATCH = PD * PH * PWP;
-    constexpr int WSL = 27 * COUT;
-    constexpr int NO = 2 * kVPT;  // output columns per thread
+    constexpr int WSL = 12 * COUT;  // at most 2 x 2 (d,h) tap pairs x 3 w taps are live for one parity class
+    constexpr int NO = 2 * kVPT;    // output columns per thread
+    constexpr int NSLOT = (PD * PH * PW + kConvThreads - 1) / kConvThreads;
+    constexpr int STAGE = CC * (PATCH + WSL);
 
-    extern __shared__ __align__(16) float smem[];
-    float* sIn = smem;
-    float* sW = smem + CC * PATCH;
+    extern __shared__ __align__(16) float smem[];  // 2 stages of [CC][2][PH][PWP] + [CC][nd*nh*3][COUT]
 
     const int tile_x = blockIdx.x % tiles_w, tile_y = blockIdx.x / tiles_w;
     const int iw0 = tile_x * kTW, ih0 = tile_y * T::TH;
@@ -233,42 +233,83 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     const size_t in_vol = (size_t)D * in_plane;
     const float* xb = x + (size_t)b * Cin * in_vol;
     const int nd = pd ? 2 : 1, nh = ph ? 2 : 1;
+    const int ntap = nd * nh * 3;  // live taps of this parity class
 
-    for (int c0 = 0; c0 < Cin; c0 += CC) {
-        __syncthreads();
-        for (int i = tid; i < CC * PD * PH * PW; i += kConvThreads) {
-            const int pw = i % PW;
-            int r = i / PW;
-            const int phh = r % PH;
-            r /= PH;
-            const int pdd = r % PD, ci = r / PD;
-            const int di = id + pdd, hi = ih0 + phh, wi = iw0 + pw;
-            float v = 0.f;
-            if (di < D && hi < H && wi < W)
-                v = __ldg(xb + (size_t)(c0 + ci) * in_vol + (size_t)di * in_plane + (size_t)hi * W + wi);
-            sIn[((ci * PD + pdd) * PH + phh) * PWP + pw] = v;
+    int goff[NSLOT], soff[NSLOT];
+    bool ok[NSLOT];
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) {
+        const int e = tid + j * kConvThreads;
+        const int pw = e % PW;
+        const int r = e / PW;
+        const int phh = r % PH, pdd = r / PH;
+        const int di = id + pdd, hi = ih0 + phh, wi = iw0 + pw;
+        const bool in_patch = e < PD * PH * PW;
+        ok[j] = in_patch && di < D && hi < H && wi < W;
+        goff[j] = ok[j] ? (di * H + hi) * W + wi : 0;
+        soff[j] = in_patch ? (pdd * PH + phh) * PWP + pw : -1;
+    }
+
+    auto stage = [&](int c0, int buf) {
+        float* sIn = smem + buf * STAGE;
+        float* sW = sIn + CC * PATCH;
+#pragma unroll
+        for (int ci = 0; ci < CC; ++ci) {
+            const float* src = xb + (size_t)(c0 + ci) * in_vol;
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j)
+                if (soff[j] >= 0) cp_async_4_zfill(sIn + ci * PATCH + soff[j], src + goff[j], ok[j]);
         }
-        {
-            const float* wsrc = wp + (size_t)c0 * WSL;
-            for (int i = tid * 4; i < CC * WSL; i += kConvThreads * 4)
-                *reinterpret_cast<float4*>(sW + i) = __ldg(reinterpret_cast<const float4*>(wsrc + i));
+        // live weight rows only: [ci][jd][jh][kw][COUT]; parity 0 uses tap k=1, parity 1 taps k=2 (j=0) and k=0 (j=1)
+        constexpr int ROW4 = COUT / 4;
+        for (int i = tid; i < CC * ntap * ROW4; i += kConvThreads) {
+            const int j4 = i % ROW4;
+            int r = i / ROW4;
+            const int kw = r % 3;
+            r /= 3;
+            const int jh = r % nh;
+            r /= nh;
+            const int jd = r % nd, ci = r / nd;
+            const int kd = pd ? (jd == 0 ? 2 : 0) : 1, kh = ph ? (jh == 0 ? 2 : 0) : 1;
+            cp_async_16(sW + ci * WSL + ((jd * nh + jh) * 3 + kw) * COUT + j4 * 4,
+                        wp + ((size_t)(c0 + ci) * 27 + (kd * 3 + kh) * 3 + kw) * COUT + j4 * 4);
+        }
+        cp_async_commit();
+    };
+
+    // zero the alignment tail of every patch row once
+    for (int i = tid; i < 2 * CC * PD * PH * (PWP - PW); i += kConvThreads) {
+        const int t = i % (PWP - PW);
+        const int r = i / (PWP - PW);
+        const int prow = r % (PD * PH), ci = (r / (PD * PH)) % CC, buf = r / (PD * PH * CC);
+        smem[buf * STAGE + ci * PATCH + prow * PWP + PW + t] = 0.f;
+    }
+
+    const int nchunks = Cin / CC;
+    stage(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) {
+            stage((ch + 1) * CC, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        const float* sIn = smem + buf * STAGE;
+        const float* sW = sIn + CC * PATCH;
 #pragma unroll 1
         for (int ci = 0; ci < CC; ++ci) {
             const float* pin = sIn + ci * PATCH + th * PWP + qx * kVPT;
             const float* pw_ = sW + ci * WSL + cg * CPT;
 #pragma unroll 1
             for (int jd = 0; jd < nd; ++jd) {
-                // parity 0: (k=1, +0) ; parity 1: jd=0 -> (k=2, +0), jd=1 -> (k=0, +1)
-                const int kd = pd ? (jd == 0 ? 2 : 0) : 1;
 #pragma unroll 1
                 for (int jh = 0; jh < nh; ++jh) {
-                    const int kh = ph ? (jh == 0 ? 2 : 0) : 1;
                     const float* prow = pin + (jd * PH + jh) * PWP;
                     const float4 a = *reinterpret_cast<const float4*>(prow);
                     const float in[5] = {a.x, a.y, a.z, a.w, prow[4]};
-                    const float* wt = pw_ + (kd * 3 + kh) * 3 * COUT;
+                    const float* wt = pw_ + (jd * nh + jh) * 3 * COUT;
                     float wk[3][CPT];
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
@@ -289,6 +330,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
                 }
             }
         }
+        __syncthreads();
     }
 
     const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
@@ -358,7 +400,8 @@ template <int COUT, int CPT, int CC>
 static int launch_deconv(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
                          cudaStream_t st) {
     using T = ConvTile<COUT, CPT>;
-    constexpr size_t smem = (size_t)CC * (2 * (T::TH + 1) * 36 + 27 * COUT) * sizeof(float);
+    constexpr size_t smem = 2 * (size_t)CC * (2 * (T::TH + 1) * 36 + 12 * COUT) * sizeof(float);
+    static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
     const int tiles_w = (int)cdiv(W, kTW), tiles_h = (int)cdiv(H, T::TH);
     auto kern = deconv3d_k3s2_kernel<COUT, CPT, CC>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

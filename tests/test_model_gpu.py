@@ -82,6 +82,26 @@ def test_forward_vs_cpu_oracle_structured_pair(model):
         assert float(ours.mean()) <= 2 * float(theirs.mean()) + 1e-4, (i, float(ours.mean()), float(theirs.mean()))
 
 
+def test_cuda_graph_replay_matches_eager(model):
+    """enable_cuda_graph(): replayed forward == eager forward, also after the inputs change."""
+    left, right = gc.seeded_pair(1, 256, 512, seed=11)
+    left, right = left.to(DEV), right.to(DEV)
+    with torch.no_grad():
+        eager = model(left, right)
+        model.enable_cuda_graph(True)
+        try:
+            first = model(left, right)
+            l2, r2 = right.clone(), left.clone()
+            model(l2, r2)  # different inputs through the same graph
+            again = model(left, right)
+        finally:
+            model.enable_cuda_graph(False)
+    for a, b, c in zip(eager, first, again):
+        # GroupNorm statistics use double atomics whose order is not fixed: allow the last-bit noise floor
+        torch.testing.assert_close(a, b, rtol=0, atol=5e-3)
+        torch.testing.assert_close(b, c, rtol=0, atol=5e-3)
+
+
 def test_bf16_aggregation_mode(model):
     """bf16-operand / fp32-accumulate 3-D aggregation (tcgen05 implicit GEMM) vs the fp32 CUDA path.
 
