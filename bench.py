@@ -14,7 +14,8 @@ and the max over ranks is reported.  Prints ONE JSON line on rank 0.
             H2D copy of both images and the D2H read of the cropped disparity every step
   roofline  K1 cost-volume kernel (the kernel BASELINE.json's metric names): algorithmic bytes / CUDA-event
             launch duration vs the measured HBM peak of MEASURED_PEAKS.json
-  kernels   per-kernel share of the step (CUDA events on the launching stream, same timed region)
+  kernels   per-kernel share of the step: the same K steps are repeated kernel-by-kernel (no graph) with a CUDA
+            event pair around every launch on the launching stream; `roofline` uses those durations
   cpu_baseline  the CPU oracle port of the reference forward timed on this box's host cores (rank 0, N=1)
 
 `--impl reference` times the reference's own CPU path (the oracle port: the reference is pure Python and
@@ -156,8 +157,8 @@ def run_ours(args, rank, world, local_rank):
     torch.manual_seed(0)
     model = get_model("cmfsm").to(dev).eval()
     model.aggregation = args.aggregation
-    if args.cuda_graph:
-        model.enable_cuda_graph(True)
+    use_graph = not args.no_cuda_graph
+    model.enable_cuda_graph(use_graph)
     left_h, right_h = (t.pin_memory() for t in synthetic_pair(1 + rank))
     left_d, right_d = left_h.to(dev), right_h.to(dev)
 
@@ -175,10 +176,9 @@ def run_ours(args, rank, world, local_rank):
         step_device()
     barrier()
 
-    # ---------------- timed region: K steps, device-resident inputs, per-kernel events on the same stream
+    # ---------------- timed region: K steps, device-resident inputs (one CUDA-graph replay per step by default)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ops.enable_event_timing(True)
     n0 = lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -187,13 +187,28 @@ def run_ours(args, rank, world, local_rank):
         out = step_device()
     e1.record()
     barrier()
-    launches = lib.launch_count() - n0
     ms_total = e0.elapsed_time(e1)
-    kernels = ops.drain_event_timing()
-    ops.enable_event_timing(False)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     assert tuple(out.shape) == (1, 1, H_IMG, W_IMG) and bool(torch.isfinite(out).all())
+
+    # ---------------- same K steps launched kernel by kernel with a CUDA event pair around every launch (on the
+    # launching stream): per-kernel durations for the roofline / share report and the launch count
+    model.enable_cuda_graph(False)
+    ops.enable_event_timing(True)
+    n0 = lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    launches = (lib.launch_count() - n0) // args.steps
+    ms_eager = ev0.elapsed_time(ev1)
+    kernels = ops.drain_event_timing()
+    ops.enable_event_timing(False)
+    model.enable_cuda_graph(use_graph)
 
     # ---------------- end-to-end: pinned host inputs -> H2D -> forward -> D2H, every step
     for _ in range(2):
@@ -221,7 +236,7 @@ def run_ours(args, rank, world, local_rank):
         k1_n, k1_ms = kernels.get(k1_name, (0, 0.0))
         k1_gbs = (k1_bytes * k1_n / (k1_ms * 1e-3) / 1e9) if k1_ms > 0 else None
         share = {k: {"launches": n // args.steps, "ms_per_step": ms / args.steps,
-                     "share": ms / ms_total} for k, (n, ms) in sorted(kernels.items())}
+                     "share": ms / ms_eager} for k, (n, ms) in sorted(kernels.items())}
         precision = ("fp32 FMA 3-D aggregation (parity mode)" if args.aggregation == "fp32" else
                      "bf16-operand/fp32-accumulate tcgen05 implicit-GEMM 3-D aggregation (stride-1 convs)")
         ig_n, ig_ms = kernels.get("conv3d_igemm_bf16_fwd", (0, 0.0))
@@ -237,7 +252,10 @@ def run_ours(args, rank, world, local_rank):
                            "precision": precision + "; fp32 FMA 2-D features, K1/K4/K5 fp32"},
                 "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "pairs/s",
                         "h2d_bytes_per_step": 2 * 3 * H_PAD * W_IMG * 4, "d2h_bytes_per_step": H_IMG * W_IMG * 4},
-                "gpu_launches": int(launches),
+                "gpu_launches": int(launches) * args.steps,
+                "launch_mode": {"timed_region": "one CUDA-graph replay per step (%d kernel nodes of libcmfb200 + ATen "
+                                                "pool/upsample/cat nodes)" % launches if use_graph else "eager launches",
+                                "ms_per_step_eager_with_events": ms_eager / args.steps},
                 "roofline": {"kernel": k1_name + " (K1)", "bound": "hbm", "achieved": k1_gbs,
                              "peak": hbm_peak, "unit": "GB/s", "frac": (k1_gbs / hbm_peak) if k1_gbs else None,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
@@ -273,7 +291,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--aggregation", default="fp32", choices=("fp32", "bf16"),
                     help="3-D aggregation arithmetic: fp32 FMA (BASELINE config 2, default) or bf16 tcgen05")
-    ap.add_argument("--cuda-graph", action="store_true", help="replay the forward as one CUDA graph")
+    ap.add_argument("--no-cuda-graph", action="store_true",
+                    help="launch the ~900 kernels of a forward one by one instead of replaying one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~30 s CPU oracle timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

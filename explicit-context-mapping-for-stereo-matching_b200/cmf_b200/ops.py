@@ -304,6 +304,42 @@ def conv3d_igemm(x, packed, want_stats=True):
     return y, sums
 
 
+def deconv3d_igemm(x, packed, want_stats=True):
+    """tcgen05 transposed conv (k3 s2 p1 op1) on C8/bf16: [B,Cin/8,D,H,W,8] -> [B,Cout/8,2D,2H,2W,8]."""
+    _req(x, packed, dtype=BF16)
+    B, NC, D, H, W, _ = x.shape
+    Cin, Cout = NC * 8, packed.shape[2]
+    y = torch.empty((B, Cout // 8, 2 * D, 2 * H, 2 * W, 8), device=x.device, dtype=BF16)
+    sums = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    with torch.cuda.device(x.device), _timed("deconv3d_igemm_bf16_fwd"):
+        _lib.check(_lib.load().cmfb200_deconv3d_igemm_bf16_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W,
+                                                               _stream()), "deconv3d_igemm_bf16_fwd")
+    return y, sums
+
+
+def c8_parity_split(x):
+    """C8 [B,C/8,D,H,W,8] -> parity-split [B,8,C/8,D/2,H/2,W/2,8] (input format of the stride-2 igemm)."""
+    _req(x, dtype=BF16)
+    B, NC, D, H, W, _ = x.shape
+    y = torch.empty((B, 8, NC, D // 2, H // 2, W // 2, 8), device=x.device, dtype=BF16)
+    with torch.cuda.device(x.device), _timed("c8_parity_split"):
+        _lib.check(_lib.load().cmfb200_c8_parity_split(_p(x), _p(y), B, NC * 8, D, H, W, _stream()), "c8_parity_split")
+    return y
+
+
+def conv3d_s2_igemm(x_split, packed, want_stats=True):
+    """tcgen05 stride-2 conv on the parity-split input: -> [B,Cout/8,D/2,H/2,W/2,8]."""
+    _req(x_split, packed, dtype=BF16)
+    B, _, NC, Do, Ho, Wo, _ = x_split.shape
+    Cin, Cout = NC * 8, packed.shape[2]
+    y = torch.empty((B, Cout // 8, Do, Ho, Wo, 8), device=x_split.device, dtype=BF16)
+    sums = torch.zeros((B, Cout, 2), device=x_split.device, dtype=torch.float64) if want_stats else None
+    with torch.cuda.device(x_split.device), _timed("conv3d_s2_igemm_bf16_fwd"):
+        _lib.check(_lib.load().cmfb200_conv3d_s2_igemm_bf16_fwd(_p(x_split), _p(packed), _p(y), _p(sums), B, Cin, Cout, Do,
+                                                                Ho, Wo, _stream()), "conv3d_s2_igemm_bf16_fwd")
+    return y, sums
+
+
 def gn_apply_c8(x, sums, gamma, beta, residual=None, relu=False, out=None, groups=GN_GROUPS, eps=GN_EPS):
     gamma, beta = gamma.detach(), beta.detach()
     _req(gamma, beta)

@@ -79,6 +79,16 @@ int cmfb200_pack_igemm_weight_bf16(const float* weight, void* packed, int Cout, 
  * double buffer receiving sum / sum of squares of the stored (rounded) values, or NULL. */
 int cmfb200_conv3d_igemm_bf16_fwd(const void* x_c8, const void* packed_w, void* y_c8, double* gn_sums,
                                   int B, int Cin, int Cout, int D, int H, int W, void* stream);
+/* Transposed conv k3 s2 p1 op1 on tensor cores: x_c8 [B][Cin/8][D][H][W][8] -> y_c8 [B][Cout/8][2D][2H][2W][8];
+ * packed_w from cmfb200_pack_igemm_weight_bf16(transposed=1).  (Cin,Cout) in {(64,64),(64,32)}. */
+int cmfb200_deconv3d_igemm_bf16_fwd(const void* x_c8, const void* packed_w, void* y_c8, double* gn_sums,
+                                    int B, int Cin, int Cout, int D, int H, int W, void* stream);
+/* Stride-2 conv k3 p1 on tensor cores.  The input is the PARITY-SPLIT copy of the C8 tensor,
+ * [B][8][Cin/8][D/2][H/2][W/2][8] with parity index (d&1)*4+(h&1)*2+(w&1) (cmfb200_c8_parity_split); the output
+ * is plain C8 [B][Cout/8][Do][Ho][Wo][8] with Do=D/2 etc.  (Cin,Cout) in {(32,64),(64,64)}. */
+int cmfb200_conv3d_s2_igemm_bf16_fwd(const void* x_split_c8, const void* packed_w, void* y_c8, double* gn_sums,
+                                     int B, int Cin, int Cout, int Do, int Ho, int Wo, void* stream);
+int cmfb200_c8_parity_split(const void* x_c8, void* y_split_c8, int B, int C, int D, int H, int W, void* stream);
 /* K1 in C8/bf16: same contract as cmfb200_cost_volume_concat_fwd, output [B][2C/8][D][h][w][8] bf16
  * (channel groups 0..C/8-1 = masked left features, C/8.. = shifted right features). */
 int cmfb200_cost_volume_concat_c8_bf16(const float* L, const float* R, void* cost_c8,

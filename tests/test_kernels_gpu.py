@@ -343,3 +343,40 @@ def test_gn_apply_c8_vs_oracle():
     xs = xq.to(DEV)
     got = ops.gn_apply_c8(ops.f32_to_c8(xs), ops.gn_stats(xs), gamma.to(DEV), beta.to(DEV), ops.f32_to_c8(rq.to(DEV)), True)
     assert _rel_l2(ops.c8_to_f32(got), want) < 3e-3
+
+
+@pytest.mark.parametrize("B,Cout,D,H,W", [(1, 64, 2, 16, 8), (2, 32, 3, 10, 12), (1, 64, 3, 18, 20), (1, 32, 5, 33, 9)])
+def test_deconv3d_igemm_tcgen05_vs_oracle(B, Cout, D, H, W):
+    from cmf_b200 import ops
+
+    x = _rand(B, 64, D, H, W, seed=90)
+    wgt = _rand(64, Cout, 3, 3, 3, seed=91) * 0.05
+    xq, wq = x.to(torch.bfloat16).double(), wgt.to(torch.bfloat16).double()
+    want = F.conv_transpose3d(xq, wq, None, stride=2, padding=1, output_padding=1)
+    y, sums = ops.deconv3d_igemm(ops.f32_to_c8(x.to(DEV)), ops.pack_igemm_weight(wgt.to(DEV), transposed=True))
+    torch.cuda.synchronize()
+    got = ops.c8_to_f32(y).cpu().double()
+    assert got.shape == want.shape
+    err = _rel_l2(got, want)
+    print("deconv igemm %s rel-L2 %.3e" % ((B, Cout, D, H, W), err))
+    assert err < 3e-3
+    torch.testing.assert_close(sums.cpu()[..., 0], got.sum((2, 3, 4)), rtol=1e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,Cin,D,H,W", [(1, 32, 4, 32, 16), (2, 64, 4, 20, 24), (1, 32, 6, 36, 44), (1, 64, 10, 66, 18)])
+def test_conv3d_s2_igemm_tcgen05_vs_oracle(B, Cin, D, H, W):
+    from cmf_b200 import ops
+
+    x = _rand(B, Cin, D, H, W, seed=92)
+    wgt = _rand(64, Cin, 3, 3, 3, seed=93) * (2.0 / (27 * Cin)) ** 0.5
+    xq, wq = x.to(torch.bfloat16).double(), wgt.to(torch.bfloat16).double()
+    want = F.conv3d(xq, wq, None, 2, 1)
+    xs = ops.c8_parity_split(ops.f32_to_c8(x.to(DEV)))
+    y, sums = ops.conv3d_s2_igemm(xs, ops.pack_igemm_weight(wgt.to(DEV)))
+    torch.cuda.synchronize()
+    got = ops.c8_to_f32(y).cpu().double()
+    assert got.shape == want.shape
+    err = _rel_l2(got, want)
+    print("s2 igemm %s rel-L2 %.3e" % ((B, Cin, D, H, W), err))
+    assert err < 3e-3
+    torch.testing.assert_close(sums.cpu()[..., 1], (got * got).sum((2, 3, 4)), rtol=1e-6, atol=1e-3)
