@@ -203,10 +203,11 @@ struct S2Cfg {
     static constexpr int PD = BD + 1;
     static constexpr int VOX = PD * kS2PH * kS2PW;
     static constexpr int CHUNK_BYTES = VOX * 16;
-    static constexpr int STAGE_BYTES = NC * CHUNK_BYTES;
+    static constexpr int STAGE_BYTES = NC * CHUNK_BYTES;               // bytes moved by one TMA box
+    static constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) & ~127;    // TMA shared-memory destinations: 128-byte aligned
     static constexpr int TAP_BYTES = CIN * COUT * 2;
     static constexpr int TMEM_COLS = (BD * COUT <= 64) ? 64 : (BD * COUT <= 128) ? 128 : (BD * COUT <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = NSA * STAGE_BYTES + NS * TAP_BYTES + 1024 + 4 * COUT * 2 * 8 + 1024;
+    static constexpr int SMEM_BYTES = NSA * STAGE_STRIDE + NS * TAP_BYTES + 1024 + 4 * COUT * 2 * 8 + 1024;
 };
 
 // taps that read input parity p along one axis: p=0 -> {k=1}; p=1 -> {k=0, k=2}
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
-    uint8_t* sW = smem + NSA * G::STAGE_BYTES;
+    uint8_t* sW = smem + NSA * G::STAGE_STRIDE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + NS * G::TAP_BYTES);
     uint64_t* barD = bars;
     uint64_t* fullW = bars + 1;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
                 const int sa = par % NSA;
                 if (par >= NSA) mbar_wait(emptyA + sa, ((par / NSA) - 1) & 1);
                 mbar_arrive_expect_tx(fullA + sa, G::STAGE_BYTES);
-                tma_load_5d(sA + sa * G::STAGE_BYTES, &tmap_xs, fullA + sa, (w0 - 1) * 8, h0 - 1, d0 - 1, par * G::NC, b);
+                tma_load_5d(sA + sa * G::STAGE_STRIDE, &tmap_xs, fullA + sa, (w0 - 1) * 8, h0 - 1, d0 - 1, par * G::NC, b);
                 const int pd = par >> 2, ph = (par >> 1) & 1, pw = par & 1;
                 for (int jd = 0; jd < s2_ntaps(pd); ++jd)
                     for (int jh = 0; jh < s2_ntaps(ph); ++jh)
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
             int t = 0;
             for (int par = 0; par < 8; ++par) {
                 const int sa = par % NSA;
-                const uint32_t a0 = a_base + sa * G::STAGE_BYTES;
+                const uint32_t a0 = a_base + sa * G::STAGE_STRIDE;
                 mbar_wait(fullA + sa, (par / NSA) & 1);
                 tc_fence_after();
                 const int pd = par >> 2, ph = (par >> 1) & 1, pw = par & 1;
