@@ -238,10 +238,17 @@ def run_ours(args, rank, world, local_rank):
         share = {k: {"launches": n // args.steps, "ms_per_step": ms / args.steps,
                      "share": ms / ms_eager} for k, (n, ms) in sorted(kernels.items())}
         precision = ("fp32 FMA 3-D aggregation (parity mode)" if args.aggregation == "fp32" else
-                     "bf16-operand/fp32-accumulate tcgen05 implicit-GEMM 3-D aggregation (stride-1 convs)")
-        ig_n, ig_ms = kernels.get("conv3d_igemm_bf16_fwd", (0, 0.0))
+                     "bf16-operand/fp32-accumulate tcgen05 implicit-GEMM 3-D aggregation (25 of 28 layers; the 32->1 classifier convs on CUDA cores)")
+        ig_n, ig_ms = 0, 0.0
+        for name in ("conv3d_igemm_bf16_fwd", "conv3d_s2_igemm_bf16_fwd", "deconv3d_igemm_bf16_fwd"):
+            n_, ms_ = kernels.get(name, (0, 0.0))
+            ig_n, ig_ms = ig_n + n_, ig_ms + ms_
         vox = D * h * w
-        ig_macs = 27 * (vox * (64 * 32 + 6 * 32 * 32) + 3 * (vox // 8) * 64 * 64 + 3 * (vox // 64) * 64 * 64)
+        # stride-1 convs (dres0/1, conv2, conv4, classif.0) + per hourglass conv1/conv3 (stride 2) and
+        # conv5/conv6 (transposed) = every 3-D layer except the three 32->1 classifier convs
+        ig_macs = 27 * (vox * (64 * 32 + 6 * 32 * 32) + 3 * (vox // 8) * 64 * 64 + 3 * (vox // 64) * 64 * 64
+                        + 3 * ((vox // 8) * 32 * 64 + (vox // 64) * 64 * 64)      # conv1, conv3
+                        + 3 * ((vox // 64) * 64 * 64 + (vox // 8) * 64 * 32))     # conv5, conv6
         line = {"metric": METRIC, "value": world * args.steps / (ms_total * 1e-3), "unit": "pairs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -266,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
                 os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
             tpeak = float(pk.get("bf16_tflops_sustained", 1400.0))
             tf = 2.0 * ig_macs * args.steps / (ig_ms * 1e-3) / 1e12
-            line["roofline_k2"] = {"kernel": "conv3d_igemm_bf16_kernel (K2, %d launches/step)" % (ig_n // args.steps),
+            line["roofline_k2"] = {"kernel": "tcgen05 implicit-GEMM kernels conv3d/conv3d_s2/deconv3d_igemm_bf16 (K2, %d launches/step)" % (ig_n // args.steps),
                                    "bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
                                    "frac": tf / tpeak, "traffic": None,
                                    "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json" if pk else "fallback",

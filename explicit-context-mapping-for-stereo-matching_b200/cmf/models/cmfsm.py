@@ -230,32 +230,37 @@ class cmfsm(nn.Module):
         feat, _ = self._c2(fe.lastconv[2], o, False)
         return feat, full
 
-    # ---- bf16 aggregation: tcgen05 implicit GEMM on the C8 layout (stride-1 convs); the stride-2 convs and the
-    # transposed convs (16 % of the MACs) still run on the fp32 kernels through layout converters (round 1).
+    # ---- bf16 aggregation: every 3x3x3 conv / strided conv / transposed conv of the 3-D network is a tcgen05
+    # implicit GEMM on the C8 layout; only the three 32->1 classifier convs (N=1: no tensor-core shape) run on the
+    # CUDA cores.
     def _pack_ig(self, conv):
         w = conv.weight
         key = (conv._cmf_name, w.device.index, "ig")
         hit = self._packed.get(key)
         if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
             return hit[2]
-        packed = ops.pack_igemm_weight(w)
+        packed = ops.pack_igemm_weight(w, transposed=isinstance(conv, nn.ConvTranspose3d))
         self._packed[key] = (w._version, w.data_ptr(), packed)
         return packed
 
     def _ig(self, block, x, residual=None, relu=False):
-        y, sums = ops.conv3d_igemm(x, self._pack_ig(block[0]))
+        conv = block[0]
+        if isinstance(conv, nn.ConvTranspose3d):
+            y, sums = ops.deconv3d_igemm(x, self._pack_ig(conv))
+        elif conv.stride[0] == 2:
+            y, sums = ops.conv3d_s2_igemm(ops.c8_parity_split(x), self._pack_ig(conv))
+        else:
+            y, sums = ops.conv3d_igemm(x, self._pack_ig(conv))
         return ops.gn_apply_c8(y, sums, block[1].weight, block[1].bias, residual, relu, out=y)
 
-    def _hourglass_bf16(self, hg, x, x32, presqu, postsqu, resid32):
-        o = ops.f32_to_c8(self._cg(hg.conv1[0], x32, 2, relu=True))
-        pre = self._ig(hg.conv2, o, residual=postsqu, relu=True)
-        pre32 = ops.c8_to_f32(pre)
-        o = ops.f32_to_c8(self._cg(hg.conv3[0], pre32, 2, relu=True))
-        o32 = ops.c8_to_f32(self._ig(hg.conv4[0], o, relu=True))
-        skip32 = ops.c8_to_f32(presqu) if presqu is not None else pre32
-        post32 = self._cg(hg.conv5, o32, residual=skip32, relu=True)
-        out32 = self._cg(hg.conv6, post32, residual=resid32, relu=False)
-        return ops.f32_to_c8(out32), out32, pre, ops.f32_to_c8(post32)
+    def _hourglass_bf16(self, hg, x, presqu, postsqu, resid):
+        out = self._ig(hg.conv1[0], x, relu=True)
+        pre = self._ig(hg.conv2, out, residual=postsqu, relu=True)
+        out = self._ig(hg.conv3[0], pre, relu=True)
+        out = self._ig(hg.conv4[0], out, relu=True)
+        post = self._ig(hg.conv5, out, residual=presqu if presqu is not None else pre, relu=True)
+        out = self._ig(hg.conv6, post, residual=resid, relu=False)
+        return out, pre, post
 
     def _classify_bf16(self, head, x):
         t32 = ops.c8_to_f32(self._ig(head[0], x, relu=True))
@@ -269,10 +274,9 @@ class cmfsm(nn.Module):
         cost0 = self._ig(self.dres0[2], cost0, relu=True)
         t = self._ig(self.dres1[0], cost0, relu=True)
         cost0 = self._ig(self.dres1[2], t, residual=cost0)
-        cost0_32 = ops.c8_to_f32(cost0)
-        out1, out1_32, pre1, post1 = self._hourglass_bf16(self.dres2, cost0, cost0_32, None, None, cost0_32)
-        out2, out2_32, _pre2, post2 = self._hourglass_bf16(self.dres3, out1, out1_32, pre1, post1, cost0_32)
-        out3, _o3, _pre3, _post3 = self._hourglass_bf16(self.dres4, out2, out2_32, pre1, post2, cost0_32)
+        out1, pre1, post1 = self._hourglass_bf16(self.dres2, cost0, None, None, cost0)
+        out2, _pre2, post2 = self._hourglass_bf16(self.dres3, out1, pre1, post1, cost0)
+        out3, _pre3, _post3 = self._hourglass_bf16(self.dres4, out2, pre1, post2, cost0)
         return (self._classify_bf16(self.classif1, out1), self._classify_bf16(self.classif2, out2),
                 self._classify_bf16(self.classif3, out3))
 
