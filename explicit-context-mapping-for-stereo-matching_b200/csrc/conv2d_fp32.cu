@@ -175,6 +175,192 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     if (gn_sums != nullptr) gn_epilogue<COUT_TILE, CPT>(s, ss, cg, smem, gn_sums, b, Cout, cb);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3x3 stride-1 (dilation 1 or 2) with TWO output rows per thread: rows r and r+DIL share the four input rows
+// r + {0,1,2,3}*DIL, so per input channel a thread issues 8 vector loads of input + 18 broadcast loads of weights
+// for 576 FMAs (1:22 instead of 1:12) -- these layers carry 80 % of the feature extractor's MACs.
+// ------------------------------------------------------------------------------------------------
+template <int DIL, int COUT_TILE>
+struct Conv2dR2Cfg {
+    static constexpr int CPT = 8;
+    static constexpr int NCG = COUT_TILE / CPT;
+    static constexpr int NQ = kConvThreads / NCG;
+    static constexpr int TROWS = NQ / (kTW / kVPT);  // thread rows
+    static constexpr int TH = 2 * TROWS;             // output rows per CTA
+    static constexpr int PH = TH + 2 * DIL;
+    static constexpr int PW = kTW + 2 * DIL;
+    static constexpr int PWP = (PW + 3) & ~3;
+    static constexpr int PATCH = PH * PWP;
+    static constexpr int NI4 = (kVPT + 2 * DIL + 3) / 4;  // 2
+    static constexpr int NSLOT = (PH * PW + kConvThreads - 1) / kConvThreads;
+    static constexpr int WSL = 9 * COUT_TILE;
+    static_assert(TROWS % DIL == 0, "row pairing needs TROWS to be a multiple of the dilation");
+    static_assert((kTW / kVPT - 1) * kVPT + NI4 * 4 <= PWP, "vector over-read leaves the patch row");
+};
+
+template <int DIL, int COUT_TILE, int CC>
+__global__ void __launch_bounds__(kConvThreads, 2)
+    conv2d_r2_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
+                     double* __restrict__ gn_sums, int Cin, int Cout, int H, int W, int tiles_w) {
+    using G = Conv2dR2Cfg<DIL, COUT_TILE>;
+    constexpr int CPT = G::CPT;
+    constexpr int STAGE = CC * (G::PATCH + G::WSL);
+    extern __shared__ __align__(16) float smem[];
+
+    const int tile_x = blockIdx.x % tiles_w, tile_y = blockIdx.x / tiles_w;
+    const int w0 = tile_x * kTW, h0 = tile_y * G::TH;
+    const int cb = blockIdx.y * COUT_TILE;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int cg = tid / G::NQ;
+    const int q = tid % G::NQ;
+    const int qx = q % (kTW / kVPT);
+    const int tr = q / (kTW / kVPT);
+    const int r0 = (tr / DIL) * 2 * DIL + (tr % DIL);  // first output row of this thread (tile-relative); second = r0+DIL
+
+    int goff[G::NSLOT], soff[G::NSLOT];
+    bool ok[G::NSLOT];
+    const int hi0 = h0 - DIL, wi0 = w0 - DIL;
+#pragma unroll
+    for (int j = 0; j < G::NSLOT; ++j) {
+        const int e = tid + j * kConvThreads;
+        const int ph = e / G::PW, pw = e - ph * G::PW;
+        const int hi = hi0 + ph, wi = wi0 + pw;
+        const bool in_patch = e < G::PH * G::PW;
+        ok[j] = in_patch && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
+        goff[j] = ok[j] ? hi * W + wi : 0;
+        soff[j] = in_patch ? ph * G::PWP + pw : -1;
+    }
+    const size_t in_plane = (size_t)H * W;
+    const float* xb = x + (size_t)b * Cin * in_plane;
+
+    auto stage = [&](int c0, int buf) {
+        float* sIn = smem + buf * STAGE;
+        float* sW = sIn + CC * G::PATCH;
+#pragma unroll
+        for (int ci = 0; ci < CC; ++ci) {
+            const float* src = xb + (size_t)(c0 + ci) * in_plane;
+#pragma unroll
+            for (int j = 0; j < G::NSLOT; ++j)
+                if (soff[j] >= 0) cp_async_4_zfill(sIn + ci * G::PATCH + soff[j], src + goff[j], ok[j]);
+        }
+        constexpr int ROW4 = COUT_TILE / 4;
+        for (int i = tid; i < CC * 9 * ROW4; i += kConvThreads) {
+            const int r = i / ROW4, j4 = i - r * ROW4;
+            cp_async_16(sW + r * COUT_TILE + j4 * 4, wp + ((size_t)c0 * 9 + r) * Cout + cb + j4 * 4);
+        }
+        cp_async_commit();
+    };
+
+    float acc[2][CPT][kVPT];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+#pragma unroll
+            for (int v = 0; v < kVPT; ++v) acc[r][c][v] = 0.f;
+
+    if constexpr (G::PWP > G::PW) {
+        for (int i = tid; i < 2 * CC * G::PH * (G::PWP - G::PW); i += kConvThreads) {
+            const int t = i % (G::PWP - G::PW);
+            const int r = i / (G::PWP - G::PW);
+            const int ph = r % G::PH, ci = (r / G::PH) % CC, buf = r / (G::PH * CC);
+            smem[buf * STAGE + ci * G::PATCH + ph * G::PWP + G::PW + t] = 0.f;
+        }
+    }
+
+    const int nchunks = Cin / CC;
+    stage(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) {
+            stage((ch + 1) * CC, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float* sIn = smem + buf * STAGE;
+        const float* sW = sIn + CC * G::PATCH;
+#pragma unroll 1
+        for (int ci = 0; ci < CC; ++ci) {
+            const float* pin = sIn + ci * G::PATCH + r0 * G::PWP + qx * kVPT;
+            const float* pwt = sW + ci * G::WSL + cg * CPT;
+            float in[4][G::NI4 * 4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int k = 0; k < G::NI4; ++k) {
+                    const float4 a = *reinterpret_cast<const float4*>(pin + j * DIL * G::PWP + 4 * k);
+                    in[j][4 * k + 0] = a.x; in[j][4 * k + 1] = a.y; in[j][4 * k + 2] = a.z; in[j][4 * k + 3] = a.w;
+                }
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float* wt = pwt + (kh * 3 + kw) * COUT_TILE;
+                    const float4 w0v = *reinterpret_cast<const float4*>(wt);
+                    const float4 w1v = *reinterpret_cast<const float4*>(wt + 4);
+                    const float wv[CPT] = {w0v.x, w0v.y, w0v.z, w0v.w, w1v.x, w1v.y, w1v.z, w1v.w};
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c)
+#pragma unroll
+                        for (int v = 0; v < kVPT; ++v) {
+                            acc[0][c][v] = fmaf(wv[c], in[kh][v + kw * DIL], acc[0][c][v]);
+                            acc[1][c][v] = fmaf(wv[c], in[kh + 1][v + kw * DIL], acc[1][c][v]);
+                        }
+                }
+        }
+        __syncthreads();
+    }
+
+    const int ow = w0 + qx * kVPT;
+    const size_t out_plane = in_plane;  // stride 1, "same" padding
+    double s[CPT], ss[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        s[c] = 0.0;
+        ss[c] = 0.0;
+    }
+    const bool vec = ((W & 3) == 0);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int oh = h0 + r0 + r * DIL;
+        if (oh < H && ow < W) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int co = cb + cg * CPT + c;
+                float* py = y + ((size_t)b * Cout + co) * out_plane + (size_t)oh * W + ow;
+                if (vec) *reinterpret_cast<float4*>(py) = make_float4(acc[r][c][0], acc[r][c][1], acc[r][c][2], acc[r][c][3]);
+#pragma unroll
+                for (int v = 0; v < kVPT; ++v)
+                    if (vec || ow + v < W) {
+                        if (!vec) py[v] = acc[r][c][v];
+                        s[c] += (double)acc[r][c][v];
+                        ss[c] = fma((double)acc[r][c][v], (double)acc[r][c][v], ss[c]);
+                    }
+            }
+        }
+    }
+    if (gn_sums != nullptr) gn_epilogue<COUT_TILE, CPT>(s, ss, cg, smem, gn_sums, b, Cout, cb);
+}
+
+template <int DIL, int COUT_TILE, int CC>
+static int launch_conv2d_r2(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int Cout, int H, int W,
+                            cudaStream_t st) {
+    using G = Conv2dR2Cfg<DIL, COUT_TILE>;
+    constexpr size_t smem = 2 * (size_t)CC * (G::PATCH + G::WSL) * sizeof(float);
+    static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
+    const int tiles_w = (int)cdiv(W, kTW), tiles_h = (int)cdiv(H, G::TH);
+    auto kern = conv2d_r2_kernel<DIL, COUT_TILE, CC>;
+    CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(Cout / COUT_TILE), (unsigned)B);
+    CMF_REQUIRE(grid.z <= 65535, "conv2d: batch too large");
+    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, Cout, H, W, tiles_w);
+    CMF_LAUNCH_CHECK("conv2d_r2_kernel");
+    return CMFB200_OK;
+}
+
 // weight packing: [Cout][Cin][KS*KS] -> [Cin][KS*KS][Cout]
 __global__ void pack_conv2d_weight_kernel(const float* __restrict__ w, float* __restrict__ p, int Cout, int Cin,
                                           int taps) {
@@ -215,6 +401,10 @@ static int dispatch_conv2d(const float* x, const float* wp, float* y, double* gn
         CMF_REQUIRE(false, "conv2d: Cin=3 only for the 3x3 s1 stem conv with Cout=32");
     }
     CMF_REQUIRE(Cin % 8 == 0, "conv2d: Cin=%d must be 3 or a multiple of 8", Cin);
+    if constexpr (KS == 3 && S == 1) {  // the bulk of the MACs: two output rows per thread
+        if (Cout == 32) return launch_conv2d_r2<DIL, 32, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st);
+        if (Cout % 64 == 0) return launch_conv2d_r2<DIL, 64, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st);
+    }
     if (Cout == 32) return launch_conv2d<KS, S, DIL, 32, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st);
     if (Cout % 64 == 0) return launch_conv2d<KS, S, DIL, 64, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st);
     CMF_REQUIRE(false, "conv2d: Cout=%d must be 32 or a multiple of 64", Cout);
