@@ -21,6 +21,7 @@ import torch.nn.functional as F
 
 from cmf_b200 import ops
 from cmf_b200 import autograd_ops as aops
+from cmf_b200 import parallel as par
 
 GN_GROUPS = 32  # cmfsm.py:33
 
@@ -311,6 +312,83 @@ class cmfsm(nn.Module):
             raise ValueError("image %dx%d (B=%d) is too small for the 64x64 SPP branch + GroupNorm" % (H, W, B))
         if not left.is_cuda:
             raise ops._lib.CmfB200Error("cmfsm runs on CUDA (sm_100a) only; there is no CPU path")
+
+    # -------------------------------------------------------------------------------- row-band sharding
+    # One high-resolution pair split over the ranks of torch.distributed by rows of the 1/4-resolution volume
+    # (BASELINE config 5).  Per 3-D layer: grouped send/recv of the boundary rows at that layer's
+    # resolution + an all-reduce of the GroupNorm sums (2 doubles per channel).  fp32 aggregation.
+    def _cg_band(self, block, x, full_rows, stride=1, residual=None, relu=False):
+        """conv/deconv + GroupNorm(+residual)(+ReLU) on a row band.  `full_rows`: rows of the UN-sharded output."""
+        conv, gn = block[0], block[1]
+        packed = self._pack(conv)
+        if isinstance(conv, nn.ConvTranspose3d):  # out rows 2i, 2i+1 need input rows i, i+1: bottom halo only
+            ext = par.exchange_row_halo(x, 0, 1, dim=3)
+            y, _ = ops.conv3d_k3(ext, packed, transposed=True)
+            y = y[:, :, :, :2 * x.shape[3]].contiguous()
+        elif stride == 2:  # out row m reads input rows 2m-1..2m+1: two top halo rows re-align the padded windows
+            ext = par.exchange_row_halo(x, 2, 0, dim=3)
+            y, _ = ops.conv3d_k3(ext, packed, 2)
+            y = y[:, :, :, 1:1 + x.shape[3] // 2].contiguous()
+        else:
+            ext = par.exchange_row_halo(x, 1, 1, dim=3)
+            y, _ = ops.conv3d_k3(ext, packed, 1)
+            y = y[:, :, :, 1:-1].contiguous()
+        sums = par.allreduce_gn_sums(ops.gn_stats(y))
+        # gn_apply derives mean/var from (sums, elements of THIS tensor): rescale the global sums so that the band's
+        # element count reproduces the statistics of the whole volume
+        sums = sums * (float(y.shape[3]) / float(full_rows))
+        return ops.gn_apply(y, sums, gn.weight, gn.bias, residual, relu, out=y)
+
+    def _hourglass_band(self, hg, x, presqu, postsqu, resid, rows):
+        out = self._cg_band(hg.conv1[0], x, rows // 2, 2, relu=True)
+        pre = self._cg_band(hg.conv2, out, rows // 2, 1, residual=postsqu, relu=True)
+        out = self._cg_band(hg.conv3[0], pre, rows // 4, 2, relu=True)
+        out = self._cg_band(hg.conv4[0], out, rows // 4, 1, relu=True)
+        post = self._cg_band(hg.conv5, out, rows // 2, residual=presqu if presqu is not None else pre, relu=True)
+        out = self._cg_band(hg.conv6, post, rows, residual=resid, relu=False)
+        return out, pre, post
+
+    def _classify_band(self, head, x, rows):
+        t = self._cg_band(head[0], x, rows, 1, relu=True)
+        ext = par.exchange_row_halo(t, 1, 1, dim=3)
+        y, _ = ops.conv3d_k3(ext, self._pack(head[2]), 1)
+        return y[:, 0, :, 1:-1].contiguous()
+
+    @torch.no_grad()
+    def forward_row_bands(self, left, right, gather=True):
+        """Sharded inference of ONE pair over all ranks (every rank passes the same images).  Returns the three
+        disparity maps ([B,1,H,W] when `gather`, else this rank's rows [B,1,H/world,W])."""
+        self._check(left, right, self.maxdisp)
+        n, r = par.world(), par.rank()
+        B, _, H, W = left.shape
+        h = H // 4
+        if h % (16 * n):
+            raise ValueError("row-band sharding needs H/4=%d to be a multiple of 16*world=%d" % (h, 16 * n))
+        feat, full = self._features(torch.cat([left.float(), right.float()], 0).contiguous())  # replicated (SURVEY.md 8e)
+        lfeat, rfeat = feat[:B], feat[B:]
+        hr = full[:B].contiguous()
+        scale = hr.shape[-1] // lfeat.shape[-1]
+        D = self.maxdisp // scale
+        sim = self.mapping_matrix.similarity1
+        weights9 = ops.ctxmap_weights(lfeat, hr, sim.conv0.weight, sim.conv1.weight, sim.conv2.weight, sim.conv3.weight)
+        r0, r1 = par.band_rows(h, n, r, multiple=16)
+        cost = ops.cost_volume_concat(lfeat[:, :, r0:r1].contiguous(), rfeat[:, :, r0:r1].contiguous(), D)
+        cost0 = self._cg_band(self.dres0[0], cost, h, relu=True)
+        del cost
+        cost0 = self._cg_band(self.dres0[2], cost0, h, relu=True)
+        t = self._cg_band(self.dres1[0], cost0, h, relu=True)
+        cost0 = self._cg_band(self.dres1[2], t, h, residual=cost0)
+        out1, pre1, post1 = self._hourglass_band(self.dres2, cost0, None, None, cost0, h)
+        out2, _p2, post2 = self._hourglass_band(self.dres3, out1, pre1, post1, cost0, h)
+        out3, _p3, _q3 = self._hourglass_band(self.dres4, out2, pre1, post2, cost0, h)
+        cs = [par.exchange_row_halo(self._classify_band(getattr(self, "classif%d" % i), o, h), 1, 1, dim=2)
+              for i, o in ((1, out1), (2, out2), (3, out3))]
+        # K4 on the band + 1-cell halo; weight rows outside the image are zero (those neighbours contribute nothing)
+        wpad = F.pad(weights9, (0, 0, scale, scale))
+        wband = wpad[:, :, scale * r0:scale * (r1 + 2)].contiguous()
+        outs = ops.softargmin_ctxmap(cs[0], cs[1], cs[2], wband, scale)
+        outs = [o[:, :, scale:-scale].contiguous() for o in outs]
+        return tuple(par.gather_bands(o, dim=2) for o in outs) if gather else tuple(outs)
 
     # -------------------------------------------------------------------------------- CUDA graph replay
     def enable_cuda_graph(self, on=True):

@@ -127,14 +127,16 @@ def conv3d_k3(x, packed, stride=1, transposed=False, want_stats=False):
     Cout = packed.shape[2]
     sums = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
     L = _lib.load()
+    if transposed:
+        y = torch.empty((B, Cout, 2 * D, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
+    else:
+        Do, Ho, Wo = (D - 1) // stride + 1, (H - 1) // stride + 1, (W - 1) // stride + 1
+        y = torch.empty((B, Cout, Do, Ho, Wo), device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device), _timed("deconv3d_k3s2_fwd" if transposed else "conv3d_k3_fwd"):
         if transposed:
-            y = torch.empty((B, Cout, 2 * D, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
             _lib.check(L.cmfb200_deconv3d_k3s2_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W, _stream()),
                        "deconv3d_k3s2_fwd")
         else:
-            Do, Ho, Wo = (D - 1) // stride + 1, (H - 1) // stride + 1, (W - 1) // stride + 1
-            y = torch.empty((B, Cout, Do, Ho, Wo), device=x.device, dtype=torch.float32)
             _lib.check(L.cmfb200_conv3d_k3_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W, stride,
                                                _stream()), "conv3d_k3_fwd")
     return y, sums

@@ -1,0 +1,74 @@
+"""Row-band sharded inference check (GPU, torchrun): N ranks cooperate on ONE pair; the gathered result must match
+the un-sharded forward of the same model (BASELINE config 5 mechanics at a test size).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 \
+        tools/check_row_bands.py [--height 512 --width 512 --maxdisp 192]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "explicit-context-mapping-for-stereo-matching_b200"))
+from cmf.models.cmfsm import cmfsm  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--height", type=int, default=512)
+    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--maxdisp", type=int, default=192)
+    ap.add_argument("--steps", type=int, default=3)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = cmfsm(maxdisp=args.maxdisp).to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    left = torch.rand(1, 3, args.height, args.width, generator=g).to(dev)
+    right = torch.rand(1, 3, args.height, args.width, generator=g).to(dev)
+    outs = model.forward_row_bands(left, right)  # warm-up + result
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        model.forward_row_bands(left, right)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        with torch.no_grad():
+            ref = model(left, right)
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(args.steps):
+                model(left, right)
+            t1.record()
+            torch.cuda.synchronize()
+        rep = {"world": world, "shape": [args.height, args.width], "maxdisp": args.maxdisp, "ms_sharded": float(ms),
+               "ms_single_gpu": t0.elapsed_time(t1) / args.steps}
+        for i, (a, b) in enumerate(zip(outs, ref), 1):
+            d = (a - b).abs()
+            rep["pred%d_max_abs" % i], rep["pred%d_mean_abs" % i] = float(d.max()), float(d.mean())
+            # same fp32 arithmetic per voxel; only GroupNorm summation order differs -> fp32 noise floor of the net
+            assert float(d.max()) < 3e-2 and float(d.mean()) < 2e-3, rep
+        print(json.dumps(rep), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
