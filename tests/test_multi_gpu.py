@@ -1,0 +1,42 @@
+"""GPU, needs >= 2 devices (skipped otherwise): the two N>1 modes on real hardware through torchrun + NCCL.
+The host-side logic of both is covered on CPU by tests/test_parallel_cpu.py (gloo, world_size 2)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _torchrun(script, *args):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_port()), os.path.join(ROOT, "tools", script)] + list(args)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    return json.loads(lines[-1])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_row_band_sharding_matches_single_gpu():
+    rep = _torchrun("check_row_bands.py", "--height", "512", "--width", "512", "--steps", "1")
+    assert rep["world"] == 2 and rep["pred3_max_abs"] < 3e-2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_gradients_match_single_process():
+    rep = _torchrun("check_dp_train.py", "--per-rank-batch", "1", "--steps", "1")
+    assert rep["world"] == 2 and rep["grad_rel_l2"] < 2e-2
