@@ -19,6 +19,7 @@
 // (tcgen05.ld -> bf16 C8 store + GroupNorm sum/sum-of-squares, reduced per CTA, one double atomic per channel).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "igemm_common.cuh"
@@ -359,6 +360,10 @@ static int launch_igemm(const void* x, const void* wpk, void* y, double* gn, int
     return CMFB200_OK;
 }
 
+// persistent schedule (conv3d_igemm_persistent.cu); the kernel above is kept as the simple reference schedule
+int conv3d_igemm_persistent_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout,
+                                     int D, int H, int W, cudaStream_t st);
+
 }  // namespace cmfb200
 
 using namespace cmfb200;
@@ -380,6 +385,8 @@ extern "C" int cmfb200_conv3d_igemm_bf16_fwd(const void* x_c8, const void* packe
     CMF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_igemm_bf16_fwd: non-positive dimension");
     CMF_REQUIRE((reinterpret_cast<uintptr_t>(x_c8) & 15) == 0, "conv3d_igemm_bf16_fwd: input must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool simple_schedule = getenv("CMFB200_IGEMM_SIMPLE") != nullptr;  // A/B switch for profiling
+    if (!simple_schedule) return conv3d_igemm_persistent_dispatch(x_c8, packed_w, y_c8, gn_sums, B, Cin, Cout, D, H, W, st);
     if (Cin == 32 && Cout == 32) return launch_igemm<32, 32, 4, 4>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
     if (Cin == 64 && Cout == 32) return launch_igemm<64, 32, 2, 4>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
     if (Cin == 64 && Cout == 64) return launch_igemm<64, 64, 2, 2>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
