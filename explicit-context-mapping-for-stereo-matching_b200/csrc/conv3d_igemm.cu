@@ -172,15 +172,9 @@ __global__ void __launch_bounds__(kIgThreads, 2)
                     }
                 }
             }
-            if (gn_sums != nullptr) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const double a = warp_sum((double)s[c]), q = warp_sum((double)ss[c]);
-                    if (lane == 0) {
-                        sred[(quad * COUT + half * 32 + c) * 2 + 0] = a;
-                        sred[(quad * COUT + half * 32 + c) * 2 + 1] = q;
-                    }
-                }
+            if (gn_sums != nullptr) {  // lane l ends up with the warp total of column half*32 + l
+                sred[(quad * COUT + half * 32 + lane) * 2 + 0] = (double)warp_transpose_sum32(s, lane);
+                sred[(quad * COUT + half * 32 + lane) * 2 + 1] = (double)warp_transpose_sum32(ss, lane);
             }
         }
         tc_fence_before();

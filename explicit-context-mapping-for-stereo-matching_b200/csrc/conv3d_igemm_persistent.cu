@@ -172,6 +172,30 @@ __global__ void __launch_bounds__(kIgThreads, 1)
         const int row = quad * 32 + lane;
         const size_t plane = (size_t)H * W;
         const int et = threadIdx.x - 64;  // 0..127
+        // GroupNorm statistics: lane l of a warp keeps the running double total of column (half*32 + l) over all
+        // tiles of the current sample; they are combined across the four warps and flushed with one atomic per
+        // channel when the sample changes / at the end (not per tile).
+        double tot_s[COUT / 32], tot_q[COUT / 32];
+#pragma unroll
+        for (int i = 0; i < COUT / 32; ++i) tot_s[i] = tot_q[i] = 0.0;
+        int cur_b = -1;
+        auto flush = [&](int b) {
+#pragma unroll
+            for (int i = 0; i < COUT / 32; ++i) {
+                sred[(quad * COUT + i * 32 + lane) * 2 + 0] = tot_s[i];
+                sred[(quad * COUT + i * 32 + lane) * 2 + 1] = tot_q[i];
+                tot_s[i] = tot_q[i] = 0.0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = et; i < COUT * 2; i += 128) {
+                const int c = i >> 1, which = i & 1;
+                double a = 0.0;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) a += sred[(qd * COUT + c) * 2 + which];
+                atomicAdd(gn_sums + ((size_t)b * COUT + c) * 2 + which, a);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int b = tile / tiles_per_sample;
@@ -182,9 +206,13 @@ __global__ void __launch_bounds__(kIgThreads, 1)
             const int h = ty * 16 + (row >> 3), w = tx * 8 + (row & 7), d0 = tz * BD;
             const bool hw_ok = (h < H) && (w < W);
             const int acc = it & 1;
+            if (gn_sums != nullptr && b != cur_b) {
+                if (cur_b >= 0) flush(cur_b);
+                cur_b = b;
+            }
             mbar_wait(tmemFull + acc, (it >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int half = 0; half < COUT / 32; ++half) {
                 float s[32], ss[32];
 #pragma unroll
@@ -221,28 +249,12 @@ __global__ void __launch_bounds__(kIgThreads, 1)
                     mbar_arrive(tmemEmpty + acc);
                 }
                 if (gn_sums != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const double a = warp_sum((double)s[c]), q = warp_sum((double)ss[c]);
-                        if (lane == 0) {
-                            sred[(quad * COUT + half * 32 + c) * 2 + 0] = a;
-                            sred[(quad * COUT + half * 32 + c) * 2 + 1] = q;
-                        }
-                    }
+                    tot_s[half] += (double)warp_transpose_sum32(s, lane);
+                    tot_q[half] += (double)warp_transpose_sum32(ss, lane);
                 }
-            }
-            if (gn_sums != nullptr) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = et; i < COUT * 2; i += 128) {
-                    const int c = i >> 1, which = i & 1;
-                    double a = 0.0;
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) a += sred[(qd * COUT + c) * 2 + which];
-                    atomicAdd(gn_sums + ((size_t)b * COUT + c) * 2 + which, a);
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // sred is rewritten by the next tile
             }
         }
+        if (gn_sums != nullptr && cur_b >= 0) flush(cur_b);
         tc_fence_before();
     }
     __syncthreads();

@@ -54,6 +54,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 }
 
 
+// Transposing warp reduction: every lane holds 32 partial values (one per column); afterwards lane l holds the sum of
+// column l over all 32 lanes.  31 shuffles + 31 adds instead of 32 x 5 (a per-value butterfly), fp32.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float give = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+        }
+    }
+    return v[0];
+}
+
 // ---- host: cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda.so) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
