@@ -120,50 +120,69 @@ __global__ void __launch_bounds__(kIgThreads, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
-                                       ((uint32_t)(128 >> 4) << 24);
-            const uint32_t a_base = smem_u32(sA), w_0 = smem_u32(sW);
+        // ===== MMA issuer: the whole warp walks the schedule (uniform control flow), one elected lane issues
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_hi = umma_desc_hi(kPW * 16), b_hi = umma_desc_hi(128);
+        const uint32_t w_lo = umma_desc_lo(smem_u32(sW), COUT * 16);
+        if constexpr (RESIDENT) {
+            mbar_wait(barW, 0);
+            tc_fence_after();
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it % NA, acc = it & 1;
+            mbar_wait(fullA + buf, (it / NA) & 1);
+            if (it >= 2) mbar_wait(tmemEmpty + acc, ((it >> 1) - 1) & 1);
+            tc_fence_after();
+            const uint32_t a_lo = umma_desc_lo(smem_u32(sA) + buf * G::A_BYTES, G::CHUNK_BYTES);
+            const uint32_t d0 = tmem_base + acc * G::ACC_COLS;
             if constexpr (RESIDENT) {
-                mbar_wait(barW, 0);
-                tc_fence_after();
-            }
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int buf = it % NA, acc = it & 1;
-                mbar_wait(fullA + buf, (it / NA) & 1);
-                if (it >= 2) mbar_wait(tmemEmpty + acc, ((it >> 1) - 1) & 1);
-                tc_fence_after();
-                const uint32_t a0 = a_base + buf * G::A_BYTES;
-                const uint32_t d0 = tmem_base + acc * G::ACC_COLS;
-                for (int tap = 0; tap < 27; ++tap) {
-                    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-                    uint32_t wb;
-                    int s = 0;
-                    if constexpr (RESIDENT) {
-                        wb = w_0 + tap * G::TAP_BYTES;
-                    } else {
-                        const int g = it * 27 + tap;
-                        s = g % NSW;
-                        mbar_wait(fullW + s, (g / NSW) & 1);
-                        tc_fence_after();
-                        wb = w_0 + s * G::TAP_BYTES;
-                    }
+                if (elect_one()) {
 #pragma unroll
-                    for (int mt = 0; mt < BD; ++mt) {
-                        const uint32_t arow = a0 + ((((mt + kd) * kPH + kh) * kPW) + kw) * 16;
+                    for (int tap = 0; tap < 27; ++tap) {
+                        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
 #pragma unroll
-                        for (int kc = 0; kc < CIN / 16; ++kc) {
-                            const uint64_t ad = umma_desc(arow + 2 * kc * G::CHUNK_BYTES, G::CHUNK_BYTES, kPW * 16);
-                            const uint64_t bd = umma_desc(wb + 2 * kc * (COUT * 16), COUT * 16, 128);
-                            umma_bf16(d0 + mt * COUT, ad, bd, idesc, (tap | kc) != 0 ? 1u : 0u);
+                        for (int mt = 0; mt < BD; ++mt) {
+#pragma unroll
+                            for (int kc = 0; kc < CIN / 16; ++kc) {
+                                const uint64_t ad = umma_desc_at(a_lo, a_hi, ((((mt + kd) * kPH + kh) * kPW) + kw) * 16 + 2 * kc * G::CHUNK_BYTES);
+                                const uint64_t bd = umma_desc_at(w_lo, b_hi, tap * G::TAP_BYTES + 2 * kc * (COUT * 16));
+                                umma_bf16(d0 + mt * COUT, ad, bd, idesc, (tap | kc) != 0 ? 1u : 0u);
+                            }
                         }
                     }
-                    if constexpr (!RESIDENT) umma_commit(emptyW + s);
+                    umma_commit(emptyA + buf);    // activation buffer may be refilled
+                    umma_commit(tmemFull + acc);  // accumulators of this tile are final
                 }
-                umma_commit(emptyA + buf);    // activation buffer may be refilled
-                umma_commit(tmemFull + acc);  // accumulators of this tile are final
+                __syncwarp();
+            } else {
+#pragma unroll 1
+                for (int tap = 0; tap < 27; ++tap) {
+                    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+                    const int g = it * 27 + tap;
+                    const int s = g % NSW;
+                    mbar_wait(fullW + s, (g / NSW) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t arow = ((((kd * kPH) + kh) * kPW) + kw) * 16;
+#pragma unroll
+                        for (int mt = 0; mt < BD; ++mt) {
+#pragma unroll
+                            for (int kc = 0; kc < CIN / 16; ++kc) {
+                                const uint64_t ad = umma_desc_at(a_lo, a_hi, arow + mt * kPH * kPW * 16 + 2 * kc * G::CHUNK_BYTES);
+                                const uint64_t bd = umma_desc_at(w_lo, b_hi, s * G::TAP_BYTES + 2 * kc * (COUT * 16));
+                                umma_bf16(d0 + mt * COUT, ad, bd, idesc, (tap | kc) != 0 ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(emptyW + s);
+                        if (tap == 26) {
+                            umma_commit(emptyA + buf);
+                            umma_commit(tmemFull + acc);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
     } else {

@@ -54,6 +54,29 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 }
 
 
+// elect.sync: exactly one lane of a converged warp gets `true` (warp-uniform control flow around tcgen05.mma lets
+// ptxas keep descriptors in uniform registers instead of electing + R2UR-ing per instruction)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, px;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// descriptor with the constant fields in the high word; only the 14-bit start-address field (low word) moves
+__device__ __forceinline__ uint64_t umma_desc_at(uint32_t lo_base, uint32_t hi, uint32_t byte_offset) {
+    return ((uint64_t)hi << 32) | (uint64_t)(lo_base + (byte_offset >> 4));
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }
+
 // Transposing warp reduction: every lane holds 32 partial values (one per column); afterwards lane l holds the sum of
 // column l over all 32 lanes.  31 shuffles + 31 adds instead of 32 x 5 (a per-value butterfly), fp32.
 __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
