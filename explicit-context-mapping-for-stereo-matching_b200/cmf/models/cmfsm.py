@@ -244,29 +244,29 @@ class cmfsm(nn.Module):
         self._packed[key] = (w._version, w.data_ptr(), packed)
         return packed
 
-    def _ig(self, block, x, residual=None, relu=False):
+    def _ig(self, block, x, residual=None, relu=False, split=False, x_split=None):
+        """conv + GroupNorm (+residual) (+ReLU) on C8.  `x_split`: parity-split copy of x (stride-2 convs);
+        `split`: also return the parity-split copy of the OUTPUT (the next layer is a stride-2 conv)."""
         conv = block[0]
         if isinstance(conv, nn.ConvTranspose3d):
             y, sums = ops.deconv3d_igemm(x, self._pack_ig(conv))
         elif conv.stride[0] == 2:
-            y, sums = ops.conv3d_s2_igemm(ops.c8_parity_split(x), self._pack_ig(conv))
+            y, sums = ops.conv3d_s2_igemm(x_split if x_split is not None else ops.c8_parity_split(x), self._pack_ig(conv))
         else:
             y, sums = ops.conv3d_igemm(x, self._pack_ig(conv))
-        return ops.gn_apply_c8(y, sums, block[1].weight, block[1].bias, residual, relu, out=y)
+        return ops.gn_apply_c8(y, sums, block[1].weight, block[1].bias, residual, relu, out=y, want_split=split)
 
-    def _hourglass_bf16(self, hg, x, presqu, postsqu, resid):
-        out = self._ig(hg.conv1[0], x, relu=True)
-        pre = self._ig(hg.conv2, out, residual=postsqu, relu=True)
-        out = self._ig(hg.conv3[0], pre, relu=True)
+    def _hourglass_bf16(self, hg, x, x_split, presqu, postsqu, resid, split_out):
+        out = self._ig(hg.conv1[0], x, relu=True, x_split=x_split)
+        pre, pre_split = self._ig(hg.conv2, out, residual=postsqu, relu=True, split=True)
+        out = self._ig(hg.conv3[0], pre, relu=True, x_split=pre_split)
         out = self._ig(hg.conv4[0], out, relu=True)
         post = self._ig(hg.conv5, out, residual=presqu if presqu is not None else pre, relu=True)
-        out = self._ig(hg.conv6, post, residual=resid, relu=False)
+        out = self._ig(hg.conv6, post, residual=resid, relu=False, split=split_out)
         return out, pre, post
 
     def _classify_bf16(self, head, x):
-        t32 = ops.c8_to_f32(self._ig(head[0], x, relu=True))
-        y, _ = ops.conv3d_k3(t32, self._pack(head[2]), 1)
-        return y.squeeze(1)
+        return ops.conv3d_c8_cout1(self._ig(head[0], x, relu=True), head[2].weight)
 
     def _aggregate_bf16(self, lfeat, rfeat, D):
         cost = ops.cost_volume_concat_c8(lfeat, rfeat, D)
@@ -274,10 +274,10 @@ class cmfsm(nn.Module):
         del cost
         cost0 = self._ig(self.dres0[2], cost0, relu=True)
         t = self._ig(self.dres1[0], cost0, relu=True)
-        cost0 = self._ig(self.dres1[2], t, residual=cost0)
-        out1, pre1, post1 = self._hourglass_bf16(self.dres2, cost0, None, None, cost0)
-        out2, _pre2, post2 = self._hourglass_bf16(self.dres3, out1, pre1, post1, cost0)
-        out3, _pre3, _post3 = self._hourglass_bf16(self.dres4, out2, pre1, post2, cost0)
+        cost0, cost0_split = self._ig(self.dres1[2], t, residual=cost0, split=True)
+        (out1, out1_split), pre1, post1 = self._hourglass_bf16(self.dres2, cost0, cost0_split, None, None, cost0, True)
+        (out2, out2_split), _pre2, post2 = self._hourglass_bf16(self.dres3, out1, out1_split, pre1, post1, cost0, True)
+        out3, _pre3, _post3 = self._hourglass_bf16(self.dres4, out2, out2_split, pre1, post2, cost0, False)
         return (self._classify_bf16(self.classif1, out1), self._classify_bf16(self.classif2, out2),
                 self._classify_bf16(self.classif3, out3))
 

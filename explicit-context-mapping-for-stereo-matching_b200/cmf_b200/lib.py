@@ -29,11 +29,12 @@ SIGNATURES = {
     "cmfb200_deconv3d_k3s2_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_pack_igemm_weight_bf16": [_P, _P, _I, _I, _I, _P],
     "cmfb200_conv3d_igemm_bf16_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "cmfb200_conv3d_c8_cout1_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_deconv3d_igemm_bf16_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_conv3d_s2_igemm_bf16_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_c8_parity_split": [_P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_cost_volume_concat_c8_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "cmfb200_gn_apply_c8_bf16": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _F, _I, _P],
+    "cmfb200_gn_apply_c8_bf16": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "cmfb200_c8_bf16_to_f32": [_P, _P, _I, _I, _LL, _P],
     "cmfb200_f32_to_c8_bf16": [_P, _P, _I, _I, _LL, _P],
     "cmfb200_pack_conv2d_weight": [_P, _P, _I, _I, _I, _P],

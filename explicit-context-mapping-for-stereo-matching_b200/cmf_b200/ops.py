@@ -306,6 +306,21 @@ def conv3d_igemm(x, packed, want_stats=True):
     return y, sums
 
 
+def conv3d_c8_cout1(x, weight):
+    """classifN.2: C8/bf16 [B,Cin/8,D,H,W,8] x nn.Conv3d weight [1,Cin,3,3,3] (fp32) -> fp32 [B,D,H,W]."""
+    weight = weight.detach()
+    _req(x, dtype=BF16)
+    _req(weight)
+    B, NC, D, H, W, _ = x.shape
+    if tuple(weight.shape) != (1, NC * 8, 3, 3, 3):
+        raise ValueError("expected a [1,%d,3,3,3] weight, got %s" % (NC * 8, tuple(weight.shape)))
+    y = torch.empty((B, D, H, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _timed("conv3d_c8_cout1_fwd"):
+        _lib.check(_lib.load().cmfb200_conv3d_c8_cout1_fwd(_p(x), _p(weight), _p(y), B, NC * 8, D, H, W, _stream()),
+                   "conv3d_c8_cout1_fwd")
+    return y
+
+
 def deconv3d_igemm(x, packed, want_stats=True):
     """tcgen05 transposed conv (k3 s2 p1 op1) on C8/bf16: [B,Cin/8,D,H,W,8] -> [B,Cout/8,2D,2H,2W,8]."""
     _req(x, packed, dtype=BF16)
@@ -342,15 +357,18 @@ def conv3d_s2_igemm(x_split, packed, want_stats=True):
     return y, sums
 
 
-def gn_apply_c8(x, sums, gamma, beta, residual=None, relu=False, out=None, groups=GN_GROUPS, eps=GN_EPS):
+def gn_apply_c8(x, sums, gamma, beta, residual=None, relu=False, out=None, want_split=False, groups=GN_GROUPS,
+                eps=GN_EPS):
+    """GroupNorm(+residual)(+ReLU) on C8/bf16.  With `want_split` also returns the parity-split copy that the
+    stride-2 implicit GEMM consumes: (y, y_split)."""
     gamma, beta = gamma.detach(), beta.detach()
     _req(gamma, beta)
     _req(x, residual, dtype=BF16)
-    B, NC = x.shape[:2]
-    spatial = x[0, 0].numel() // 8
+    B, NC, D, H, W, _ = x.shape
     y = torch.empty_like(x) if out is None else out
+    split = torch.empty((B, 8, NC, D // 2, H // 2, W // 2, 8), device=x.device, dtype=BF16) if want_split else None
     with torch.cuda.device(x.device), _timed("gn_apply_c8_bf16"):
-        _lib.check(_lib.load().cmfb200_gn_apply_c8_bf16(_p(x), _p(sums), _p(gamma), _p(beta), _p(residual), _p(y), B,
-                                                        NC * 8, groups, spatial, eps, int(relu), _stream()),
-                   "gn_apply_c8_bf16")
-    return y
+        _lib.check(_lib.load().cmfb200_gn_apply_c8_bf16(_p(x), _p(sums), _p(gamma), _p(beta), _p(residual), _p(y),
+                                                        _p(split), B, NC * 8, groups, D, H, W, eps, int(relu),
+                                                        _stream()), "gn_apply_c8_bf16")
+    return (y, split) if want_split else y

@@ -211,32 +211,43 @@ __global__ void pack_igemm_weight_kernel(const float* __restrict__ w, __nv_bfloa
 }
 
 // K1 in C8/bf16: cost[b][chunk][d][y][x][8]; chunks 0..C/8-1 = left features masked by x>=d, the rest = right
-// features shifted by d.  L,R fp32 NCHW.
-__global__ void cost_volume_c8_bf16_kernel(const float* __restrict__ L, const float* __restrict__ R,
-                                           __nv_bfloat16* __restrict__ cost, int C, int h, int w, int D) {
+// features shifted by d.  L,R fp32 NCHW.  Same scheme as the fp32 kernel (cost_volume.cu): a CTA stages the rows of
+// one 8-channel group once in shared memory (converted to bf16, 16 B per voxel, right rows behind a zero prefix)
+// and streams the D shifted / masked copies with 128-bit stores; for fixed (chunk, d) its rows are contiguous.
+constexpr int kCv8Rows = 2;
+__global__ void __launch_bounds__(256) cost_volume_c8_bf16_kernel(const float* __restrict__ L,
+                                                                  const float* __restrict__ R,
+                                                                  __nv_bfloat16* __restrict__ cost, int C, int h, int w,
+                                                                  int D, int DP) {
+    extern __shared__ uint4 sv[];  // [rows][DP + w]
     const int nc = C / 8;
+    const int y0 = blockIdx.x * kCv8Rows, chunk = blockIdx.y, b = blockIdx.z;
+    const int rows = min(kCv8Rows, h - y0);
+    const bool right = chunk >= nc;
+    const int c0 = (right ? chunk - nc : chunk) * 8;
     const size_t plane = (size_t)h * w;
-    const size_t total = (size_t)2 * nc * D * plane;  // 16-byte units per sample
-    const int b = blockIdx.y;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % w);
-        const int yy = (int)((i / w) % h);
-        const int d = (int)((i / plane) % D);
-        const int chunk = (int)(i / (plane * D));
-        const bool right = chunk >= nc;
-        const int c0 = (right ? chunk - nc : chunk) * 8;
-        const float* src = (right ? R : L) + ((size_t)b * C + c0) * plane + (size_t)yy * w + (right ? x - d : x);
+    const int pitch = DP + w;
+    const float* src = (right ? R : L) + ((size_t)b * C + c0) * plane + (size_t)y0 * w;
+    for (int i = threadIdx.x; i < rows * w; i += 256) {  // rows are contiguous: i == r*w + x
         __nv_bfloat162 p[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float f0 = 0.f, f1 = 0.f;
-            if (x >= d) {
-                f0 = __ldg(src + (2 * e) * plane);
-                f1 = __ldg(src + (2 * e + 1) * plane);
-            }
-            p[e] = __floats2bfloat162_rn(f0, f1);
+        for (int e = 0; e < 4; ++e) p[e] = __floats2bfloat162_rn(__ldg(src + (2 * e) * plane + i), __ldg(src + (2 * e + 1) * plane + i));
+        sv[(i / w) * pitch + DP + (i % w)] = *reinterpret_cast<const uint4*>(p);
+    }
+    for (int i = threadIdx.x; i < rows * DP; i += 256) sv[(i / DP) * pitch + (i % DP)] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4* out = reinterpret_cast<uint4*>(cost) + (((size_t)b * 2 * nc + chunk) * D) * plane + (size_t)y0 * w;
+    for (int d = warp; d < D; d += 8) {
+        uint4* o = out + (size_t)d * plane;
+        for (int i = lane; i < rows * w; i += 32) {
+            const int r = i / w, x = i - r * w;
+            uint4 v = sv[r * pitch + DP + (right ? x - d : x)];
+            if (!right && x < d) v = make_uint4(0, 0, 0, 0);
+            asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(o + i), "r"(v.x), "r"(v.y),
+                         "r"(v.z), "r"(v.w)
+                         : "memory");
         }
-        *reinterpret_cast<uint4*>(cost + ((size_t)b * total + i) * 8) = *reinterpret_cast<const uint4*>(p);
     }
 }
 
@@ -246,8 +257,10 @@ __global__ void __launch_bounds__(256) gn_apply_c8_bf16_kernel(const __nv_bfloat
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta,
                                                                const __nv_bfloat16* __restrict__ residual,
-                                                               __nv_bfloat16* __restrict__ y, int C, int G,
-                                                               long long spatial, float eps, int relu) {
+                                                               __nv_bfloat16* __restrict__ y,
+                                                               __nv_bfloat16* __restrict__ y_split, int C, int G,
+                                                               int D, int H, int W, float eps, int relu) {
+    const long long spatial = (long long)D * H * W;
     __shared__ float sscale[8], sshift[8];
     const int nc = C / 8;
     const int chunk = blockIdx.y % nc;
@@ -299,6 +312,60 @@ __global__ void __launch_bounds__(256) gn_apply_c8_bf16_kernel(const __nv_bfloat
             out[e] = __floats2bfloat162_rn(f0, f1);
         }
         *reinterpret_cast<uint4*>(y + (base + i) * 8) = *reinterpret_cast<const uint4*>(out);
+    }
+}
+
+// classifier tail conv (Cin -> 1, 3x3x3, pad 1) straight from C8/bf16 to the fp32 volume K4 consumes
+// (classifN.2, cmf/models/cmfsm.py:624,629,634).  N=1 has no tensor-core shape; the op is bound by reading the
+// input once (106 MB at config 2): one thread per output voxel, 128-bit loads that hit L1 for the 27-fold reuse,
+// fp32 accumulation; weights [Cin][27] fp32 staged in shared memory as [Cin/8][27][8].
+__global__ void __launch_bounds__(256) conv3d_c8_cout1_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const float* __restrict__ wgt, float* __restrict__ y,
+                                                              int NC, int D, int H, int W) {
+    extern __shared__ __align__(16) float sw[];  // [NC][27][8]
+    for (int i = threadIdx.x; i < NC * 27 * 8; i += 256) {
+        const int j = i & 7, tap = (i >> 3) % 27, chunk = i / (27 * 8);
+        sw[i] = wgt[(chunk * 8 + j) * 27 + tap];
+    }
+    __syncthreads();
+    const size_t plane = (size_t)H * W, vol = (size_t)D * plane;
+    const int b = blockIdx.y;
+    const uint4* xb = reinterpret_cast<const uint4*>(x) + (size_t)b * NC * vol;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < vol; i += (size_t)gridDim.x * 256) {
+        const int w = (int)(i % W), h = (int)((i / W) % H), d = (int)(i / plane);
+        float acc = 0.f;
+        for (int chunk = 0; chunk < NC; ++chunk) {
+            const uint4* xc = xb + (size_t)chunk * vol;
+            const float* wc = sw + chunk * 27 * 8;
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+                const int dd = d + kd - 1;
+                if ((unsigned)dd >= (unsigned)D) continue;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int hh = h + kh - 1;
+                    if ((unsigned)hh >= (unsigned)H) continue;
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int ww = w + kw - 1;
+                        if ((unsigned)ww >= (unsigned)W) continue;
+                        const uint4 raw = __ldg(xc + (size_t)dd * plane + (size_t)hh * W + ww);
+                        const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                        const float4 w0 = *reinterpret_cast<const float4*>(wc + ((kd * 3 + kh) * 3 + kw) * 8);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wc + ((kd * 3 + kh) * 3 + kw) * 8 + 4);
+                        acc = fmaf(__low2float(v[0]), w0.x, acc);
+                        acc = fmaf(__high2float(v[0]), w0.y, acc);
+                        acc = fmaf(__low2float(v[1]), w0.z, acc);
+                        acc = fmaf(__high2float(v[1]), w0.w, acc);
+                        acc = fmaf(__low2float(v[2]), w1.x, acc);
+                        acc = fmaf(__high2float(v[2]), w1.y, acc);
+                        acc = fmaf(__low2float(v[3]), w1.z, acc);
+                        acc = fmaf(__high2float(v[3]), w1.w, acc);
+                    }
+                }
+            }
+        }
+        y[(size_t)b * vol + i] = acc;
     }
 }
 
@@ -393,25 +460,32 @@ extern "C" int cmfb200_cost_volume_concat_c8_bf16(const float* L, const float* R
     CMF_REQUIRE(L && R && cost_c8, "cost_volume_concat_c8_bf16: null pointer");
     CMF_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && h > 0 && w > 0 && D > 0, "cost_volume_concat_c8_bf16: bad shape");
     CMF_REQUIRE(B <= 65535, "cost_volume_concat_c8_bf16: B exceeds grid limit");
-    const size_t total = (size_t)2 * (C / 8) * D * h * w;
-    dim3 grid((unsigned)min((size_t)kNumSMs * 16, (size_t)cdiv((long long)total, 256)), (unsigned)B);
-    cost_volume_c8_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(L, R, reinterpret_cast<__nv_bfloat16*>(cost_c8),
-                                                                        C, h, w, D);
+    const int DP = (D + 3) & ~3;
+    const size_t smem = (size_t)kCv8Rows * (DP + w) * 16;
+    CMF_REQUIRE(smem <= 200 * 1024, "cost_volume_concat_c8_bf16: row block does not fit in shared memory");
+    if (smem > 48 * 1024)
+        CMF_CUDA(cudaFuncSetAttribute(cost_volume_c8_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)cdiv(h, kCv8Rows), (unsigned)(2 * (C / 8)), (unsigned)B);
+    cost_volume_c8_bf16_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(L, R, reinterpret_cast<__nv_bfloat16*>(cost_c8),
+                                                                           C, h, w, D, DP);
     CMF_LAUNCH_CHECK("cost_volume_c8_bf16_kernel");
     return CMFB200_OK;
 }
 
 extern "C" int cmfb200_gn_apply_c8_bf16(const void* x_c8, const double* gn_sums, const float* gamma, const float* beta,
-                                        const void* residual_c8, void* y_c8, int B, int C, int G, long long spatial,
-                                        float eps, int relu, void* stream) {
+                                        const void* residual_c8, void* y_c8, void* y_split_c8, int B, int C, int G,
+                                        int D, int H, int W, float eps, int relu, void* stream) {
     CMF_REQUIRE(x_c8 && gn_sums && gamma && beta && y_c8, "gn_apply_c8_bf16: null pointer");
-    CMF_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && G > 0 && C % G == 0 && spatial > 0, "gn_apply_c8_bf16: bad shape");
+    CMF_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && G > 0 && C % G == 0 && D > 0 && H > 0 && W > 0, "gn_apply_c8_bf16: bad shape");
+    CMF_REQUIRE(y_split_c8 == nullptr || ((D % 2 == 0) && (H % 2 == 0) && (W % 2 == 0)),
+                "gn_apply_c8_bf16: the parity-split copy needs even D,H,W (got %d,%d,%d)", D, H, W);
+    const long long spatial = (long long)D * H * W;
     CMF_REQUIRE((long long)B * (C / 8) <= 65535, "gn_apply_c8_bf16: B*C/8 exceeds grid limit");
     dim3 grid((unsigned)min((long long)kNumSMs * 8, cdiv(spatial, 256)), (unsigned)(B * (C / 8)));
     gn_apply_c8_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x_c8), gn_sums, gamma, beta,
-        reinterpret_cast<const __nv_bfloat16*>(residual_c8), reinterpret_cast<__nv_bfloat16*>(y_c8), C, G, spatial, eps,
-        relu);
+        reinterpret_cast<const __nv_bfloat16*>(residual_c8), reinterpret_cast<__nv_bfloat16*>(y_c8),
+        reinterpret_cast<__nv_bfloat16*>(y_split_c8), C, G, D, H, W, eps, relu);
     CMF_LAUNCH_CHECK("gn_apply_c8_bf16_kernel");
     return CMFB200_OK;
 }
@@ -432,5 +506,18 @@ extern "C" int cmfb200_f32_to_c8_bf16(const float* x, void* y_c8, int B, int C, 
     dim3 grid((unsigned)min((long long)kNumSMs * 8, cdiv(spatial, 256)), (unsigned)(B * (C / 8)));
     f32_to_c8_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y_c8), spatial);
     CMF_LAUNCH_CHECK("f32_to_c8_bf16_kernel");
+    return CMFB200_OK;
+}
+
+extern "C" int cmfb200_conv3d_c8_cout1_fwd(const void* x_c8, const float* weight, float* y, int B, int Cin, int D, int H,
+                                           int W, void* stream) {
+    CMF_REQUIRE(x_c8 && weight && y, "conv3d_c8_cout1_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && Cin > 0 && Cin % 8 == 0 && D > 0 && H > 0 && W > 0 && B <= 65535, "conv3d_c8_cout1_fwd: bad shape");
+    const long long vol = (long long)D * H * W;
+    const size_t smem = (size_t)Cin * 27 * sizeof(float);
+    dim3 grid((unsigned)min((long long)kNumSMs * 16, cdiv(vol, 256)), (unsigned)B);
+    conv3d_c8_cout1_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_c8), weight,
+                                                                       y, Cin / 8, D, H, W);
+    CMF_LAUNCH_CHECK("conv3d_c8_cout1_kernel");
     return CMFB200_OK;
 }

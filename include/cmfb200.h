@@ -79,6 +79,10 @@ int cmfb200_pack_igemm_weight_bf16(const float* weight, void* packed, int Cout, 
  * double buffer receiving sum / sum of squares of the stored (rounded) values, or NULL. */
 int cmfb200_conv3d_igemm_bf16_fwd(const void* x_c8, const void* packed_w, void* y_c8, double* gn_sums,
                                   int B, int Cin, int Cout, int D, int H, int W, void* stream);
+/* Classifier tail conv Cin -> 1 (k3 p1) from C8/bf16 to fp32 [B,D,H,W]; weight = nn.Conv3d weight [1,Cin,3,3,3]
+ * fp32 (unpacked).  CUDA cores (N=1 has no tensor-core shape), fp32 accumulation. */
+int cmfb200_conv3d_c8_cout1_fwd(const void* x_c8, const float* weight, float* y, int B, int Cin, int D, int H,
+                                int W, void* stream);
 /* Transposed conv k3 s2 p1 op1 on tensor cores: x_c8 [B][Cin/8][D][H][W][8] -> y_c8 [B][Cout/8][2D][2H][2W][8];
  * packed_w from cmfb200_pack_igemm_weight_bf16(transposed=1).  (Cin,Cout) in {(64,64),(64,32)}. */
 int cmfb200_deconv3d_igemm_bf16_fwd(const void* x_c8, const void* packed_w, void* y_c8, double* gn_sums,
@@ -93,10 +97,11 @@ int cmfb200_c8_parity_split(const void* x_c8, void* y_split_c8, int B, int C, in
  * (channel groups 0..C/8-1 = masked left features, C/8.. = shifted right features). */
 int cmfb200_cost_volume_concat_c8_bf16(const float* L, const float* R, void* cost_c8,
                                        int B, int C, int h, int w, int D, void* stream);
-/* K3 on C8/bf16: y = GroupNorm(x) (+residual) (ReLU), fp32 math, bf16 in/out; y may alias x. */
+/* K3 on C8/bf16: y = GroupNorm(x) (+residual) (ReLU), fp32 math, bf16 in/out; y may alias x.  If y_split_c8 != NULL
+ * the result is ALSO written in the parity-split layout a stride-2 consumer reads (D,H,W even). */
 int cmfb200_gn_apply_c8_bf16(const void* x_c8, const double* gn_sums, const float* gamma, const float* beta,
-                             const void* residual_c8, void* y_c8, int B, int C, int G, long long spatial,
-                             float eps, int relu, void* stream);
+                             const void* residual_c8, void* y_c8, void* y_split_c8, int B, int C, int G,
+                             int D, int H, int W, float eps, int relu, void* stream);
 /* layout/dtype converters between C8/bf16 and dense fp32 [B,C,spatial] (NCDHW). */
 int cmfb200_c8_bf16_to_f32(const void* x_c8, float* y, int B, int C, long long spatial, void* stream);
 int cmfb200_f32_to_c8_bf16(const float* x, void* y_c8, int B, int C, long long spatial, void* stream);

@@ -335,14 +335,19 @@ def test_conv3d_igemm_tcgen05_vs_oracle(B, Cin, Cout, D, H, W):
 def test_gn_apply_c8_vs_oracle():
     from cmf_b200 import ops
 
-    x = _rand(2, 64, 3, 6, 10, seed=80) * 2 + 0.3
-    r = _rand(2, 64, 3, 6, 10, seed=81)
+    x = _rand(2, 64, 4, 6, 10, seed=80) * 2 + 0.3
+    r = _rand(2, 64, 4, 6, 10, seed=81)
     gamma, beta = _rand(64, seed=82), _rand(64, seed=83)
     xq, rq = x.to(torch.bfloat16).float(), r.to(torch.bfloat16).float()
     want = (F.group_norm(xq.double(), 32, gamma.double(), beta.double(), 1e-5) + rq.double()).relu()
     xs = xq.to(DEV)
-    got = ops.gn_apply_c8(ops.f32_to_c8(xs), ops.gn_stats(xs), gamma.to(DEV), beta.to(DEV), ops.f32_to_c8(rq.to(DEV)), True)
+    got, split = ops.gn_apply_c8(ops.f32_to_c8(xs), ops.gn_stats(xs), gamma.to(DEV), beta.to(DEV),
+                                 ops.f32_to_c8(rq.to(DEV)), True, want_split=True)
     assert _rel_l2(ops.c8_to_f32(got), want) < 3e-3
+    assert torch.equal(split, ops.c8_parity_split(got))  # fused parity-split copy == the stand-alone kernel
+    B, NC, D, H, W, _ = got.shape  # and == the definition: [B][(d&1)*4+(h&1)*2+(w&1)][C/8][D/2][H/2][W/2][8]
+    ref = got.view(B, NC, D // 2, 2, H // 2, 2, W // 2, 2, 8).permute(0, 3, 5, 7, 1, 2, 4, 6, 8).reshape(B, 8, NC, D // 2, H // 2, W // 2, 8)
+    assert torch.equal(split, ref)
 
 
 @pytest.mark.parametrize("B,Cout,D,H,W", [(1, 64, 2, 16, 8), (2, 32, 3, 10, 12), (1, 64, 3, 18, 20), (1, 32, 5, 33, 9)])
@@ -380,3 +385,14 @@ def test_conv3d_s2_igemm_tcgen05_vs_oracle(B, Cin, D, H, W):
     print("s2 igemm %s rel-L2 %.3e" % ((B, Cin, D, H, W), err))
     assert err < 3e-3
     torch.testing.assert_close(sums.cpu()[..., 1], (got * got).sum((2, 3, 4)), rtol=1e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,D,H,W", [(1, 4, 6, 10), (2, 5, 9, 33)])
+def test_conv3d_c8_cout1_vs_oracle(B, D, H, W):
+    from cmf_b200 import ops
+
+    x = _rand(B, 32, D, H, W, seed=95)
+    wgt = _rand(1, 32, 3, 3, 3, seed=96) * 0.05
+    want = F.conv3d(x.to(torch.bfloat16).double(), wgt.double(), None, 1, 1).squeeze(1)
+    got = ops.conv3d_c8_cout1(ops.f32_to_c8(x.to(DEV)), wgt.to(DEV))
+    assert _rel_l2(got, want) < 1e-5  # fp32 accumulation of exactly representable bf16 inputs
