@@ -312,6 +312,12 @@ __global__ void __launch_bounds__(256) gn_apply_c8_bf16_kernel(const __nv_bfloat
             out[e] = __floats2bfloat162_rn(f0, f1);
         }
         *reinterpret_cast<uint4*>(y + (base + i) * 8) = *reinterpret_cast<const uint4*>(out);
+        if (y_split != nullptr) {  // parity-split copy for a stride-2 consumer: [B][8][C/8][D/2][H/2][W/2][8]
+            const int w = (int)(i % W), h = (int)((i / W) % H), d = (int)(i / ((long long)W * H));
+            const int par = ((d & 1) << 2) | ((h & 1) << 1) | (w & 1);
+            const size_t dst = (((((size_t)b * 8 + par) * nc + chunk) * (D >> 1) + (d >> 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+            *reinterpret_cast<uint4*>(y_split + dst * 8) = *reinterpret_cast<const uint4*>(out);
+        }
     }
 }
 
