@@ -8,8 +8,8 @@ checkpoints and the reference drivers (train.py, test.py, eval_kitti.py) work un
 What differs underneath: cost volume, 3-D aggregation (conv/deconv + GroupNorm + residual + ReLU),
 context-mapping weights and the soft-argmin/upsample/mapping epilogue run as hand-written sm_100a kernels
 from libcmfb200.so (`cmf_b200.ops`), and so do the 2-D feature extractor's convolutions + GroupNorms at
-inference (its four SPP average pools / bilinear upsamples are still ATen calls; under autograd the 2-D
-extractor runs through cuDNN in strict fp32).  Output semantics are per-sample `[B,1,H,W]` (the reference
+inference, including the SPP pools / bilinear upsamples / concat (under autograd the 2-D extractor runs
+through cuDNN in strict fp32).  Output semantics are per-sample `[B,1,H,W]` (the reference
 broadcasts to `[B,B,H,W]` for B>1).  There is no CPU path: CPU inputs raise.
 """
 import math
@@ -219,14 +219,9 @@ class cmfsm(nn.Module):
             if name == "layer2":
                 raw = o
         skip = o
-        size = skip.shape[2:]
-        pyramid = []
-        for i in (4, 3, 2, 1):
-            branch = getattr(fe, "branch%d" % i)
-            pooled = branch[0](skip)  # AvgPool2d: tiny; TODO own kernel together with the bilinear upsample
-            pyramid.append(F.interpolate(self._cg2(branch[1], pooled.contiguous(), relu=True), size, mode="bilinear",
-                                         align_corners=False))
-        cat = torch.cat([raw, skip] + pyramid, 1)
+        pooled = ops.spp_pool(skip)  # (64, 32, 16, 8) pools = inputs of branch1..branch4
+        b1, b2, b3, b4 = [self._cg2(getattr(fe, "branch%d" % (i + 1))[1], p, relu=True) for i, p in enumerate(pooled)]
+        cat = ops.spp_upsample_concat(raw, skip, b4, b3, b2, b1)
         o = self._cg2(fe.lastconv[0], cat, relu=True)
         feat, _ = self._c2(fe.lastconv[2], o, False)
         return feat, full

@@ -39,6 +39,8 @@ SIGNATURES = {
     "cmfb200_f32_to_c8_bf16": [_P, _P, _I, _I, _LL, _P],
     "cmfb200_pack_conv2d_weight": [_P, _P, _I, _I, _I, _P],
     "cmfb200_conv2d_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cmfb200_spp_pool_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "cmfb200_spp_upsample_concat_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "cmfb200_gn_stats": [_P, _P, _I, _I, _LL, _P],
     "cmfb200_gn_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _F, _I, _P],
     "cmfb200_ctxmap_weights_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

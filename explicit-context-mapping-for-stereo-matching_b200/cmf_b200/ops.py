@@ -174,6 +174,30 @@ def conv2d(x, packed, ksize, stride=1, dilation=1, want_stats=False):
     return y, sums
 
 
+def spp_pool(x):
+    """AvgPool2d 64/32/16/8 (stride = kernel) of [B,C,H,W]; returns (p64, p32, p16, p8) = branch1..branch4 inputs."""
+    _req(x)
+    B, C, H, W = x.shape
+    ps = [torch.empty((B, C, H // k, W // k), device=x.device, dtype=torch.float32) for k in (8, 16, 32, 64)]
+    with torch.cuda.device(x.device), _timed("spp_pool_fwd"):
+        _lib.check(_lib.load().cmfb200_spp_pool_fwd(_p(x), _p(ps[0]), _p(ps[1]), _p(ps[2]), _p(ps[3]), B, C, H, W,
+                                                    _stream()), "spp_pool_fwd")
+    return ps[3], ps[2], ps[1], ps[0]
+
+
+def spp_upsample_concat(raw, skip, b4, b3, b2, b1):
+    """cat([raw, skip, up(b4), up(b3), up(b2), up(b1)], 1) with bilinear (align_corners=False) upsampling."""
+    _req(raw, skip, b4, b3, b2, b1)
+    B, _, H, W = skip.shape
+    if raw.shape[1] != 64 or skip.shape[1] != 128 or any(t.shape[1] != 32 for t in (b4, b3, b2, b1)):
+        raise ValueError("spp_upsample_concat expects 64 + 128 + 4 x 32 channels")
+    cat = torch.empty((B, 320, H, W), device=skip.device, dtype=torch.float32)
+    with torch.cuda.device(skip.device), _timed("spp_upsample_concat_fwd"):
+        _lib.check(_lib.load().cmfb200_spp_upsample_concat_fwd(_p(raw), _p(skip), _p(b4), _p(b3), _p(b2), _p(b1), _p(cat),
+                                                               B, H, W, _stream()), "spp_upsample_concat_fwd")
+    return cat
+
+
 def gn_stats(x):
     _req(x)
     B, C = x.shape[:2]

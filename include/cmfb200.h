@@ -116,6 +116,15 @@ int cmfb200_pack_conv2d_weight(const float* weight, float* packed, int Cout, int
 int cmfb200_conv2d_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
                        int B, int Cin, int Cout, int H, int W, int ksize, int stride, int dilation, void* stream);
 
+/* SPP tail of the feature extractor (cmfsm.py:152-170, 207-233).
+ * pool: x [B,C,H,W] -> average pools with kernel = stride = 8/16/32/64 (floor mode): p8 [B,C,H/8,W/8] ... p64.
+ * upsample_concat: cat [B,320,H,W] = [raw(64) | skip(128) | up(b4) | up(b3) | up(b2) | up(b1)], b4..b1 =
+ * [B,32,H/8,W/8] .. [B,32,H/64,W/64], bilinear, align_corners=False (F.interpolate semantics). */
+int cmfb200_spp_pool_fwd(const float* x, float* p8, float* p16, float* p32, float* p64,
+                         int B, int C, int H, int W, void* stream);
+int cmfb200_spp_upsample_concat_fwd(const float* raw, const float* skip, const float* b4, const float* b3,
+                                    const float* b2, const float* b1, float* cat, int B, int H, int W, void* stream);
+
 /* ---- K3: GroupNorm (+ residual add) (+ ReLU) ---------------------------------------------------
  * Replaces nn.GroupNorm(32,C) (cmfsm.py:58,269,280), the residual adds (:288,297,299,685,687,690,693)
  * and nn.ReLU / F.relu around them.

@@ -396,3 +396,19 @@ def test_conv3d_c8_cout1_vs_oracle(B, D, H, W):
     want = F.conv3d(x.to(torch.bfloat16).double(), wgt.double(), None, 1, 1).squeeze(1)
     got = ops.conv3d_c8_cout1(ops.f32_to_c8(x.to(DEV)), wgt.to(DEV))
     assert _rel_l2(got, want) < 1e-5  # fp32 accumulation of exactly representable bf16 inputs
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 64, 128), (2, 144, 240), (1, 96, 312)])
+def test_spp_pool_and_upsample_concat_vs_oracle(B, H, W):
+    """SPP pools (floor mode) and the bilinear upsample + concat vs the ATen ops the reference calls."""
+    from cmf_b200 import ops
+
+    skip = _rand(B, 128, H, W, seed=97)
+    raw = _rand(B, 64, H, W, seed=98)
+    got = ops.spp_pool(skip.to(DEV))
+    for k, g in zip((64, 32, 16, 8), got):
+        torch.testing.assert_close(g.cpu(), F.avg_pool2d(skip, (k, k), (k, k)), rtol=1e-5, atol=1e-6)
+    bs = [_rand(B, 32, H // k, W // k, seed=100 + k) for k in (8, 16, 32, 64)]  # b4, b3, b2, b1
+    cat = ops.spp_upsample_concat(raw.to(DEV), skip.to(DEV), *[t.to(DEV) for t in bs])
+    want = torch.cat([raw, skip] + [F.interpolate(t, (H, W), mode="bilinear", align_corners=False) for t in bs], 1)
+    torch.testing.assert_close(cat.cpu(), want, rtol=1e-5, atol=1e-5)
