@@ -236,6 +236,10 @@ def run_ours(args, rank, world, local_rank):
         k1_name = "cost_volume_concat_fwd" if args.aggregation == "fp32" else "cost_volume_concat_c8_bf16"
         k1_bytes = 2 * 32 * h * w * 4 + 64 * D * h * w * s_out
         k1_n, k1_ms = kernels.get(k1_name, (0, 0.0))
+        k1_traffic = None  # dram read+write bytes per launch of the fp32 kernel, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")
+        if args.aggregation == "fp32" and os.path.exists(tpath):
+            k1_traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
         k1_gbs = (k1_bytes * k1_n / (k1_ms * 1e-3) / 1e9) if k1_ms > 0 else None
         share = {k: {"launches": n // args.steps, "ms_per_step": ms / args.steps,
                      "share": ms / ms_eager} for k, (n, ms) in sorted(kernels.items())}
@@ -267,7 +271,8 @@ def run_ours(args, rank, world, local_rank):
                                 "ms_per_step_eager_with_events": ms_eager / args.steps},
                 "roofline": {"kernel": k1_name + " (K1)", "bound": "hbm", "achieved": k1_gbs,
                              "peak": hbm_peak, "unit": "GB/s", "frac": (k1_gbs / hbm_peak) if k1_gbs else None,
-                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
+                             "traffic": k1_traffic, "traffic_source": "profiles/k1_ncu_traffic.json (ncu --set full)",
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
                              "us_per_launch": (k1_ms / k1_n * 1e3) if k1_n else None},
                 "kernels": share, "clocks": sampler.summary()}
         if ig_n:
