@@ -96,32 +96,36 @@ __global__ void __launch_bounds__(kIgThreads, 2)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
-                                       ((uint32_t)(128 >> 4) << 24);
-            const uint32_t a0 = smem_u32(sA), w_0 = smem_u32(sW);
-            uint32_t started = 0;  // bit per (ph,pw) class: accumulator already initialised
-            mbar_wait(barA, 0);
+        // MMA issuer: whole warp converged, one elected lane issues (see conv3d_igemm_persistent.cu)
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_lo = umma_desc_lo(smem_u32(sA), G::CHUNK_BYTES), a_hi = umma_desc_hi(kS2PW * 16);
+        const uint32_t w_lo = umma_desc_lo(smem_u32(sW), COUT * 16), b_hi = umma_desc_hi(128);
+        uint32_t started = 0;  // bit per (ph,pw) class: accumulator already initialised
+        mbar_wait(barA, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int t = 0; t < ntap; ++t) {
+            const int s = t % NS;
+            const int jd = t / 9, kh = (t % 9) / 3, kw = t % 3;
+            const int sd = (pd && jd == 1) ? 1 : 0;  // k=0 reads input i+1
+            const int sh = (kh == 0) ? 1 : 0, sw = (kw == 0) ? 1 : 0;
+            const int cls = ((kh != 1) ? 2 : 0) | ((kw != 1) ? 1 : 0);
+            mbar_wait(full + s, (t / NS) & 1);
             tc_fence_after();
-            for (int t = 0; t < ntap; ++t) {
-                const int s = t % NS;
-                const int jd = t / 9, kh = (t % 9) / 3, kw = t % 3;
-                const int sd = (pd && jd == 1) ? 1 : 0;         // k=0 reads input i+1
-                const int sh = (kh == 0) ? 1 : 0, sw = (kw == 0) ? 1 : 0;
-                const int cls = ((kh != 1) ? 2 : 0) | ((kw != 1) ? 1 : 0);
-                mbar_wait(full + s, (t / NS) & 1);
-                tc_fence_after();
-                const uint32_t arow = a0 + ((sd * kS2PH + sh) * kS2PW + sw) * 16;
+            if (elect_one()) {
+                const uint32_t arow = ((sd * kS2PH + sh) * kS2PW + sw) * 16;
 #pragma unroll
                 for (int kc = 0; kc < CIN / 16; ++kc) {
-                    const uint64_t ad = umma_desc(arow + 2 * kc * G::CHUNK_BYTES, G::CHUNK_BYTES, kS2PW * 16);
-                    const uint64_t bd = umma_desc(w_0 + s * G::TAP_BYTES + 2 * kc * (COUT * 16), COUT * 16, 128);
+                    const uint64_t ad = umma_desc_at(a_lo, a_hi, arow + 2 * kc * G::CHUNK_BYTES);
+                    const uint64_t bd = umma_desc_at(w_lo, b_hi, s * G::TAP_BYTES + 2 * kc * (COUT * 16));
                     umma_bf16(tmem_base + cls * COUT, ad, bd, idesc, (((started >> cls) & 1u) | (uint32_t)kc) ? 1u : 0u);
                 }
-                started |= 1u << cls;
                 umma_commit(empty + s);
+                if (t == ntap - 1) umma_commit(barD);
             }
-            umma_commit(barD);
+            __syncwarp();
+            started |= 1u << cls;
         }
     } else {
         const int quad = warp & 3;
@@ -211,7 +215,7 @@ __device__ __forceinline__ int s2_tap(int p, int j) { return p ? (j == 0 ? 0 : 2
 __device__ __forceinline__ int s2_shift(int k) { return k == 0 ? 0 : 1; }
 
 template <int CIN, int COUT, int BD, int NSA, int NS>
-__global__ void __launch_bounds__(kIgThreads, 1)
+__global__ void __launch_bounds__(kIgThreads, (CIN == 32) ? 2 : 1)
     conv3d_s2_igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_xs, const __nv_bfloat16* __restrict__ wpk,
                                 __nv_bfloat16* __restrict__ y, double* __restrict__ gn_sums, int Do, int Ho, int Wo,
                                 int tiles_w) {
@@ -279,40 +283,45 @@ __global__ void __launch_bounds__(kIgThreads, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
-                                       ((uint32_t)(128 >> 4) << 24);
-            const uint32_t a_base = smem_u32(sA), w_0 = smem_u32(sW);
-            int t = 0;
-            for (int par = 0; par < 8; ++par) {
-                const int sa = par % NSA;
-                const uint32_t a0 = a_base + sa * G::STAGE_STRIDE;
-                mbar_wait(fullA + sa, (par / NSA) & 1);
+        // MMA issuer: whole warp converged, one elected lane issues
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_hi = umma_desc_hi(kS2PW * 16), b_hi = umma_desc_hi(128);
+        const uint32_t w_lo = umma_desc_lo(smem_u32(sW), COUT * 16);
+        int t = 0;
+#pragma unroll 1
+        for (int par = 0; par < 8; ++par) {
+            const int sa = par % NSA;
+            const uint32_t a_lo = umma_desc_lo(smem_u32(sA) + sa * G::STAGE_STRIDE, G::CHUNK_BYTES);
+            mbar_wait(fullA + sa, (par / NSA) & 1);
+            tc_fence_after();
+            const int pd = par >> 2, ph = (par >> 1) & 1, pw = par & 1;
+            const int ntp = s2_ntaps(pd) * s2_ntaps(ph) * s2_ntaps(pw);
+#pragma unroll 1
+            for (int j = 0; j < ntp; ++j, ++t) {
+                // same (jd, jh, jw) enumeration order as the producer
+                const int jw = j % s2_ntaps(pw), jh = (j / s2_ntaps(pw)) % s2_ntaps(ph), jd = j / (s2_ntaps(pw) * s2_ntaps(ph));
+                const int sd = s2_shift(s2_tap(pd, jd)), sh = s2_shift(s2_tap(ph, jh)), sw = s2_shift(s2_tap(pw, jw));
+                const int s = t % NS;
+                mbar_wait(fullW + s, (t / NS) & 1);
                 tc_fence_after();
-                const int pd = par >> 2, ph = (par >> 1) & 1, pw = par & 1;
-                for (int jd = 0; jd < s2_ntaps(pd); ++jd)
-                    for (int jh = 0; jh < s2_ntaps(ph); ++jh)
-                        for (int jw = 0; jw < s2_ntaps(pw); ++jw, ++t) {
-                            const int sd = s2_shift(s2_tap(pd, jd)), sh = s2_shift(s2_tap(ph, jh)),
-                                      sw = s2_shift(s2_tap(pw, jw));
-                            const int s = t % NS;
-                            mbar_wait(fullW + s, (t / NS) & 1);
-                            tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t arow = (((sd * kS2PH + sh) * kS2PW) + sw) * 16;
 #pragma unroll
-                            for (int mt = 0; mt < BD; ++mt) {
-                                const uint32_t arow = a0 + ((((mt + sd) * kS2PH + sh) * kS2PW) + sw) * 16;
+                    for (int mt = 0; mt < BD; ++mt) {
 #pragma unroll
-                                for (int kc = 0; kc < CIN / 16; ++kc) {
-                                    const uint64_t ad = umma_desc(arow + 2 * kc * G::CHUNK_BYTES, G::CHUNK_BYTES, kS2PW * 16);
-                                    const uint64_t bd = umma_desc(w_0 + s * G::TAP_BYTES + 2 * kc * (COUT * 16), COUT * 16, 128);
-                                    umma_bf16(tmem_base + mt * COUT, ad, bd, idesc, (t | kc) != 0 ? 1u : 0u);
-                                }
-                            }
-                            umma_commit(emptyW + s);
+                        for (int kc = 0; kc < CIN / 16; ++kc) {
+                            const uint64_t ad = umma_desc_at(a_lo, a_hi, arow + mt * kS2PH * kS2PW * 16 + 2 * kc * G::CHUNK_BYTES);
+                            const uint64_t bd = umma_desc_at(w_lo, b_hi, s * G::TAP_BYTES + 2 * kc * (COUT * 16));
+                            umma_bf16(tmem_base + mt * COUT, ad, bd, idesc, (t | kc) != 0 ? 1u : 0u);
                         }
-                umma_commit(emptyA + sa);  // this parity sub-volume may be overwritten
+                    }
+                    umma_commit(emptyW + s);
+                    if (j == ntp - 1) umma_commit(emptyA + sa);  // this parity sub-volume may be overwritten
+                    if (t == 26) umma_commit(barD);
+                }
+                __syncwarp();
             }
-            umma_commit(barD);
         }
     } else {
         const int quad = warp & 3;
@@ -443,8 +452,8 @@ extern "C" int cmfb200_deconv3d_igemm_bf16_fwd(const void* x_c8, const void* pac
     CMF_REQUIRE(x_c8 && packed_w && y_c8, "deconv3d_igemm_bf16_fwd: null pointer");
     CMF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "deconv3d_igemm_bf16_fwd: non-positive dimension");
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cin == 64 && Cout == 64) return launch_deconv_igemm<64, 64, 6>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
-    if (Cin == 64 && Cout == 32) return launch_deconv_igemm<64, 32, 8>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
+    if (Cin == 64 && Cout == 64) return launch_deconv_igemm<64, 64, 8>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
+    if (Cin == 64 && Cout == 32) return launch_deconv_igemm<64, 32, 16>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
     CMF_REQUIRE(false, "deconv3d_igemm_bf16_fwd: unsupported (Cin=%d, Cout=%d); supported: 64->64, 64->32", Cin, Cout);
 }
 
@@ -455,9 +464,9 @@ extern "C" int cmfb200_conv3d_s2_igemm_bf16_fwd(const void* x_split_c8, const vo
     CMF_REQUIRE(B > 0 && Do > 0 && Ho > 0 && Wo > 0, "conv3d_s2_igemm_bf16_fwd: non-positive dimension");
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 32 && Cout == 64)
-        return launch_s2_igemm<32, 64, 2, 3, 6>(x_split_c8, packed_w, y_c8, gn_sums, B, Do, Ho, Wo, st);
+        return launch_s2_igemm<32, 64, 2, 2, 10>(x_split_c8, packed_w, y_c8, gn_sums, B, Do, Ho, Wo, st);
     if (Cin == 64 && Cout == 64)
-        return launch_s2_igemm<64, 64, 2, 2, 6>(x_split_c8, packed_w, y_c8, gn_sums, B, Do, Ho, Wo, st);
+        return launch_s2_igemm<64, 64, 2, 2, 10>(x_split_c8, packed_w, y_c8, gn_sums, B, Do, Ho, Wo, st);
     CMF_REQUIRE(false, "conv3d_s2_igemm_bf16_fwd: unsupported (Cin=%d, Cout=%d); supported: 32->64, 64->64", Cin, Cout);
 }
 
