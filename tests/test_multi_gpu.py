@@ -40,3 +40,28 @@ def test_row_band_sharding_matches_single_gpu():
 def test_data_parallel_gradients_match_single_process():
     rep = _torchrun("check_dp_train.py", "--per-rank-batch", "1", "--steps", "1")
     assert rep["world"] == 2 and rep["grad_rel_l2"] < 2e-2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_reference_style_dataparallel_wrapper():
+    """The reference drivers wrap the model in nn.DataParallel (test.py:40-44, one sample per replica thread):
+    the drop-in module and libcmfb200 must work re-entrantly on two devices from two Python threads."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "explicit-context-mapping-for-stereo-matching_b200"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import golden_common as gc
+    from cmf.models import get_model
+
+    torch.manual_seed(gc.WEIGHT_SEED)
+    model = get_model("cmfsm").cuda(0).eval()
+    left, right = gc.seeded_pair(2, 256, 512, seed=21)
+    left, right = left.cuda(0), right.cuda(0)
+    with torch.no_grad():
+        single = [model(left[i:i + 1].contiguous(), right[i:i + 1].contiguous()) for i in range(2)]
+        dp = torch.nn.DataParallel(model, device_ids=[0, 1])
+        out = dp(left, right)
+    assert out[2].shape == (2, 1, 256, 512) and out[2].device.index == 0
+    for i in range(2):
+        for a, b in zip(out, single[i]):
+            torch.testing.assert_close(a[i:i + 1], b, rtol=0, atol=5e-3)
