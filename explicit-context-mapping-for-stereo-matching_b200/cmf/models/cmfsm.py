@@ -349,6 +349,54 @@ class cmfsm(nn.Module):
         y, _ = ops.conv3d_k3(ext, self._pack(head[2]), 1)
         return y[:, 0, :, 1:-1].contiguous()
 
+    # 2-D extractor on a row band: every 3x3 conv exchanges `dilation` halo rows (stride 2: two top rows), every
+    # GroupNorm all-reduces its sums; the SPP pools are computed per band (bands are multiples of 64 rows at 1/4
+    # resolution, so every pooling window lies inside one band) and the tiny pooled maps are all-gathered.
+    def _conv2_band(self, conv, x):
+        k, s, d = conv.kernel_size[0], conv.stride[0], conv.dilation[0]
+        packed = self._pack(conv)
+        if k == 1:
+            return ops.conv2d(x, packed, 1, s, 1)[0]
+        if s == 2:
+            y, _ = ops.conv2d(par.exchange_row_halo(x, 2, 0, dim=2), packed, 3, 2, 1)
+            return y[:, :, 1:1 + x.shape[2] // 2].contiguous()
+        y, _ = ops.conv2d(par.exchange_row_halo(x, d, d, dim=2), packed, 3, 1, d)
+        return y[:, :, d:-d].contiguous()
+
+    def _cg2_band(self, block, x, full_rows, residual=None, relu=False):
+        y = self._conv2_band(block[0], x)
+        sums = par.allreduce_gn_sums(ops.gn_stats(y)) * (float(y.shape[2]) / float(full_rows))
+        return ops.gn_apply(y, sums, block[1].weight, block[1].bias, residual, relu, out=y)
+
+    def _features_band(self, both, r0, r1):
+        """Rows [r0,r1) (1/4-resolution units) of the feature maps of `both` ([2B,3,H,W], whole images)."""
+        fe = self.feature_extraction
+        H, h = both.shape[2], both.shape[2] // 4
+        x = both[:, :, 4 * r0:4 * r1].contiguous()
+        o = self._cg2_band(fe.firstconv[0], x, H, relu=True)
+        o = self._cg2_band(fe.firstconv[2], o, H, relu=True)
+        o = self._cg2_band(fe.firstconv[4], o, H, relu=True)
+        full = self._conv2_band(fe.firstconv[6], o)
+        gn0 = fe.secondconv[0]
+        sums = par.allreduce_gn_sums(ops.gn_stats(full)) * (float(full.shape[2]) / float(H))
+        o = ops.gn_apply(full, sums, gn0.weight, gn0.bias, None, True)
+        o = self._cg2_band(fe.secondconv[2], o, H // 2, relu=True)
+        o = self._cg2_band(fe.secondconv[4], o, H // 2, relu=True)
+        raw = None
+        for name, rows in (("layer1", H // 2), ("layer2", h), ("layer3", h), ("layer4", h)):
+            for unit in getattr(fe, name):
+                t = self._cg2_band(unit.conv1[0], o, rows, relu=True)
+                skip = o if unit.downsample is None else self._cg2_band(unit.downsample, o, rows)
+                o = self._cg2_band(unit.conv2, t, rows, residual=skip)
+            if name == "layer2":
+                raw = o
+        skip = o
+        pooled = [par.gather_bands(p, dim=2) for p in ops.spp_pool(skip)]  # whole-image pooled maps (tiny)
+        b1, b2, b3, b4 = [self._cg2(getattr(fe, "branch%d" % (i + 1))[1], p, relu=True) for i, p in enumerate(pooled)]
+        cat = ops.spp_upsample_concat(raw, skip, b4, b3, b2, b1, full_rows=h, row_offset=r0)
+        o = self._cg2_band(fe.lastconv[0], cat, h, relu=True)
+        return self._conv2_band(fe.lastconv[2], o), full
+
     @torch.no_grad()
     def forward_row_bands(self, left, right, gather=True):
         """Sharded inference of ONE pair over all ranks (every rank passes the same images).  Returns the three
@@ -359,15 +407,28 @@ class cmfsm(nn.Module):
         h = H // 4
         if h % (16 * n):
             raise ValueError("row-band sharding needs H/4=%d to be a multiple of 16*world=%d" % (h, 16 * n))
-        feat, full = self._features(torch.cat([left.float(), right.float()], 0).contiguous())  # replicated
-        lfeat, rfeat = feat[:B], feat[B:]
-        hr = full[:B].contiguous()
-        scale = hr.shape[-1] // lfeat.shape[-1]
-        D = self.maxdisp // scale
+        both = torch.cat([left.float(), right.float()], 0).contiguous()
         sim = self.mapping_matrix.similarity1
-        weights9 = ops.ctxmap_weights(lfeat, hr, sim.conv0.weight, sim.conv1.weight, sim.conv2.weight, sim.conv3.weight)
-        r0, r1 = par.band_rows(h, n, r, multiple=16)
-        cost = ops.cost_volume_concat(lfeat[:, :, r0:r1].contiguous(), rfeat[:, :, r0:r1].contiguous(), D)
+        mlp = (sim.conv0.weight, sim.conv1.weight, sim.conv2.weight, sim.conv3.weight)
+        scale = 4
+        D = self.maxdisp // scale
+        if h % (64 * n) == 0:
+            # bands are multiples of 64 rows: the 2-D extractor and K5 are sharded too
+            r0, r1 = par.band_rows(h, n, r, multiple=64)
+            feat, full = self._features_band(both, r0, r1)
+            lband, rband = feat[:B].contiguous(), feat[B:].contiguous()
+            lr_ext = par.exchange_row_halo(lband, 1, 1, dim=2)
+            hr_ext = par.exchange_row_halo(full[:B].contiguous(), scale, scale, dim=2)
+            valid = (1 if r0 == 0 else 0, lr_ext.shape[2] - (1 if r1 == h else 0))
+            wband = ops.ctxmap_weights(lr_ext, hr_ext, *mlp, valid_rows=valid)  # rows of cells r0-1 .. r1
+        else:
+            feat, full = self._features(both)  # replicated on every rank
+            r0, r1 = par.band_rows(h, n, r, multiple=16)
+            lband, rband = feat[:B, :, r0:r1].contiguous(), feat[B:, :, r0:r1].contiguous()
+            weights9 = ops.ctxmap_weights(feat[:B], full[:B].contiguous(), *mlp)
+            # weight rows outside the image are zero (those neighbours contribute nothing)
+            wband = F.pad(weights9, (0, 0, scale, scale))[:, :, scale * r0:scale * (r1 + 2)].contiguous()
+        cost = ops.cost_volume_concat(lband, rband, D)
         cost0 = self._cg_band(self.dres0[0], cost, h, relu=True)
         del cost
         cost0 = self._cg_band(self.dres0[2], cost0, h, relu=True)
@@ -378,10 +439,7 @@ class cmfsm(nn.Module):
         out3, _p3, _q3 = self._hourglass_band(self.dres4, out2, pre1, post2, cost0, h)
         cs = [par.exchange_row_halo(self._classify_band(getattr(self, "classif%d" % i), o, h), 1, 1, dim=2)
               for i, o in ((1, out1), (2, out2), (3, out3))]
-        # K4 on the band + 1-cell halo; weight rows outside the image are zero (those neighbours contribute nothing)
-        wpad = F.pad(weights9, (0, 0, scale, scale))
-        wband = wpad[:, :, scale * r0:scale * (r1 + 2)].contiguous()
-        outs = ops.softargmin_ctxmap(cs[0], cs[1], cs[2], wband, scale)
+        outs = ops.softargmin_ctxmap(cs[0], cs[1], cs[2], wband, scale)  # K4 on the band + 1-cell halo
         outs = [o[:, :, scale:-scale].contiguous() for o in outs]
         return tuple(par.gather_bands(o, dim=2) for o in outs) if gather else tuple(outs)
 

@@ -185,8 +185,9 @@ def spp_pool(x):
     return ps[3], ps[2], ps[1], ps[0]
 
 
-def spp_upsample_concat(raw, skip, b4, b3, b2, b1):
-    """cat([raw, skip, up(b4), up(b3), up(b2), up(b1)], 1) with bilinear (align_corners=False) upsampling."""
+def spp_upsample_concat(raw, skip, b4, b3, b2, b1, full_rows=None, row_offset=0):
+    """cat([raw, skip, up(b4), up(b3), up(b2), up(b1)], 1) with bilinear (align_corners=False) upsampling.
+    Row bands: raw/skip hold rows [row_offset, row_offset+H) of an image with `full_rows` rows; b* cover all of it."""
     _req(raw, skip, b4, b3, b2, b1)
     B, _, H, W = skip.shape
     if raw.shape[1] != 64 or skip.shape[1] != 128 or any(t.shape[1] != 32 for t in (b4, b3, b2, b1)):
@@ -194,7 +195,8 @@ def spp_upsample_concat(raw, skip, b4, b3, b2, b1):
     cat = torch.empty((B, 320, H, W), device=skip.device, dtype=torch.float32)
     with torch.cuda.device(skip.device), _timed("spp_upsample_concat_fwd"):
         _lib.check(_lib.load().cmfb200_spp_upsample_concat_fwd(_p(raw), _p(skip), _p(b4), _p(b3), _p(b2), _p(b1), _p(cat),
-                                                               B, H, W, _stream()), "spp_upsample_concat_fwd")
+                                                               B, H, W, H if full_rows is None else full_rows,
+                                                               row_offset, _stream()), "spp_upsample_concat_fwd")
     return cat
 
 
@@ -230,8 +232,9 @@ def conv3d_gn(x, packed, gamma, beta, stride=1, transposed=False, residual=None,
 
 
 # ------------------------------------------------------------------------------------------ K5 / K4
-def ctxmap_weights(lr, hr, w0, w1, w2, w3):
-    """eight_related_context_mapping: [B,32,h,w],[B,32,H,W] -> [B,9,H,W] (cmf/models/cmfsm.py:443-593)."""
+def ctxmap_weights(lr, hr, w0, w1, w2, w3, valid_rows=None):
+    """eight_related_context_mapping: [B,32,h,w],[B,32,H,W] -> [B,9,H,W] (cmf/models/cmfsm.py:443-593).
+    `valid_rows` = (y0, y1): low-res rows of `lr` that lie inside the image (row bands pass halo rows)."""
     ws = [w.detach().reshape(w.shape[0], w.shape[1]).contiguous() for w in (w0, w1, w2, w3)]
     _req(lr, hr, *ws)
     B, C, h, w = lr.shape
@@ -242,9 +245,10 @@ def ctxmap_weights(lr, hr, w0, w1, w2, w3):
     if H != h * scale or W != w * scale:
         raise ValueError("hr %dx%d is not an integer multiple of lr %dx%d" % (H, W, h, w))
     out = torch.empty((B, 9, H, W), device=lr.device, dtype=torch.float32)
+    vy0, vy1 = (0, h) if valid_rows is None else valid_rows
     with torch.cuda.device(lr.device), _timed("ctxmap_weights_fwd"):
         _lib.check(_lib.load().cmfb200_ctxmap_weights_fwd(_p(lr), _p(hr), _p(ws[0]), _p(ws[1]), _p(ws[2]), _p(ws[3]),
-                                                          _p(out), B, h, w, scale, _stream()), "ctxmap_weights_fwd")
+                                                          _p(out), B, h, w, scale, vy0, vy1, _stream()), "ctxmap_weights_fwd")
     return out
 
 

@@ -31,7 +31,7 @@ __device__ __forceinline__ float pos_code(int kind, int i, int s) {
 __global__ void __launch_bounds__(kK5Threads) ctxmap_weights_kernel(
     const float* __restrict__ lr, const float* __restrict__ hr, const float* __restrict__ w0,
     const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3,
-    float* __restrict__ out, int h, int w, int scale) {
+    float* __restrict__ out, int h, int w, int scale, int vy0, int vy1) {
     __shared__ __align__(16) float sW0lr[32][32];  // [in][out]
     __shared__ __align__(16) float sW0hr[32][32];  // [in][out]
     __shared__ __align__(16) float sW0c[2][32];    // code channels 64,65
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kK5Threads) ctxmap_weights_kernel(
             const int ky = (k == 3 || k == 7) ? 2 : ((k == 4 || k == 8) ? 1 : 0);  // code over y (channel 65)
             const int ny = cy + dy, nx = cx + dx;
             float logit = -100.0f;
-            if (ny >= 0 && ny < h && nx >= 0 && nx < w) {
+            if (ny >= vy0 && ny < vy1 && nx >= 0 && nx < w) {  // [vy0,vy1): cell rows inside the IMAGE (row bands pass halos)
                 const float p0 = pos_code(kx, px, scale), p1 = pos_code(ky, py, scale);
                 const float* alr = &sAlr[(ly + dy) * kK5HaloX + lx + dx][0];
                 float h1[16];
@@ -179,13 +179,15 @@ using namespace cmfb200;
 
 extern "C" int cmfb200_ctxmap_weights_fwd(const float* lr, const float* hr, const float* w0, const float* w1,
                                           const float* w2, const float* w3, float* weights9, int B, int h, int w,
-                                          int scale, void* stream) {
+                                          int scale, int valid_y0, int valid_y1, void* stream) {
     CMF_REQUIRE(lr && hr && w0 && w1 && w2 && w3 && weights9, "ctxmap_weights_fwd: null pointer");
     CMF_REQUIRE(B > 0 && h > 0 && w > 0, "ctxmap_weights_fwd: non-positive dimension");
     CMF_REQUIRE(scale >= 2 && scale % 2 == 0, "ctxmap_weights_fwd: odd scale %d (the reference exit()s)", scale);
     CMF_REQUIRE(B <= 65535, "ctxmap_weights_fwd: B exceeds grid limit");
     dim3 grid((unsigned)cdiv(w, kK5CellsX), (unsigned)cdiv(h, kK5CellsY), (unsigned)B);
-    ctxmap_weights_kernel<<<grid, kK5Threads, 0, (cudaStream_t)stream>>>(lr, hr, w0, w1, w2, w3, weights9, h, w, scale);
+    CMF_REQUIRE(valid_y0 >= 0 && valid_y1 <= h && valid_y0 < valid_y1, "ctxmap_weights_fwd: bad valid row range [%d,%d) for h=%d", valid_y0, valid_y1, h);
+    ctxmap_weights_kernel<<<grid, kK5Threads, 0, (cudaStream_t)stream>>>(lr, hr, w0, w1, w2, w3, weights9, h, w, scale,
+                                                                          valid_y0, valid_y1);
     CMF_LAUNCH_CHECK("ctxmap_weights_kernel");
     return CMFB200_OK;
 }

@@ -57,7 +57,7 @@ __device__ __forceinline__ float bilinear_at(const float* __restrict__ m, int h,
 // cat[b][0:64] = raw, [64:192] = skip, [192:224] = up(branch4), [224:256] = up(b3), [256:288] = up(b2), [288:320] = up(b1)
 __global__ void spp_upsample_concat_kernel(const float* __restrict__ raw, const float* __restrict__ skip, BranchMap b4,
                                            BranchMap b3, BranchMap b2, BranchMap b1, float* __restrict__ cat, int H,
-                                           int W) {
+                                           int W, int H_full, int y_off) {
     const int b = blockIdx.z, c = blockIdx.y;  // c in [0,320)
     const size_t plane = (size_t)H * W;
     float* dst = cat + ((size_t)b * 320 + c) * plane;
@@ -75,10 +75,10 @@ __global__ void spp_upsample_concat_kernel(const float* __restrict__ raw, const 
     const int k = (c - 192) >> 5, ch = (c - 192) & 31;
     const BranchMap bm = k == 0 ? b4 : (k == 1 ? b3 : (k == 2 ? b2 : b1));
     const float* m = bm.ptr + ((size_t)b * 32 + ch) * bm.h * bm.w;
-    const float ry = (float)bm.h / (float)H, rx = (float)bm.w / (float)W;
+    const float ry = (float)bm.h / (float)H_full, rx = (float)bm.w / (float)W;  // branch maps cover the FULL image
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
         const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
-        dst[i] = bilinear_at(m, bm.h, bm.w, ry * ((float)y + 0.5f) - 0.5f, rx * ((float)x + 0.5f) - 0.5f);
+        dst[i] = bilinear_at(m, bm.h, bm.w, ry * ((float)(y + y_off) + 0.5f) - 0.5f, rx * ((float)x + 0.5f) - 0.5f);
     }
 }
 
@@ -109,12 +109,13 @@ extern "C" int cmfb200_spp_pool_fwd(const float* x, float* p8, float* p16, float
 
 extern "C" int cmfb200_spp_upsample_concat_fwd(const float* raw, const float* skip, const float* b4, const float* b3,
                                                const float* b2, const float* b1, float* cat, int B, int H, int W,
-                                               void* stream) {
+                                               int H_full, int y_off, void* stream) {
     CMF_REQUIRE(raw && skip && b4 && b3 && b2 && b1 && cat, "spp_upsample_concat_fwd: null pointer");
-    CMF_REQUIRE(B > 0 && H >= 64 && W >= 64 && B <= 65535, "spp_upsample_concat_fwd: bad shape");
-    const BranchMap m4{b4, H / 8, W / 8}, m3{b3, H / 16, W / 16}, m2{b2, H / 32, W / 32}, m1{b1, H / 64, W / 64};
+    CMF_REQUIRE(B > 0 && H > 0 && H_full >= 64 && W >= 64 && B <= 65535, "spp_upsample_concat_fwd: bad shape");
+    CMF_REQUIRE(y_off >= 0 && y_off + H <= H_full, "spp_upsample_concat_fwd: rows [%d,%d) outside the image height %d", y_off, y_off + H, H_full);
+    const BranchMap m4{b4, H_full / 8, W / 8}, m3{b3, H_full / 16, W / 16}, m2{b2, H_full / 32, W / 32}, m1{b1, H_full / 64, W / 64};
     dim3 grid((unsigned)min((long long)16, cdiv((long long)H * W, 1024)), 320, (unsigned)B);
-    spp_upsample_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, skip, m4, m3, m2, m1, cat, H, W);
+    spp_upsample_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, skip, m4, m3, m2, m1, cat, H, W, H_full, y_off);
     CMF_LAUNCH_CHECK("spp_upsample_concat_kernel");
     return CMFB200_OK;
 }

@@ -119,11 +119,13 @@ int cmfb200_conv2d_fwd(const float* x, const float* packed_w, float* y, double* 
 /* SPP tail of the feature extractor (cmfsm.py:152-170, 207-233).
  * pool: x [B,C,H,W] -> average pools with kernel = stride = 8/16/32/64 (floor mode): p8 [B,C,H/8,W/8] ... p64.
  * upsample_concat: cat [B,320,H,W] = [raw(64) | skip(128) | up(b4) | up(b3) | up(b2) | up(b1)], b4..b1 =
- * [B,32,H/8,W/8] .. [B,32,H/64,W/64], bilinear, align_corners=False (F.interpolate semantics). */
+ * [B,32,H_full/8,W/8] .. [B,32,H_full/64,W/64], bilinear, align_corners=False (F.interpolate semantics);
+ * raw/skip/cat hold rows [y_off, y_off+H) of an image of height H_full (H_full=H, y_off=0: whole image). */
 int cmfb200_spp_pool_fwd(const float* x, float* p8, float* p16, float* p32, float* p64,
                          int B, int C, int H, int W, void* stream);
 int cmfb200_spp_upsample_concat_fwd(const float* raw, const float* skip, const float* b4, const float* b3,
-                                    const float* b2, const float* b1, float* cat, int B, int H, int W, void* stream);
+                                    const float* b2, const float* b1, float* cat, int B, int H, int W,
+                                    int H_full, int y_off, void* stream);
 
 /* ---- K3: GroupNorm (+ residual add) (+ ReLU) ---------------------------------------------------
  * Replaces nn.GroupNorm(32,C) (cmfsm.py:58,269,280), the residual adds (:288,297,299,685,687,690,693)
@@ -143,10 +145,11 @@ int cmfb200_gn_apply(const float* x, const double* gn_sums, const float* gamma, 
  * lr: [B,32,h,w] (1/scale-res features), hr: [B,32,H,W] (full-res firstconv output), H=h*scale, W=w*scale,
  * scale in {4} (even).  w0:[32,66] w1:[16,32] w2:[8,16] w3:[1,8] (1x1 conv weights, no bias).
  * weights9: [B,9,H,W] softmax over the 9 neighbours (order c,l,r,t,b,lt,rt,lb,rb); out-of-image
- * neighbours take the constant logit -100. */
+ * neighbours take the constant logit -100.  [valid_y0, valid_y1) = low-res rows that are inside the IMAGE
+ * (0,h for a whole image; a row band passes its halo rows in lr/hr and marks them here). */
 int cmfb200_ctxmap_weights_fwd(const float* lr, const float* hr, const float* w0, const float* w1,
                                const float* w2, const float* w3, float* weights9,
-                               int B, int h, int w, int scale, void* stream);
+                               int B, int h, int w, int scale, int valid_y0, int valid_y1, void* stream);
 
 /* ---- K4: soft-argmin + x scale upsample + 9-neighbour context mapping ---------------------------
  * Replaces cmfsm.py:703-769 (3x softmax, disparityregression :111-123, ~60 slice kernels).

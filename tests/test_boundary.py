@@ -87,7 +87,7 @@ def test_c_abi_argument_validation_without_gpu():
     assert rc == -1 and b"multiple of 4" in L.cmfb200_last_error()
     rc = L.cmfb200_conv3d_k3_fwd(p, p, p, None, 1, 32, 48, 4, 4, 4, 1, None)
     assert rc == -1 and b"unsupported" in L.cmfb200_last_error()
-    rc = L.cmfb200_ctxmap_weights_fwd(p, p, p, p, p, p, p, 1, 4, 4, 3, None)
+    rc = L.cmfb200_ctxmap_weights_fwd(p, p, p, p, p, p, p, 1, 4, 4, 3, 0, 4, None)
     assert rc == -1 and b"odd scale" in L.cmfb200_last_error()
 
 
