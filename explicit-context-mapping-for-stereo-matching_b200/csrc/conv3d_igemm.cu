@@ -322,82 +322,56 @@ __global__ void __launch_bounds__(256) gn_apply_c8_bf16_kernel(const __nv_bfloat
 }
 
 // classifier tail conv (Cin -> 1, 3x3x3, pad 1) straight from C8/bf16 to the fp32 volume K4 consumes
-// (classifN.2, cmf/models/cmfsm.py:624,629,634).  N=1 has no tensor-core shape.  A CTA stages the halo'd
-// 4 x 10 x 34 voxel block of every channel group in shared memory (bf16, 16 B per voxel) and produces
-// 2 x 8 x 32 outputs; a thread owns 4 consecutive-w outputs, so per (group, kd, kh) it reads 6 voxels + 3 taps of
-// weights for 96 FMAs; fp32 accumulation.  Weights [Cin][27] fp32 are staged as [Cin/8][27][8].
-constexpr int kC1TD = 2, kC1TH = 8, kC1TW = 32;
-constexpr int kC1PD = kC1TD + 2, kC1PH = kC1TH + 2, kC1PW = kC1TW + 2;
-__global__ void __launch_bounds__(128) conv3d_c8_cout1_kernel(const __nv_bfloat16* __restrict__ x,
+// (classifN.2, cmf/models/cmfsm.py:624,629,634).  N=1 has no tensor-core shape; the op is bound by reading the
+// input once (106 MB at config 2): one thread per output voxel, 128-bit loads that hit L1 for the 27-fold reuse,
+// fp32 accumulation; weights [Cin][27] fp32 staged in shared memory as [Cin/8][27][8].
+__global__ void __launch_bounds__(256) conv3d_c8_cout1_kernel(const __nv_bfloat16* __restrict__ x,
                                                               const float* __restrict__ wgt, float* __restrict__ y,
-                                                              int NC, int D, int H, int W, int tiles_w) {
-    extern __shared__ __align__(16) uint8_t c1_smem[];
-    uint4* sx = reinterpret_cast<uint4*>(c1_smem);                                   // [NC][PD][PH][PW]
-    float* sw = reinterpret_cast<float*>(c1_smem + (size_t)NC * kC1PD * kC1PH * kC1PW * 16);  // [NC][27][8]
-    const int tile_x = blockIdx.x % tiles_w, tile_y = blockIdx.x / tiles_w;
-    const int w0 = tile_x * kC1TW, h0 = tile_y * kC1TH, d0 = blockIdx.y * kC1TD, b = blockIdx.z;
-    const size_t plane = (size_t)H * W, vol = (size_t)D * plane;
-    const uint4* xb = reinterpret_cast<const uint4*>(x) + (size_t)b * NC * vol;
-    for (int i = threadIdx.x; i < NC * 27 * 8; i += 128) {
+                                                              int NC, int D, int H, int W) {
+    extern __shared__ __align__(16) float sw[];  // [NC][27][8]
+    for (int i = threadIdx.x; i < NC * 27 * 8; i += 256) {
         const int j = i & 7, tap = (i >> 3) % 27, chunk = i / (27 * 8);
         sw[i] = wgt[(chunk * 8 + j) * 27 + tap];
     }
-    constexpr int PV = kC1PD * kC1PH * kC1PW;
-    for (int i = threadIdx.x; i < NC * PV; i += 128) {
-        const int chunk = i / PV;
-        int r = i - chunk * PV;
-        const int pw = r % kC1PW;
-        r /= kC1PW;
-        const int ph = r % kC1PH, pd = r / kC1PH;
-        const int d = d0 + pd - 1, h = h0 + ph - 1, w = w0 + pw - 1;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if ((unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
-            v = __ldg(xb + (size_t)chunk * vol + (size_t)d * plane + (size_t)h * W + w);
-        sx[i] = v;
-    }
     __syncthreads();
-    const int qx = threadIdx.x & 7, th = (threadIdx.x >> 3) & 7, td = threadIdx.x >> 6;  // 8 quads x 8 rows x 2 slices
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int chunk = 0; chunk < NC; ++chunk) {
-        const float* wc = sw + chunk * 27 * 8;
+    const size_t plane = (size_t)H * W, vol = (size_t)D * plane;
+    const int b = blockIdx.y;
+    const uint4* xb = reinterpret_cast<const uint4*>(x) + (size_t)b * NC * vol;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < vol; i += (size_t)gridDim.x * 256) {
+        const int w = (int)(i % W), h = (int)((i / W) % H), d = (int)(i / plane);
+        float acc = 0.f;
+        for (int chunk = 0; chunk < NC; ++chunk) {
+            const uint4* xc = xb + (size_t)chunk * vol;
+            const float* wc = sw + chunk * 27 * 8;
 #pragma unroll
-        for (int kd = 0; kd < 3; ++kd)
+            for (int kd = 0; kd < 3; ++kd) {
+                const int dd = d + kd - 1;
+                if ((unsigned)dd >= (unsigned)D) continue;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const uint4* row = sx + ((chunk * kC1PD + td + kd) * kC1PH + th + kh) * kC1PW + qx * 4;
-                float in[6][8];
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int hh = h + kh - 1;
+                    if ((unsigned)hh >= (unsigned)H) continue;
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    const uint4 raw = row[j];
-                    const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        in[j][2 * e] = __low2float(v[e]);
-                        in[j][2 * e + 1] = __high2float(v[e]);
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int ww = w + kw - 1;
+                        if ((unsigned)ww >= (unsigned)W) continue;
+                        const uint4 raw = __ldg(xc + (size_t)dd * plane + (size_t)hh * W + ww);
+                        const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                        const float4 w0 = *reinterpret_cast<const float4*>(wc + ((kd * 3 + kh) * 3 + kw) * 8);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wc + ((kd * 3 + kh) * 3 + kw) * 8 + 4);
+                        acc = fmaf(__low2float(v[0]), w0.x, acc);
+                        acc = fmaf(__high2float(v[0]), w0.y, acc);
+                        acc = fmaf(__low2float(v[1]), w0.z, acc);
+                        acc = fmaf(__high2float(v[1]), w0.w, acc);
+                        acc = fmaf(__low2float(v[2]), w1.x, acc);
+                        acc = fmaf(__high2float(v[2]), w1.y, acc);
+                        acc = fmaf(__low2float(v[3]), w1.z, acc);
+                        acc = fmaf(__high2float(v[3]), w1.w, acc);
                     }
                 }
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float4 wa = *reinterpret_cast<const float4*>(wc + ((kd * 3 + kh) * 3 + kw) * 8);
-                    const float4 wb = *reinterpret_cast<const float4*>(wc + ((kd * 3 + kh) * 3 + kw) * 8 + 4);
-                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                    for (int v = 0; v < 4; ++v)
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) acc[v] = fmaf(in[v + kw][c], wv[c], acc[v]);
-                }
             }
-    }
-    const int d = d0 + td, h = h0 + th, w = w0 + qx * 4;
-    if (d < D && h < H) {
-        float* py = y + (size_t)b * vol + (size_t)d * plane + (size_t)h * W + w;
-        if ((W & 3) == 0 && w + 3 < W) {
-            *reinterpret_cast<float4*>(py) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        } else {
-#pragma unroll
-            for (int v = 0; v < 4; ++v)
-                if (w + v < W) py[v] = acc[v];
         }
+        y[(size_t)b * vol + i] = acc;
     }
 }
 
@@ -545,15 +519,11 @@ extern "C" int cmfb200_conv3d_c8_cout1_fwd(const void* x_c8, const float* weight
                                            int W, void* stream) {
     CMF_REQUIRE(x_c8 && weight && y, "conv3d_c8_cout1_fwd: null pointer");
     CMF_REQUIRE(B > 0 && Cin > 0 && Cin % 8 == 0 && D > 0 && H > 0 && W > 0 && B <= 65535, "conv3d_c8_cout1_fwd: bad shape");
-    const int NC = Cin / 8;
-    const size_t smem = (size_t)NC * kC1PD * kC1PH * kC1PW * 16 + (size_t)Cin * 27 * sizeof(float);
-    CMF_REQUIRE(smem <= 200 * 1024, "conv3d_c8_cout1_fwd: Cin=%d does not fit the shared-memory tile", Cin);
-    CMF_CUDA(cudaFuncSetAttribute(conv3d_c8_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tiles_w = (int)cdiv(W, kC1TW), tiles_h = (int)cdiv(H, kC1TH);
-    dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)cdiv(D, kC1TD), (unsigned)B);
-    CMF_REQUIRE(grid.y <= 65535, "conv3d_c8_cout1_fwd: depth too large");
-    conv3d_c8_cout1_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_c8), weight,
-                                                                       y, NC, D, H, W, tiles_w);
+    const long long vol = (long long)D * H * W;
+    const size_t smem = (size_t)Cin * 27 * sizeof(float);
+    dim3 grid((unsigned)min((long long)kNumSMs * 16, cdiv(vol, 256)), (unsigned)B);
+    conv3d_c8_cout1_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_c8), weight,
+                                                                       y, Cin / 8, D, H, W);
     CMF_LAUNCH_CHECK("conv3d_c8_cout1_kernel");
     return CMFB200_OK;
 }
