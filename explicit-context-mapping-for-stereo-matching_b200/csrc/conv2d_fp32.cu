@@ -180,42 +180,42 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 // r + {0,1,2,3}*DIL, so per input channel a thread issues 8 vector loads of input + 18 broadcast loads of weights
 // for 576 FMAs (1:22 instead of 1:12) -- these layers carry 80 % of the feature extractor's MACs.
 // ------------------------------------------------------------------------------------------------
-template <int DIL, int COUT_TILE>
+template <int DIL, int COUT_TILE, int TW>
 struct Conv2dR2Cfg {
     static constexpr int CPT = 8;
     static constexpr int NCG = COUT_TILE / CPT;
     static constexpr int NQ = kConvThreads / NCG;
-    static constexpr int TROWS = NQ / (kTW / kVPT);  // thread rows
+    static constexpr int TROWS = NQ / (TW / kVPT);  // thread rows
     static constexpr int TH = 2 * TROWS;             // output rows per CTA
     static constexpr int PH = TH + 2 * DIL;
-    static constexpr int PW = kTW + 2 * DIL;
+    static constexpr int PW = TW + 2 * DIL;
     static constexpr int PWP = (PW + 3) & ~3;
     static constexpr int PATCH = PH * PWP;
     static constexpr int NI4 = (kVPT + 2 * DIL + 3) / 4;  // 2
     static constexpr int NSLOT = (PH * PW + kConvThreads - 1) / kConvThreads;
     static constexpr int WSL = 9 * COUT_TILE;
     static_assert(TROWS % DIL == 0, "row pairing needs TROWS to be a multiple of the dilation");
-    static_assert((kTW / kVPT - 1) * kVPT + NI4 * 4 <= PWP, "vector over-read leaves the patch row");
+    static_assert((TW / kVPT - 1) * kVPT + NI4 * 4 <= PWP, "vector over-read leaves the patch row");
 };
 
-template <int DIL, int COUT_TILE, int CC>
+template <int DIL, int COUT_TILE, int CC, int TW>
 __global__ void __launch_bounds__(kConvThreads, 2)
     conv2d_r2_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
                      double* __restrict__ gn_sums, int Cin, int Cout, int H, int W, int tiles_w) {
-    using G = Conv2dR2Cfg<DIL, COUT_TILE>;
+    using G = Conv2dR2Cfg<DIL, COUT_TILE, TW>;
     constexpr int CPT = G::CPT;
     constexpr int STAGE = CC * (G::PATCH + G::WSL);
     extern __shared__ __align__(16) float smem[];
 
     const int tile_x = blockIdx.x % tiles_w, tile_y = blockIdx.x / tiles_w;
-    const int w0 = tile_x * kTW, h0 = tile_y * G::TH;
+    const int w0 = tile_x * TW, h0 = tile_y * G::TH;
     const int cb = blockIdx.y * COUT_TILE;
     const int b = blockIdx.z;
     const int tid = threadIdx.x;
     const int cg = tid / G::NQ;
     const int q = tid % G::NQ;
-    const int qx = q % (kTW / kVPT);
-    const int tr = q / (kTW / kVPT);
+    const int qx = q % (TW / kVPT);
+    const int tr = q / (TW / kVPT);
     const int r0 = (tr / DIL) * 2 * DIL + (tr % DIL);  // first output row of this thread (tile-relative); second = r0+DIL
 
     int goff[G::NSLOT], soff[G::NSLOT];
@@ -345,20 +345,30 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     if (gn_sums != nullptr) gn_epilogue<COUT_TILE, CPT>(s, ss, cg, smem, gn_sums, b, Cout, cb);
 }
 
-template <int DIL, int COUT_TILE, int CC>
-static int launch_conv2d_r2(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int Cout, int H, int W,
+template <int DIL, int COUT_TILE, int CC, int TW>
+static int launch_conv2d_r2_tw(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int Cout, int H, int W,
                             cudaStream_t st) {
-    using G = Conv2dR2Cfg<DIL, COUT_TILE>;
+    using G = Conv2dR2Cfg<DIL, COUT_TILE, TW>;
     constexpr size_t smem = 2 * (size_t)CC * (G::PATCH + G::WSL) * sizeof(float);
     static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
-    const int tiles_w = (int)cdiv(W, kTW), tiles_h = (int)cdiv(H, G::TH);
-    auto kern = conv2d_r2_kernel<DIL, COUT_TILE, CC>;
+    const int tiles_w = (int)cdiv(W, TW), tiles_h = (int)cdiv(H, G::TH);
+    auto kern = conv2d_r2_kernel<DIL, COUT_TILE, CC, TW>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(Cout / COUT_TILE), (unsigned)B);
     CMF_REQUIRE(grid.z <= 65535, "conv2d: batch too large");
     kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, Cout, H, W, tiles_w);
     CMF_LAUNCH_CHECK("conv2d_r2_kernel");
     return CMFB200_OK;
+}
+
+template <int DIL, int COUT_TILE, int CC>
+static int launch_conv2d_r2(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int Cout, int H, int W,
+                            cudaStream_t st) {
+    // tile width 32 or 16: whichever wastes fewer lanes on the ragged edges (w = 240 = 15 x 16 = 7.5 x 32)
+    const long long c32 = cdiv(W, 32) * 32 * cdiv(H, Conv2dR2Cfg<DIL, COUT_TILE, 32>::TH) * Conv2dR2Cfg<DIL, COUT_TILE, 32>::TH;
+    const long long c16 = cdiv(W, 16) * 16 * cdiv(H, Conv2dR2Cfg<DIL, COUT_TILE, 16>::TH) * Conv2dR2Cfg<DIL, COUT_TILE, 16>::TH;
+    if (c16 < c32) return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 16>(x, wp, y, gn, B, Cin, Cout, H, W, st);
+    return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 32>(x, wp, y, gn, B, Cin, Cout, H, W, st);
 }
 
 // weight packing: [Cout][Cin][KS*KS] -> [Cin][KS*KS][Cout]

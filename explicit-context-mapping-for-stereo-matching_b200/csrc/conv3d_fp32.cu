@@ -20,12 +20,12 @@ namespace cmfb200 {
 // ------------------------------------------------------------------------------------------------
 // forward convolution, stride S in {1,2}
 // ------------------------------------------------------------------------------------------------
-template <int COUT, int CPT, int S, int CC>
+template <int COUT, int CPT, int S, int CC, int TW>
 __global__ void __launch_bounds__(kConvThreads, 2)
     conv3d_k3_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
                      double* __restrict__ gn_sums, int Cin, int D, int H, int W, int Do, int Ho, int Wo, int tiles_w) {
-    using T = ConvTile<COUT, CPT>;
-    constexpr int PD = (T::TD - 1) * S + 3, PH = (T::TH - 1) * S + 3, PW = (kTW - 1) * S + 3;
+    using T = ConvTile<COUT, CPT, TW>;
+    constexpr int PD = (T::TD - 1) * S + 3, PH = (T::TH - 1) * S + 3, PW = (TW - 1) * S + 3;
     constexpr int PWP = (PW + 3) & ~3;
     constexpr int PATCH = PD * PH * PWP;  // floats per input channel
     constexpr int WSL = 27 * COUT;        // weight floats per input channel
@@ -33,19 +33,19 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     constexpr int NI4 = (NI + 3) / 4;
     constexpr int NSLOT = (PD * PH * PW + kConvThreads - 1) / kConvThreads;
     constexpr int STAGE = CC * (PATCH + WSL);  // floats per pipeline stage
-    static_assert((kTW / kVPT - 1) * kVPT * S + NI4 * 4 <= PWP, "vector over-read leaves the patch row");
+    static_assert((TW / kVPT - 1) * kVPT * S + NI4 * 4 <= PWP, "vector over-read leaves the patch row");
     static_assert((CC * WSL) % 4 == 0 && (CC * PATCH) % 4 == 0, "stage slices must stay 16-byte aligned");
 
     extern __shared__ __align__(16) float smem[];  // 2 stages of [CC][PD][PH][PWP] + [CC][27][COUT]
 
     const int tile_x = blockIdx.x % tiles_w, tile_y = blockIdx.x / tiles_w;
-    const int w0 = tile_x * kTW, h0 = tile_y * T::TH, d0 = blockIdx.y * T::TD;
+    const int w0 = tile_x * TW, h0 = tile_y * T::TH, d0 = blockIdx.y * T::TD;
     const int b = blockIdx.z;
     const int tid = threadIdx.x;
     const int cg = tid / T::NQ;
     const int q = tid % T::NQ;
-    const int qx = q % (kTW / kVPT);
-    const int row = q / (kTW / kVPT);
+    const int qx = q % (TW / kVPT);
+    const int row = q / (TW / kVPT);
     const int th = row % T::TH, td = row / T::TH;
 
     float acc[CPT][kVPT];
@@ -377,23 +377,34 @@ __global__ void pack_conv3d_weight_kernel(const float* __restrict__ w, float* __
     }
 }
 
-template <int COUT, int CPT, int S, int CC>
+template <int COUT, int CPT, int S, int CC, int TW>
 static int launch_conv(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
                        cudaStream_t st) {
-    using T = ConvTile<COUT, CPT>;
-    constexpr int PD = (T::TD - 1) * S + 3, PH = (T::TH - 1) * S + 3, PW = (kTW - 1) * S + 3;
+    using T = ConvTile<COUT, CPT, TW>;
+    constexpr int PD = (T::TD - 1) * S + 3, PH = (T::TH - 1) * S + 3, PW = (TW - 1) * S + 3;
     constexpr int PWP = (PW + 3) & ~3;
     constexpr size_t smem = 2 * (size_t)CC * (PD * PH * PWP + 27 * COUT) * sizeof(float);
     static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
     const int Do = (D - 1) / S + 1, Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
-    const int tiles_w = (int)cdiv(Wo, kTW), tiles_h = (int)cdiv(Ho, T::TH);
-    auto kern = conv3d_k3_kernel<COUT, CPT, S, CC>;
+    const int tiles_w = (int)cdiv(Wo, TW), tiles_h = (int)cdiv(Ho, T::TH);
+    auto kern = conv3d_k3_kernel<COUT, CPT, S, CC, TW>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)cdiv(Do, T::TD), (unsigned)B);
     CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d: grid too large");
     kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, D, H, W, Do, Ho, Wo, tiles_w);
     CMF_LAUNCH_CHECK("conv3d_k3_kernel");
     return CMFB200_OK;
+}
+
+// picks the tile width (32 or 16 voxels) that wastes fewer lanes on the ragged right / bottom edge
+template <int COUT, int CPT, int S, int CC>
+static int launch_conv_best(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
+                            cudaStream_t st) {
+    const long long Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+    const long long c32 = cdiv(Wo, 32) * 32 * cdiv(Ho, ConvTile<COUT, CPT, 32>::TH) * ConvTile<COUT, CPT, 32>::TH;
+    const long long c16 = cdiv(Wo, 16) * 16 * cdiv(Ho, ConvTile<COUT, CPT, 16>::TH) * ConvTile<COUT, CPT, 16>::TH;
+    if (c16 < c32) return launch_conv<COUT, CPT, S, CC, 16>(x, wp, y, gn, B, Cin, D, H, W, st);
+    return launch_conv<COUT, CPT, S, CC, 32>(x, wp, y, gn, B, Cin, D, H, W, st);
 }
 
 template <int COUT, int CPT, int CC>
@@ -434,11 +445,11 @@ extern "C" int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, floa
     CMF_REQUIRE(Cin % 8 == 0, "conv3d_k3_fwd: Cin=%d must be a multiple of 8", Cin);
     CMF_REQUIRE(stride == 1 || stride == 2, "conv3d_k3_fwd: stride=%d not in {1,2}", stride);
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cout == 32 && stride == 1) return launch_conv<32, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 64 && stride == 1) return launch_conv<64, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 2>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 64 && stride == 2) return launch_conv<64, 8, 2, 2>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 1 && stride == 1) return launch_conv<1, 1, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 32 && stride == 1) return launch_conv_best<32, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 64 && stride == 1) return launch_conv_best<64, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 64 && stride == 2) return launch_conv<64, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 1 && stride == 1) return launch_conv_best<1, 1, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
     CMF_REQUIRE(false, "conv3d_k3_fwd: unsupported (Cout=%d, stride=%d); Cout in {1,32,64}", Cout, stride);
 }
 

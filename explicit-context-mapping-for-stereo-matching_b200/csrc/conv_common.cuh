@@ -8,14 +8,15 @@ constexpr int kConvThreads = 256;
 constexpr int kTW = 32;  // output voxels along w per CTA
 constexpr int kVPT = 4;  // consecutive-w output voxels per thread
 
-template <int COUT, int CPT>
+// TW = output voxels along w per CTA: 32, or 16 when that wastes fewer lanes (e.g. w = 240 = 15 x 16 = 7.5 x 32)
+template <int COUT, int CPT, int TW = kTW>
 struct ConvTile {
     static constexpr int NCG = COUT / CPT;               // channel groups
     static constexpr int NQ = kConvThreads / NCG;        // voxel quads per CTA
-    static constexpr int ROWS = NQ / (kTW / kVPT);       // (d,h) rows of 32 voxels
+    static constexpr int ROWS = NQ / (TW / kVPT);        // (d,h) rows of TW voxels
     static constexpr int TD = (COUT == 1) ? 4 : 1;
     static constexpr int TH = ROWS / TD;
-    static_assert(NCG * NQ == kConvThreads && TD * TH * (kTW / kVPT) == NQ, "bad tile");
+    static_assert(NCG * NQ == kConvThreads && TD * TH * (TW / kVPT) == NQ, "bad tile");
 };
 
 // epilogue helper: block-level reduction of per-thread channel sums into gn_sums[b][co][2] (double atomics).
