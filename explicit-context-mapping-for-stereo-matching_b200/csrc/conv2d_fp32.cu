@@ -367,7 +367,9 @@ static int launch_conv2d_r2(const float* x, const float* wp, float* y, double* g
     // tile width 32 or 16: whichever wastes fewer lanes on the ragged edges (w = 240 = 15 x 16 = 7.5 x 32)
     const long long c32 = cdiv(W, 32) * 32 * cdiv(H, Conv2dR2Cfg<DIL, COUT_TILE, 32>::TH) * Conv2dR2Cfg<DIL, COUT_TILE, 32>::TH;
     const long long c16 = cdiv(W, 16) * 16 * cdiv(H, Conv2dR2Cfg<DIL, COUT_TILE, 16>::TH) * Conv2dR2Cfg<DIL, COUT_TILE, 16>::TH;
-    if (c16 < c32) return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 16>(x, wp, y, gn, B, Cin, Cout, H, W, st);
+    // measured at w=240 (6.7 % fewer lanes): 16-wide tiles are 1.4 % SLOWER here (smaller halo reuse, 2-way bank
+    // conflicts on the 80-byte row pitch), so they are only used when they save more than 10 %
+    if (c16 * 10 < c32 * 9) return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 16>(x, wp, y, gn, B, Cin, Cout, H, W, st);
     return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 32>(x, wp, y, gn, B, Cin, Cout, H, W, st);
 }
 
