@@ -1,0 +1,95 @@
+"""GPU: size-independent properties at BASELINE config 2's FULL sizes (576x960 -> 144x240 at 1/4 resolution, D'=48),
+where the CPU oracle would take minutes: exact linearity under power-of-two scaling, statistics identities,
+normalisation invariants, convexity bounds, agreement of the tcgen05 path with the fp32 path."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+D, H, W = 48, 144, 240
+
+
+def _randn(*shape, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return torch.randn(*shape, generator=g, device=DEV)
+
+
+def test_conv3d_fp32_linearity_and_fused_statistics():
+    from cmf_b200 import ops
+
+    x = _randn(1, 32, D, H, W, seed=1)
+    w = ops.pack_conv3d_weight(_randn(32, 32, 3, 3, 3, seed=2) * 0.05)
+    y, sums = ops.conv3d_k3(x, w, 1, want_stats=True)
+    y2, _ = ops.conv3d_k3(x * 2.0, w, 1)
+    assert torch.equal(y2, y * 2.0)  # scaling by a power of two commutes exactly with fp32 FMA chains
+    torch.testing.assert_close(sums[..., 0], y.double().sum((2, 3, 4)), rtol=1e-9, atol=1e-6)
+    torch.testing.assert_close(sums[..., 1], (y.double() ** 2).sum((2, 3, 4)), rtol=1e-9, atol=1e-6)
+    # shift equivariance along depth away from the borders
+    xs = torch.roll(x, 1, dims=2)
+    ys, _ = ops.conv3d_k3(xs, w, 1)
+    assert torch.equal(ys[:, :, 3:-3], torch.roll(y, 1, dims=2)[:, :, 3:-3])
+
+
+def test_groupnorm_apply_normalises_full_volume():
+    from cmf_b200 import ops
+
+    x = _randn(1, 64, D // 2, H // 2, W // 2, seed=3) * 3.0 + 1.5
+    ones, zeros = torch.ones(64, device=DEV), torch.zeros(64, device=DEV)
+    y = ops.gn_apply(x, ops.gn_stats(x), ones, zeros)
+    g = y.double().view(1, 32, -1)
+    assert float(g.mean(2).abs().max()) < 1e-5
+    assert float((g.var(2, unbiased=False) - 1).abs().max()) < 1e-4
+    r = _randn(1, 64, D // 2, H // 2, W // 2, seed=4)
+    yr = ops.gn_apply(x, ops.gn_stats(x), ones, zeros, r, True)
+    torch.testing.assert_close(yr, torch.relu(y + r), rtol=0, atol=1e-6)
+
+
+def test_tcgen05_igemm_agrees_with_fp32_path_full_size():
+    from cmf_b200 import ops
+
+    x = _randn(1, 32, D, H, W, seed=5).to(torch.bfloat16).float()  # both paths see identical (bf16-exact) operands
+    wgt = (_randn(32, 32, 3, 3, 3, seed=6) * 0.05).to(torch.bfloat16).float()
+    y32, s32 = ops.conv3d_k3(x, ops.pack_conv3d_weight(wgt), 1, want_stats=True)
+    y16, s16 = ops.conv3d_igemm(ops.f32_to_c8(x), ops.pack_igemm_weight(wgt))
+    got = ops.c8_to_f32(y16)
+    rel = float((got.double() - y32.double()).norm() / y32.double().norm())
+    assert rel < 2.5e-3, rel  # only the final bf16 rounding of the output (2^-9/sqrt(3) = 1.1e-3 expected)
+    torch.testing.assert_close(s16[..., 0], s32[..., 0], rtol=0, atol=2e-3 * float(y32.abs().sum()) / 32)
+
+
+def test_k5_k4_invariants_full_size():
+    from cmf_b200 import ops
+
+    lr, hr = _randn(1, 32, H, W, seed=7), _randn(1, 32, 4 * H, 4 * W, seed=8)
+    ws = [_randn(32, 66, 1, 1, seed=9) * 0.2, _randn(16, 32, 1, 1, seed=10) * 0.3, _randn(8, 16, 1, 1, seed=11) * 0.4,
+          _randn(1, 8, 1, 1, seed=12)]
+    w9 = ops.ctxmap_weights(lr, hr, *ws)
+    torch.testing.assert_close(w9.sum(1), torch.ones_like(w9[:, 0]), rtol=0, atol=1e-5)
+    assert float(w9[:, 1, :, :4].max()) < 1e-30 and float(w9[:, 4, -4:].max()) < 1e-30  # out-of-image neighbours
+    c = [_randn(1, D, H, W, seed=13 + i) * 3 for i in range(3)]
+    outs, low = ops.softargmin_ctxmap(*c, w9, 4, want_lowres=True)
+    for o in outs:
+        assert float(o.min()) >= 0.0 and float(o.max()) <= 4.0 * (D - 1) + 1e-3  # convex combination of 4*p
+    # with a one-hot centre weight the output is exactly 4 x nearest-upsampled soft-argmin
+    onehot = torch.zeros_like(w9)
+    onehot[:, 0] = 1.0
+    o1 = ops.softargmin_ctxmap(*c, onehot, 4)[0]
+    assert torch.equal(o1[0, 0], (4.0 * low[0, 0]).repeat_interleave(4, 0).repeat_interleave(4, 1))
+    p_ref = (torch.softmax(c[0], 1) * torch.arange(D, device=DEV, dtype=torch.float32).view(1, D, 1, 1)).sum(1)
+    torch.testing.assert_close(low[0], p_ref, rtol=1e-5, atol=1e-4)
+
+
+def test_full_network_config2_is_finite_and_reproducible():
+    import golden_common as gc
+    from cmf.models import get_model
+
+    torch.manual_seed(gc.WEIGHT_SEED)
+    model = get_model("cmfsm").to(DEV).eval()
+    left, right = gc.seeded_pair(1, 576, 960)
+    with torch.no_grad():
+        a = model(left.to(DEV), right.to(DEV))
+        b = model(left.to(DEV), right.to(DEV))
+    for x, y in zip(a, b):
+        assert x.shape == (1, 1, 576, 960) and bool(torch.isfinite(x).all())
+        assert float(x.min()) >= -1e-3 and float(x.max()) <= 188.0 + 1e-3  # max representable disparity 4*(48-1)
+        assert float((x - y).abs().max()) < 5e-3  # double atomics in the GroupNorm sums are order-dependent
