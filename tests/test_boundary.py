@@ -43,8 +43,8 @@ def test_checkpoint_round_trip_with_module_prefix(tmp_path):
     """train.py:228-234 saves {'epoch','model_state','optimizer_state'} from a DataParallel wrapper."""
     from cmf.models import get_model
 
-    model = torch.nn.DataParallel(get_model("cmfsm"), device_ids=None) if False else get_model("cmfsm")
-    state = {"module." + k: v for k, v in model.state_dict().items()}
+    model = get_model("cmfsm")
+    state = {"module." + k: v for k, v in model.state_dict().items()}  # what a DataParallel wrapper would save
     path = tmp_path / "ckpt.pkl"
     torch.save({"epoch": 3, "model_state": state, "optimizer_state": {}}, path)
     ckpt = torch.load(path)
