@@ -252,13 +252,14 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         cp_async_commit();
     };
 
-    float acc[2][CPT][kVPT];
+    // channel-pair accumulators updated with FFMA2 (packed fp32x2 FMA, bit-identical to two FFMAs)
+    float2 acc2[2][CPT / 2][kVPT];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int c = 0; c < CPT; ++c)
+        for (int c = 0; c < CPT / 2; ++c)
 #pragma unroll
-            for (int v = 0; v < kVPT; ++v) acc[r][c][v] = 0.f;
+            for (int v = 0; v < kVPT; ++v) acc2[r][c][v] = make_float2(0.f, 0.f);
 
     if constexpr (G::PWP > G::PW) {
         for (int i = tid; i < 2 * CC * G::PH * (G::PWP - G::PW); i += kConvThreads) {
@@ -301,19 +302,30 @@ __global__ void __launch_bounds__(kConvThreads, 2)
                     const float* wt = pwt + (kh * 3 + kw) * COUT_TILE;
                     const float4 w0v = *reinterpret_cast<const float4*>(wt);
                     const float4 w1v = *reinterpret_cast<const float4*>(wt + 4);
-                    const float wv[CPT] = {w0v.x, w0v.y, w0v.z, w0v.w, w1v.x, w1v.y, w1v.z, w1v.w};
+                    const float2 w2[CPT / 2] = {make_float2(w0v.x, w0v.y), make_float2(w0v.z, w0v.w),
+                                                make_float2(w1v.x, w1v.y), make_float2(w1v.z, w1v.w)};
 #pragma unroll
-                    for (int c = 0; c < CPT; ++c)
+                    for (int v = 0; v < kVPT; ++v) {
+                        const float2 i0 = make_float2(in[kh][v + kw * DIL], in[kh][v + kw * DIL]);
+                        const float2 i1 = make_float2(in[kh + 1][v + kw * DIL], in[kh + 1][v + kw * DIL]);
 #pragma unroll
-                        for (int v = 0; v < kVPT; ++v) {
-                            acc[0][c][v] = fmaf(wv[c], in[kh][v + kw * DIL], acc[0][c][v]);
-                            acc[1][c][v] = fmaf(wv[c], in[kh + 1][v + kw * DIL], acc[1][c][v]);
+                        for (int c = 0; c < CPT / 2; ++c) {
+                            acc2[0][c][v] = __ffma2_rn(w2[c], i0, acc2[0][c][v]);
+                            acc2[1][c][v] = __ffma2_rn(w2[c], i1, acc2[1][c][v]);
                         }
+                    }
                 }
         }
         __syncthreads();
     }
 
+    float acc[2][CPT][kVPT];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+#pragma unroll
+            for (int v = 0; v < kVPT; ++v) acc[r][c][v] = (c & 1) ? acc2[r][c >> 1][v].y : acc2[r][c >> 1][v].x;
     const int ow = w0 + qx * kVPT;
     const size_t out_plane = in_plane;  // stride 1, "same" padding
     double s[CPT], ss[CPT];

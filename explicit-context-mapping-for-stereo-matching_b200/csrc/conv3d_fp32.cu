@@ -48,11 +48,14 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     const int row = q / (TW / kVPT);
     const int th = row % T::TH, td = row / T::TH;
 
-    float acc[CPT][kVPT];
+    // accumulators as channel pairs: one FFMA2 (sm_100 packed fp32x2 FMA, two IEEE round-to-nearest FMAs) updates
+    // channels (2j, 2j+1) of one voxel -- half the issue slots of scalar FFMA, bit-identical results
+    constexpr int CP2 = (CPT + 1) / 2;
+    float2 acc2[CP2][kVPT];
 #pragma unroll
-    for (int c = 0; c < CPT; ++c)
+    for (int c = 0; c < CP2; ++c)
 #pragma unroll
-        for (int v = 0; v < kVPT; ++v) acc[c][v] = 0.f;
+        for (int v = 0; v < kVPT; ++v) acc2[c][v] = make_float2(0.f, 0.f);
 
     const size_t in_plane = (size_t)H * W;
     const size_t in_vol = (size_t)D * in_plane;
@@ -131,26 +134,33 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
                         const float* wt = pw_ + ((kd * 3 + kh) * 3 + kw) * COUT;
-                        float wv[CPT];
+                        float2 w2[CP2];
                         if constexpr (CPT == 8) {
                             const float4 w0v = *reinterpret_cast<const float4*>(wt);
                             const float4 w1v = *reinterpret_cast<const float4*>(wt + 4);
-                            wv[0] = w0v.x; wv[1] = w0v.y; wv[2] = w0v.z; wv[3] = w0v.w;
-                            wv[4] = w1v.x; wv[5] = w1v.y; wv[6] = w1v.z; wv[7] = w1v.w;
+                            w2[0] = make_float2(w0v.x, w0v.y); w2[1] = make_float2(w0v.z, w0v.w);
+                            w2[2] = make_float2(w1v.x, w1v.y); w2[3] = make_float2(w1v.z, w1v.w);
                         } else {
-#pragma unroll
-                            for (int c = 0; c < CPT; ++c) wv[c] = wt[c];
+                            w2[0] = make_float2(wt[0], 0.f);
                         }
 #pragma unroll
-                        for (int c = 0; c < CPT; ++c)
+                        for (int v = 0; v < kVPT; ++v) {
+                            const float2 i2 = make_float2(in[v * S + kw], in[v * S + kw]);
 #pragma unroll
-                            for (int v = 0; v < kVPT; ++v) acc[c][v] = fmaf(wv[c], in[v * S + kw], acc[c][v]);
+                            for (int c = 0; c < CP2; ++c) acc2[c][v] = __ffma2_rn(w2[c], i2, acc2[c][v]);
+                        }
                     }
                 }
             }
         }
         __syncthreads();  // everyone done with `buf` before the next prefetch overwrites it
     }
+
+    float acc[CPT][kVPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+#pragma unroll
+        for (int v = 0; v < kVPT; ++v) acc[c][v] = (c & 1) ? acc2[c >> 1][v].y : acc2[c >> 1][v].x;
 
     // ---- epilogue: store + GroupNorm partial sums
     const int od = d0 + td, oh = h0 + th, ow = w0 + qx * kVPT;
