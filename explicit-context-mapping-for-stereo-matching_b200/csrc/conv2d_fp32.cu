@@ -89,11 +89,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         cp_async_commit();
     };
 
-    float acc[CPT][kVPT];
+    float2 acc2[CPT / 2][kVPT];  // channel pairs, updated with FFMA2 (packed fp32x2 FMA)
 #pragma unroll
-    for (int c = 0; c < CPT; ++c)
+    for (int c = 0; c < CPT / 2; ++c)
 #pragma unroll
-        for (int v = 0; v < kVPT; ++v) acc[c][v] = 0.f;
+        for (int v = 0; v < kVPT; ++v) acc2[c][v] = make_float2(0.f, 0.f);
 
     // zero the alignment tail of every patch row once (never written by cp.async, read by vector loads)
     if constexpr (G::PWP > G::PW) {
@@ -136,11 +136,14 @@ __global__ void __launch_bounds__(kConvThreads, 2)
                     const float* wt = pwt + (kh * KS + kw) * COUT_TILE;
                     const float4 w0v = *reinterpret_cast<const float4*>(wt);
                     const float4 w1v = *reinterpret_cast<const float4*>(wt + 4);
-                    const float wv[CPT] = {w0v.x, w0v.y, w0v.z, w0v.w, w1v.x, w1v.y, w1v.z, w1v.w};
+                    const float2 w2[CPT / 2] = {make_float2(w0v.x, w0v.y), make_float2(w0v.z, w0v.w),
+                                                make_float2(w1v.x, w1v.y), make_float2(w1v.z, w1v.w)};
 #pragma unroll
-                    for (int c = 0; c < CPT; ++c)
+                    for (int v = 0; v < kVPT; ++v) {
+                        const float2 i2 = make_float2(in[v * S + kw * DIL], in[v * S + kw * DIL]);
 #pragma unroll
-                        for (int v = 0; v < kVPT; ++v) acc[c][v] = fmaf(wv[c], in[v * S + kw * DIL], acc[c][v]);
+                        for (int c = 0; c < CPT / 2; ++c) acc2[c][v] = __ffma2_rn(w2[c], i2, acc2[c][v]);
+                    }
                 }
             }
         }
@@ -148,6 +151,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     }
 
     // ---- epilogue
+    float acc[CPT][kVPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+#pragma unroll
+        for (int v = 0; v < kVPT; ++v) acc[c][v] = (c & 1) ? acc2[c >> 1][v].y : acc2[c >> 1][v].x;
     const int oh = h0 + th, ow = w0 + qx * kVPT;
     const size_t out_plane = (size_t)Ho * Wo;
     double s[CPT], ss[CPT];

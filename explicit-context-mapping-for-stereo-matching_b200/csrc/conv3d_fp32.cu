@@ -233,11 +233,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     const int qx = q % (kTW / kVPT);
     const int th = q / (kTW / kVPT);
 
-    float acc[CPT][NO];
+    float2 acc2[CPT / 2][NO];  // channel pairs, updated with FFMA2 (packed fp32x2 FMA)
 #pragma unroll
-    for (int c = 0; c < CPT; ++c)
+    for (int c = 0; c < CPT / 2; ++c)
 #pragma unroll
-        for (int v = 0; v < NO; ++v) acc[c][v] = 0.f;
+        for (int v = 0; v < NO; ++v) acc2[c][v] = make_float2(0.f, 0.f);
 
     const size_t in_plane = (size_t)H * W;
     const size_t in_vol = (size_t)D * in_plane;
@@ -320,29 +320,36 @@ __global__ void __launch_bounds__(kConvThreads, 2)
                     const float4 a = *reinterpret_cast<const float4*>(prow);
                     const float in[5] = {a.x, a.y, a.z, a.w, prow[4]};
                     const float* wt = pw_ + (jd * nh + jh) * 3 * COUT;
-                    float wk[3][CPT];
+                    float2 wk[3][CPT / 2];
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
                         const float4 w0v = *reinterpret_cast<const float4*>(wt + kw * COUT);
                         const float4 w1v = *reinterpret_cast<const float4*>(wt + kw * COUT + 4);
-                        wk[kw][0] = w0v.x; wk[kw][1] = w0v.y; wk[kw][2] = w0v.z; wk[kw][3] = w0v.w;
-                        wk[kw][4] = w1v.x; wk[kw][5] = w1v.y; wk[kw][6] = w1v.z; wk[kw][7] = w1v.w;
+                        wk[kw][0] = make_float2(w0v.x, w0v.y); wk[kw][1] = make_float2(w0v.z, w0v.w);
+                        wk[kw][2] = make_float2(w1v.x, w1v.y); wk[kw][3] = make_float2(w1v.z, w1v.w);
                     }
 #pragma unroll
-                    for (int c = 0; c < CPT; ++c)
+                    for (int v = 0; v < kVPT; ++v) {
+                        // even column 2*(i+v): tap kw=1 of input v ; odd column: kw=2 of v, kw=0 of v+1
+                        const float2 a = make_float2(in[v], in[v]), bnext = make_float2(in[v + 1], in[v + 1]);
 #pragma unroll
-                        for (int v = 0; v < kVPT; ++v) {
-                            // even column 2*(i+v): tap kw=1 of input v ; odd column: kw=2 of v, kw=0 of v+1
-                            acc[c][2 * v] = fmaf(wk[1][c], in[v], acc[c][2 * v]);
-                            acc[c][2 * v + 1] = fmaf(wk[2][c], in[v], acc[c][2 * v + 1]);
-                            acc[c][2 * v + 1] = fmaf(wk[0][c], in[v + 1], acc[c][2 * v + 1]);
+                        for (int c = 0; c < CPT / 2; ++c) {
+                            acc2[c][2 * v] = __ffma2_rn(wk[1][c], a, acc2[c][2 * v]);
+                            acc2[c][2 * v + 1] = __ffma2_rn(wk[2][c], a, acc2[c][2 * v + 1]);
+                            acc2[c][2 * v + 1] = __ffma2_rn(wk[0][c], bnext, acc2[c][2 * v + 1]);
                         }
+                    }
                 }
             }
         }
         __syncthreads();
     }
 
+    float acc[CPT][NO];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+#pragma unroll
+        for (int v = 0; v < NO; ++v) acc[c][v] = (c & 1) ? acc2[c >> 1][v].y : acc2[c >> 1][v].x;
     const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
     const int od = 2 * id + pd, oh = 2 * (ih0 + th) + ph, ow = 2 * (iw0 + qx * kVPT);
     const size_t out_plane = (size_t)Ho * Wo;
