@@ -12,6 +12,8 @@
 // accumulators for CPT=8).  Per (ci,kd,kh) it issues 2 vector loads of input + 6 broadcast loads of weights
 // for 96 FMAs, i.e. the inner loop is FMA-issue bound, not shared-memory bound.
 // GroupNorm statistics (sum, sum of squares per (b,channel)) are reduced in the epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "conv_common.cuh"
 
@@ -197,6 +199,213 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         }
     }
     if (gn_sums != nullptr) gn_epilogue<COUT, CPT>(s, ss, cg, smem, gn_sums, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stride-1 convolution, TWO output rows per thread (the layers that carry 90 % of the 3-D MACs).
+// With FFMA2 the scalar kernel above became shared-memory bound (ncu: 86 % of the LSU wavefront peak vs 74 % FMA
+// pipe): rows r and r+1 share the four input rows r..r+3, so per (ci,kd) a thread issues 8 vector loads of input +
+// 18 broadcast loads of weights for 576 FMAs (26 loads) instead of 3 x (2+6) = 24 loads for 288 FMAs.
+// Tile: 2 depth slices x TH rows x TW columns, TW in {32, 16}.
+// ------------------------------------------------------------------------------------------------
+template <int COUT, int TW>
+struct Conv3dR2Cfg {
+    static constexpr int CPT = 8;
+    static constexpr int NCG = COUT / CPT;
+    static constexpr int NQ = kConvThreads / NCG;
+    static constexpr int NTR = NQ / (TW / kVPT);  // thread rows (each = one row pair)
+    static constexpr int TD = 2;
+    static constexpr int TH = NTR;                // NTR/2 pairs per depth slice x 2 rows
+    static constexpr int PD = TD + 2, PH = TH + 2, PW = TW + 2;
+    static constexpr int PWP = (TW == 16) ? 24 : 36;  // 24: rows 2 apart land 16 banks apart (conflict-free LDS.128)
+    static constexpr int PATCH = PD * PH * PWP;
+    static constexpr int WSL = 27 * COUT;
+    static constexpr int NSLOT = (PD * PH * PW + kConvThreads - 1) / kConvThreads;
+    static_assert(NTR % 2 == 0 && (TW / kVPT - 1) * kVPT + 8 <= PWP, "bad R2 tile");
+};
+
+template <int COUT, int CC, int TW>
+__global__ void __launch_bounds__(kConvThreads, 2)
+    conv3d_k3_r2_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
+                        double* __restrict__ gn_sums, int Cin, int D, int H, int W, int tiles_w) {
+    using G = Conv3dR2Cfg<COUT, TW>;
+    constexpr int CPT = G::CPT;
+    constexpr int STAGE = CC * (G::PATCH + G::WSL);
+    extern __shared__ __align__(16) float smem[];
+
+    const int tile_x = blockIdx.x % tiles_w, tile_y = blockIdx.x / tiles_w;
+    const int w0 = tile_x * TW, h0 = tile_y * G::TH, d0 = blockIdx.y * G::TD;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int cg = tid / G::NQ;
+    const int q = tid % G::NQ;
+    const int qx = q % (TW / kVPT);
+    const int tr = q / (TW / kVPT);
+    const int td = tr / (G::NTR / 2);
+    const int r0 = 2 * (tr % (G::NTR / 2));  // first output row of this thread inside the tile; second = r0 + 1
+
+    const size_t in_plane = (size_t)H * W;
+    const size_t in_vol = (size_t)D * in_plane;
+    const float* xb = x + (size_t)b * Cin * in_vol;
+    const int di0 = d0 - 1, hi0 = h0 - 1, wi0 = w0 - 1;
+
+    int goff[G::NSLOT], soff[G::NSLOT];
+    bool ok[G::NSLOT];
+#pragma unroll
+    for (int j = 0; j < G::NSLOT; ++j) {
+        const int e = tid + j * kConvThreads;
+        const int pw = e % G::PW;
+        const int r = e / G::PW;
+        const int ph = r % G::PH, pd = r / G::PH;
+        const int di = di0 + pd, hi = hi0 + ph, wi = wi0 + pw;
+        const bool in_patch = e < G::PD * G::PH * G::PW;
+        ok[j] = in_patch && (unsigned)di < (unsigned)D && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
+        goff[j] = ok[j] ? (di * H + hi) * W + wi : 0;
+        soff[j] = in_patch ? (pd * G::PH + ph) * G::PWP + pw : -1;
+    }
+    auto stage = [&](int c0, int buf) {
+        float* sIn = smem + buf * STAGE;
+        float* sW = sIn + CC * G::PATCH;
+#pragma unroll
+        for (int ci = 0; ci < CC; ++ci) {
+            const float* src = xb + (size_t)(c0 + ci) * in_vol;
+#pragma unroll
+            for (int j = 0; j < G::NSLOT; ++j)
+                if (soff[j] >= 0) cp_async_4_zfill(sIn + ci * G::PATCH + soff[j], src + goff[j], ok[j]);
+        }
+        const float* wsrc = wp + (size_t)c0 * G::WSL;
+        for (int i = tid * 4; i < CC * G::WSL; i += kConvThreads * 4) cp_async_16(sW + i, wsrc + i);
+        cp_async_commit();
+    };
+
+    float2 acc2[2][CPT / 2][kVPT];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < CPT / 2; ++c)
+#pragma unroll
+            for (int v = 0; v < kVPT; ++v) acc2[r][c][v] = make_float2(0.f, 0.f);
+
+    // zero the alignment tail of every patch row once (never written by cp.async, read by the vector loads)
+    for (int i = tid; i < 2 * CC * G::PD * G::PH * (G::PWP - G::PW); i += kConvThreads) {
+        const int t = i % (G::PWP - G::PW);
+        const int r = i / (G::PWP - G::PW);
+        const int prow = r % (G::PD * G::PH), ci = (r / (G::PD * G::PH)) % CC, buf = r / (G::PD * G::PH * CC);
+        smem[buf * STAGE + ci * G::PATCH + prow * G::PWP + G::PW + t] = 0.f;
+    }
+
+    const int nchunks = Cin / CC;
+    stage(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) {
+            stage((ch + 1) * CC, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float* sIn = smem + buf * STAGE;
+        const float* sW = sIn + CC * G::PATCH;
+#pragma unroll 1
+        for (int ci = 0; ci < CC; ++ci) {
+            const float* pin = sIn + ci * G::PATCH + (td * G::PH + r0) * G::PWP + qx * kVPT;
+            const float* pw_ = sW + ci * G::WSL + cg * CPT;
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+                float in[4][8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float* prow = pin + (kd * G::PH + j) * G::PWP;
+                    const float4 a = *reinterpret_cast<const float4*>(prow);
+                    const float4 c4 = *reinterpret_cast<const float4*>(prow + 4);
+                    in[j][0] = a.x; in[j][1] = a.y; in[j][2] = a.z; in[j][3] = a.w;
+                    in[j][4] = c4.x; in[j][5] = c4.y; in[j][6] = c4.z; in[j][7] = c4.w;
+                }
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float* wt = pw_ + ((kd * 3 + kh) * 3 + kw) * COUT;
+                        const float4 w0v = *reinterpret_cast<const float4*>(wt);
+                        const float4 w1v = *reinterpret_cast<const float4*>(wt + 4);
+                        const float2 w2[CPT / 2] = {make_float2(w0v.x, w0v.y), make_float2(w0v.z, w0v.w),
+                                                    make_float2(w1v.x, w1v.y), make_float2(w1v.z, w1v.w)};
+#pragma unroll
+                        for (int v = 0; v < kVPT; ++v) {
+                            const float2 i0 = make_float2(in[kh][v + kw], in[kh][v + kw]);
+                            const float2 i1 = make_float2(in[kh + 1][v + kw], in[kh + 1][v + kw]);
+#pragma unroll
+                            for (int c = 0; c < CPT / 2; ++c) {
+                                acc2[0][c][v] = __ffma2_rn(w2[c], i0, acc2[0][c][v]);
+                                acc2[1][c][v] = __ffma2_rn(w2[c], i1, acc2[1][c][v]);
+                            }
+                        }
+                    }
+            }
+        }
+        __syncthreads();
+    }
+
+    const int od = d0 + td, ow = w0 + qx * kVPT;
+    const size_t out_plane = in_plane;
+    double s[CPT], ss[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        s[c] = 0.0;
+        ss[c] = 0.0;
+    }
+    const bool vec = ((W & 3) == 0);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int oh = h0 + r0 + r;
+        if (od < D && oh < H && ow < W) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                float a[kVPT];
+#pragma unroll
+                for (int v = 0; v < kVPT; ++v) a[v] = (c & 1) ? acc2[r][c >> 1][v].y : acc2[r][c >> 1][v].x;
+                float* py = y + (((size_t)b * COUT + cg * CPT + c) * D + od) * out_plane + (size_t)oh * W + ow;
+                if (vec) *reinterpret_cast<float4*>(py) = make_float4(a[0], a[1], a[2], a[3]);
+#pragma unroll
+                for (int v = 0; v < kVPT; ++v)
+                    if (vec || ow + v < W) {
+                        if (!vec) py[v] = a[v];
+                        s[c] += (double)a[v];
+                        ss[c] = fma((double)a[v], (double)a[v], ss[c]);
+                    }
+            }
+        }
+    }
+    if (gn_sums != nullptr) gn_epilogue<COUT, CPT>(s, ss, cg, smem, gn_sums, b);
+}
+
+template <int COUT, int CC, int TW>
+static int launch_conv_r2(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
+                          cudaStream_t st) {
+    using G = Conv3dR2Cfg<COUT, TW>;
+    constexpr size_t smem = 2 * (size_t)CC * (G::PATCH + G::WSL) * sizeof(float);
+    static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
+    const int tiles_w = (int)cdiv(W, TW), tiles_h = (int)cdiv(H, G::TH);
+    auto kern = conv3d_k3_r2_kernel<COUT, CC, TW>;
+    CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)cdiv(D, G::TD), (unsigned)B);
+    CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d: grid too large");
+    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, D, H, W, tiles_w);
+    CMF_LAUNCH_CHECK("conv3d_k3_r2_kernel");
+    return CMFB200_OK;
+}
+
+// stride-1, Cout in {32,64}: two-rows-per-thread kernel with the tile width that wastes fewer lanes
+template <int COUT, int CC>
+static int launch_conv_r2_best(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
+                               cudaStream_t st) {
+    using G32 = Conv3dR2Cfg<COUT, 32>;
+    using G16 = Conv3dR2Cfg<COUT, 16>;
+    const long long c32 = cdiv(W, 32) * 32 * cdiv(H, G32::TH) * G32::TH;
+    const long long c16 = cdiv(W, 16) * 16 * cdiv(H, G16::TH) * G16::TH;
+    if (c16 < c32) return launch_conv_r2<COUT, CC, 16>(x, wp, y, gn, B, Cin, D, H, W, st);
+    return launch_conv_r2<COUT, CC, 32>(x, wp, y, gn, B, Cin, D, H, W, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -462,6 +671,9 @@ extern "C" int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, floa
     CMF_REQUIRE(Cin % 8 == 0, "conv3d_k3_fwd: Cin=%d must be a multiple of 8", Cin);
     CMF_REQUIRE(stride == 1 || stride == 2, "conv3d_k3_fwd: stride=%d not in {1,2}", stride);
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool one_row = getenv("CMFB200_CONV3D_ONE_ROW") != nullptr;  // A/B switch for profiling
+    if (Cout == 32 && stride == 1 && !one_row) return launch_conv_r2_best<32, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 64 && stride == 1 && !one_row) return launch_conv_r2_best<64, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
     if (Cout == 32 && stride == 1) return launch_conv_best<32, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
     if (Cout == 64 && stride == 1) return launch_conv_best<64, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
     if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
