@@ -197,7 +197,8 @@ struct Conv2dR2Cfg {
     static constexpr int TH = 2 * TROWS;             // output rows per CTA
     static constexpr int PH = TH + 2 * DIL;
     static constexpr int PW = TW + 2 * DIL;
-    static constexpr int PWP = (PW + 3) & ~3;
+    // TW=16, DIL=1: pitch 24 puts the two rows of a load phase (2 rows apart) 16 banks apart -> conflict-free LDS.128
+    static constexpr int PWP = (TW == 16 && DIL == 1) ? 24 : ((PW + 3) & ~3);
     static constexpr int PATCH = PH * PWP;
     static constexpr int NI4 = (kVPT + 2 * DIL + 3) / 4;  // 2
     static constexpr int NSLOT = (PH * PW + kConvThreads - 1) / kConvThreads;
@@ -389,7 +390,8 @@ static int launch_conv2d_r2(const float* x, const float* wp, float* y, double* g
     const long long c16 = cdiv(W, 16) * 16 * cdiv(H, Conv2dR2Cfg<DIL, COUT_TILE, 16>::TH) * Conv2dR2Cfg<DIL, COUT_TILE, 16>::TH;
     // measured at w=240 (6.7 % fewer lanes): 16-wide tiles are 1.4 % SLOWER here (smaller halo reuse, 2-way bank
     // conflicts on the 80-byte row pitch), so they are only used when they save more than 10 %
-    if (c16 * 10 < c32 * 9) return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 16>(x, wp, y, gn, B, Cin, Cout, H, W, st);
+    if ((DIL == 1 && c16 < c32) || c16 * 10 < c32 * 9)
+        return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 16>(x, wp, y, gn, B, Cin, Cout, H, W, st);
     return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 32>(x, wp, y, gn, B, Cin, Cout, H, W, st);
 }
 
