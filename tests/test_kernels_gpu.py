@@ -309,6 +309,8 @@ def test_k1_c8_bf16_matches_fp32_cost_volume():
 
 IGEMM_CASES = [  # B, Cin, Cout, D, H, W
     (1, 32, 32, 4, 16, 8), (1, 32, 32, 6, 20, 12), (2, 64, 32, 5, 16, 8), (1, 64, 64, 4, 18, 24), (1, 32, 32, 9, 37, 29),
+    # depth-walking schedule: single plane, two planes, several work units per CTA / depth segments, sample changes
+    (2, 32, 32, 1, 16, 8), (1, 32, 32, 2, 16, 16), (1, 64, 32, 12, 64, 80), (3, 32, 32, 16, 48, 200),
 ]
 
 
