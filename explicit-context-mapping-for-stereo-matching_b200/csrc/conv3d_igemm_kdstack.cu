@@ -1,5 +1,5 @@
-// K2 (throughput path) -- "kd-stacked" persistent implicit GEMM for the stride-1 3x3x3 layers with Cout = 32
-// (32->32 and 64->32: 9 of the 13 stride-1 layers and 86 % of the tensor FLOPs of the aggregation).
+// K2 (throughput path) -- "kd-stacked" persistent implicit GEMM for the stride-1 3x3x3 layers: 32->32, 64->32 and
+// 64->64 (as two independent groups of 32 output channels, each on half of the CTAs).
 //
 // conv3d_igemm_persistent.cu issues one M128 x N32 MMA per (tap, k-step): with both operands in shared memory such an
 // MMA reads 4 KB of A + 1 KB of B through the 128 B/clk port = 40 clk for 16 clk of tensor work (the 40 % ceiling
@@ -46,27 +46,37 @@ struct KdUnit {
     int b, ty, tx, d0, d1, pl0, pl1;
 };
 
-__device__ __forceinline__ KdUnit kd_unit(int unit, int tiles_w, int tiles_h, int nseg, int D) {
-    const int per_seg = tiles_w * tiles_h, per_sample = per_seg * nseg;
-    KdUnit u;
-    u.b = unit / per_sample;
-    int r = unit - u.b * per_sample;
-    const int seg = r / per_seg;
-    r -= seg * per_seg;
-    u.ty = r / tiles_w;
-    u.tx = r - u.ty * tiles_w;
-    u.d0 = (int)((long long)seg * D / nseg);
-    u.d1 = (int)((long long)(seg + 1) * D / nseg);
-    u.pl0 = u.d0 > 0 ? u.d0 - 1 : 0;
-    u.pl1 = u.d1 < D ? u.d1 : D - 1;
-    return u;
-}
+// Work partition: the (tile column, depth) space of one output-channel group is linearised (column-major, depth
+// fastest) and cut into equal contiguous ranges, one per CTA of the group; a range is walked as segments that stay
+// inside one column.  A segment [d0,d1) needs the input planes d0-1 .. d1 (clipped to the volume).
+struct KdWalk {
+    long long pos, end;
+    int D, tiles_w, per_sample;
+    __device__ __forceinline__ KdWalk(int rank, int nranks, long long total, int D_, int tiles_w_, int tiles_h_)
+        : pos(total * rank / nranks), end(total * (rank + 1) / nranks), D(D_), tiles_w(tiles_w_),
+          per_sample(tiles_w_ * tiles_h_) {}
+    __device__ __forceinline__ bool next(KdUnit& u) {
+        if (pos >= end) return false;
+        const int col = (int)(pos / D);
+        u.d0 = (int)(pos - (long long)col * D);
+        const long long left = end - pos;
+        u.d1 = (left < (long long)(D - u.d0)) ? u.d0 + (int)left : D;
+        pos += u.d1 - u.d0;
+        u.b = col / per_sample;
+        const int r = col - u.b * per_sample;
+        u.ty = r / tiles_w;
+        u.tx = r - u.ty * tiles_w;
+        u.pl0 = u.d0 > 0 ? u.d0 - 1 : 0;
+        u.pl1 = u.d1 < D ? u.d1 : D - 1;
+        return true;
+    }
+};
 
 template <int CIN, int NS>
 __global__ void __launch_bounds__(kIgThreads, 1)
     conv3d_igemm_kdstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ wpk,
                                 __nv_bfloat16* __restrict__ y, double* __restrict__ gn_sums, int D, int H, int W,
-                                int tiles_w, int tiles_h, int nseg, int total_units) {
+                                int tiles_w, int tiles_h, long long total_planes, int cout_total, int ctas_per_group) {
     using G = KdCfg<CIN, NS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -82,6 +92,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
     double* sred = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [4][32][2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = blockIdx.x / ctas_per_group, rank = blockIdx.x - group * ctas_per_group;  // group = 32 couts
 
     if (threadIdx.x == 0) {
         mbar_init(barW, 1);
@@ -112,11 +123,13 @@ __global__ void __launch_bounds__(kIgThreads, 1)
             for (int tap = 0; tap < 27; ++tap) {
                 const int kd = tap / 9, khkw = tap % 9;
                 for (int c = 0; c < G::NC; ++c)
-                    bulk_g2s(sW + ((khkw * G::NC + c) * 3 + kd) * 512, wpk + (size_t)tap * CIN * 32 + c * 256, 512, barW);
+                    bulk_g2s(sW + ((khkw * G::NC + c) * 3 + kd) * 512,
+                             wpk + ((size_t)tap * G::NC + c) * cout_total * 8 + group * 256, 512, barW);
             }
             int g = 0;
-            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-                const KdUnit u = kd_unit(unit, tiles_w, tiles_h, nseg, D);
+            KdWalk walk(rank, ctas_per_group, total_planes, D, tiles_w, tiles_h);
+            KdUnit u;
+            while (walk.next(u)) {
                 for (int p = u.pl0; p <= u.pl1; ++p, ++g) {
                     const int s = g % NS;
                     if (g >= NS) mbar_wait(emptyA + s, ((g / NS) - 1) & 1);
@@ -134,8 +147,9 @@ __global__ void __launch_bounds__(kIgThreads, 1)
         mbar_wait(barW, 0);
         tc_fence_after();
         int g = 0;
-        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-            const KdUnit u = kd_unit(unit, tiles_w, tiles_h, nseg, D);
+        KdWalk walk(rank, ctas_per_group, total_planes, D, tiles_w, tiles_h);
+        KdUnit u;
+        while (walk.next(u)) {
             for (int p = u.pl0; p <= u.pl1; ++p, ++g) {
                 const int s = g % NS, buf = g & 3;
                 mbar_wait(fullA + s, (g / NS) & 1);
@@ -179,13 +193,14 @@ __global__ void __launch_bounds__(kIgThreads, 1)
                 double a = 0.0;
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) a += sred[(qd * 32 + c) * 2 + which];
-                atomicAdd(gn_sums + ((size_t)b * 32 + c) * 2 + which, a);
+                atomicAdd(gn_sums + ((size_t)b * cout_total + group * 32 + c) * 2 + which, a);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         };
         int g_base = 0, acquired = 0;
-        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-            const KdUnit u = kd_unit(unit, tiles_w, tiles_h, nseg, D);
+        KdWalk walk(rank, ctas_per_group, total_planes, D, tiles_w, tiles_h);
+        KdUnit u;
+        while (walk.next(u)) {
             const int h = u.ty * 16 + (row >> 3), w = u.tx * 8 + (row & 7);
             const bool hw_ok = (h < H) && (w < W);
             if (gn_sums != nullptr && u.b != cur_b) {
@@ -240,7 +255,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
                             s[j * 8 + 2 * e + 1] += r1;
                             ss[j * 8 + 2 * e + 1] = fmaf(r1, r1, ss[j * 8 + 2 * e + 1]);
                         }
-                        __nv_bfloat16* dst = y + ((((size_t)u.b * 4 + j) * D + d) * plane + (size_t)h * W + w) * 8;
+                        __nv_bfloat16* dst = y + ((((size_t)u.b * (cout_total >> 3) + group * 4 + j) * D + d) * plane + (size_t)h * W + w) * 8;
                         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(pk);
                     }
                 }
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
 }
 
 template <int CIN, int NS>
-static int launch_kdstack(const void* x, const void* wpk, void* y, double* gn, int B, int D, int H, int W,
+static int launch_kdstack(const void* x, const void* wpk, void* y, double* gn, int B, int Cout, int D, int H, int W,
                           cudaStream_t st) {
     using G = KdCfg<CIN, NS>;
     CUtensorMap tmap;
@@ -284,35 +299,23 @@ static int launch_kdstack(const void* x, const void* wpk, void* y, double* gn, i
     CMF_CUDA(cudaGetDevice(&dev));
     CMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int tiles_w = (int)cdiv(W, 8), tiles_h = (int)cdiv(H, 16);
-    const long long columns = (long long)tiles_w * tiles_h * B;
-    // depth segments per tile column: trade the 2 halo planes per segment against the fill of the last round
-    int nseg = 1;
-    double best = 0.0;
-    for (int n = 1; n <= 8 && n <= D; ++n) {
-        const long long units = columns * n;
-        const double fill = (double)units / (double)(cdiv(units, sms) * sms);
-        const double dseg = (double)D / n;
-        const double eff = fill * dseg / (dseg + (n > 1 ? 2.0 : 0.0));
-        if (eff > best + 1e-9) {
-            best = eff;
-            nseg = n;
-        }
-    }
-    const long long total = columns * nseg;
-    CMF_REQUIRE(total < (1ll << 31), "conv3d_igemm_kdstack: too many work units");
-    const unsigned grid = (unsigned)(total < sms ? total : sms);
-    kern<<<grid, kIgThreads, G::SMEM_BYTES, st>>>(tmap, reinterpret_cast<const __nv_bfloat16*>(wpk),
-                                                  reinterpret_cast<__nv_bfloat16*>(y), gn, D, H, W, tiles_w, tiles_h,
-                                                  nseg, (int)total);
+    const int groups = Cout / 32;  // every CTA keeps the stacked weights of ONE group of 32 output channels resident
+    const long long total_planes = (long long)tiles_w * tiles_h * B * D;
+    long long per_group = sms / groups;
+    if (per_group < 1) per_group = 1;
+    if (per_group > total_planes) per_group = total_planes;  // every CTA gets at least one plane
+    kern<<<(unsigned)(per_group * groups), kIgThreads, G::SMEM_BYTES, st>>>(
+        tmap, reinterpret_cast<const __nv_bfloat16*>(wpk), reinterpret_cast<__nv_bfloat16*>(y), gn, D, H, W, tiles_w,
+        tiles_h, total_planes, Cout, (int)per_group);
     CMF_LAUNCH_CHECK("conv3d_igemm_kdstack_kernel");
     return CMFB200_OK;
 }
 
-// used by conv3d_igemm_persistent_dispatch for the Cout = 32 layers
-int conv3d_igemm_kdstack_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int D, int H,
-                                  int W, cudaStream_t st) {
-    if (Cin == 32) return launch_kdstack<32, 6>(x, wpk, y, gn, B, D, H, W, st);
-    if (Cin == 64) return launch_kdstack<64, 4>(x, wpk, y, gn, B, D, H, W, st);
+// used by conv3d_igemm_persistent_dispatch: 32->32, 64->32 and (as two groups of 32 output channels) 64->64
+int conv3d_igemm_kdstack_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout, int D,
+                                  int H, int W, cudaStream_t st) {
+    if (Cin == 32) return launch_kdstack<32, 6>(x, wpk, y, gn, B, Cout, D, H, W, st);
+    if (Cin == 64) return launch_kdstack<64, 4>(x, wpk, y, gn, B, Cout, D, H, W, st);
     CMF_REQUIRE(false, "conv3d_igemm_kdstack: unsupported Cin=%d", Cin);
 }
 

@@ -310,14 +310,15 @@ static int launch_persistent(const void* x, const void* wpk, void* y, double* gn
     return CMFB200_OK;
 }
 
-int conv3d_igemm_kdstack_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int D, int H,
-                                  int W, cudaStream_t st);  // conv3d_igemm_kdstack.cu
+int conv3d_igemm_kdstack_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout, int D,
+                                  int H, int W, cudaStream_t st);  // conv3d_igemm_kdstack.cu
 
 // dispatcher used by cmfb200_conv3d_igemm_bf16_fwd (conv3d_igemm.cu)
 int conv3d_igemm_persistent_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout,
                                      int D, int H, int W, cudaStream_t st) {
     static const bool tap_schedule = getenv("CMFB200_IGEMM_PER_TAP") != nullptr;  // A/B switch: one N=32 MMA per tap
-    if (Cout == 32 && !tap_schedule) return conv3d_igemm_kdstack_dispatch(x, wpk, y, gn, B, Cin, D, H, W, st);
+    if (!tap_schedule && (Cout == 32 || (Cin == 64 && Cout == 64)))
+        return conv3d_igemm_kdstack_dispatch(x, wpk, y, gn, B, Cin, Cout, D, H, W, st);
     if (Cin == 32 && Cout == 32) return launch_persistent<32, 32, 4, 2, true, 1>(x, wpk, y, gn, B, D, H, W, st);
     if (Cin == 64 && Cout == 32) return launch_persistent<64, 32, 2, 1, true, 1>(x, wpk, y, gn, B, D, H, W, st);
     if (Cin == 64 && Cout == 64) return launch_persistent<64, 64, 2, 1, false, 12>(x, wpk, y, gn, B, D, H, W, st);

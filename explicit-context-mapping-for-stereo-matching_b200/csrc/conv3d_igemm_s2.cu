@@ -443,6 +443,9 @@ static int launch_s2_igemm(const void* xs, const void* wpk, void* y, double* gn,
     return CMFB200_OK;
 }
 
+int deconv3d_igemm_persistent_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout,
+                                       int D, int H, int W, cudaStream_t st);  // deconv3d_igemm_persistent.cu
+
 }  // namespace cmfb200
 
 using namespace cmfb200;
@@ -452,6 +455,9 @@ extern "C" int cmfb200_deconv3d_igemm_bf16_fwd(const void* x_c8, const void* pac
     CMF_REQUIRE(x_c8 && packed_w && y_c8, "deconv3d_igemm_bf16_fwd: null pointer");
     CMF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "deconv3d_igemm_bf16_fwd: non-positive dimension");
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool simple_schedule = getenv("CMFB200_IGEMM_SIMPLE") != nullptr;  // A/B switch: one tile per CTA
+    if (!simple_schedule && Cin == 64 && (Cout == 32 || Cout == 64))
+        return deconv3d_igemm_persistent_dispatch(x_c8, packed_w, y_c8, gn_sums, B, Cin, Cout, D, H, W, st);
     if (Cin == 64 && Cout == 64) return launch_deconv_igemm<64, 64, 8>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
     if (Cin == 64 && Cout == 32) return launch_deconv_igemm<64, 32, 16>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
     CMF_REQUIRE(false, "deconv3d_igemm_bf16_fwd: unsupported (Cin=%d, Cout=%d); supported: 64->64, 64->32", Cin, Cout);

@@ -310,7 +310,7 @@ def test_k1_c8_bf16_matches_fp32_cost_volume():
 IGEMM_CASES = [  # B, Cin, Cout, D, H, W
     (1, 32, 32, 4, 16, 8), (1, 32, 32, 6, 20, 12), (2, 64, 32, 5, 16, 8), (1, 64, 64, 4, 18, 24), (1, 32, 32, 9, 37, 29),
     # depth-walking schedule: single plane, two planes, several work units per CTA / depth segments, sample changes
-    (2, 32, 32, 1, 16, 8), (1, 32, 32, 2, 16, 16), (1, 64, 32, 12, 64, 80), (3, 32, 32, 16, 48, 200),
+    (2, 32, 32, 1, 16, 8), (1, 32, 32, 2, 16, 16), (1, 64, 32, 12, 64, 80), (3, 32, 32, 16, 48, 200), (2, 64, 64, 6, 40, 72),
 ]
 
 
@@ -352,7 +352,8 @@ def test_gn_apply_c8_vs_oracle():
     assert torch.equal(split, ref)
 
 
-@pytest.mark.parametrize("B,Cout,D,H,W", [(1, 64, 2, 16, 8), (2, 32, 3, 10, 12), (1, 64, 3, 18, 20), (1, 32, 5, 33, 9)])
+@pytest.mark.parametrize("B,Cout,D,H,W", [(1, 64, 2, 16, 8), (2, 32, 3, 10, 12), (1, 64, 3, 18, 20), (1, 32, 5, 33, 9),
+                                           (3, 32, 6, 40, 60), (2, 64, 4, 36, 60)])  # several tiles per persistent CTA
 def test_deconv3d_igemm_tcgen05_vs_oracle(B, Cout, D, H, W):
     from cmf_b200 import ops
 
