@@ -227,8 +227,8 @@ class cmfsm(nn.Module):
         return feat, full
 
     # ---- bf16 aggregation: every 3x3x3 conv / strided conv / transposed conv of the 3-D network is a tcgen05
-    # implicit GEMM on the C8 layout; only the three 32->1 classifier convs (N=1: no tensor-core shape) run on the
-    # CUDA cores.
+    # implicit GEMM on the C8 layout, including the three 32->1 classifier convs (weights zero-padded to 32
+    # output channels, depth-stacked schedule, fp32 output).
     def _pack_ig(self, conv):
         w = conv.weight
         key = (conv._cmf_name, w.device.index, "ig")
@@ -260,8 +260,20 @@ class cmfsm(nn.Module):
         out = self._ig(hg.conv6, post, residual=resid, relu=False, split=split_out)
         return out, pre, post
 
+    def _pack_ig_cout1(self, conv):
+        w = conv.weight
+        key = (conv._cmf_name, w.device.index, "ig1")
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+            return hit[2]
+        padded = torch.zeros((32,) + tuple(w.shape[1:]), device=w.device, dtype=w.dtype)
+        padded[:1] = w.detach()
+        packed = ops.pack_igemm_weight(padded)
+        self._packed[key] = (w._version, w.data_ptr(), packed)
+        return packed
+
     def _classify_bf16(self, head, x):
-        return ops.conv3d_c8_cout1(self._ig(head[0], x, relu=True), head[2].weight)
+        return ops.conv3d_igemm_cout1(self._ig(head[0], x, relu=True), self._pack_ig_cout1(head[2]))
 
     def _aggregate_bf16(self, lfeat, rfeat, D):
         cost = ops.cost_volume_concat_c8(lfeat, rfeat, D)

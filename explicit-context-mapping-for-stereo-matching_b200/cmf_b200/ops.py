@@ -349,6 +349,21 @@ def conv3d_c8_cout1(x, weight):
     return y
 
 
+def conv3d_igemm_cout1(x, packed32):
+    """classifN.2 on tensor cores: C8/bf16 [B,4,D,H,W,8] x pack_igemm_weight(weight zero-padded to 32 couts)
+    -> fp32 [B,D,H,W]."""
+    _req(x, packed32, dtype=BF16)
+    B, NC, D, H, W, _ = x.shape
+    if tuple(packed32.shape) != (27, NC, 32, 8) or NC != 4:
+        raise ValueError("expected packed weights [27,4,32,8] and a 32-channel input, got %s / %d channels"
+                         % (tuple(packed32.shape), NC * 8))
+    y = torch.empty((B, D, H, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _timed("conv3d_igemm_cout1_bf16_fwd"):
+        _lib.check(_lib.load().cmfb200_conv3d_igemm_cout1_bf16_fwd(_p(x), _p(packed32), _p(y), B, NC * 8, D, H, W, _stream()),
+                   "conv3d_igemm_cout1_bf16_fwd")
+    return y
+
+
 def deconv3d_igemm(x, packed, want_stats=True):
     """tcgen05 transposed conv (k3 s2 p1 op1) on C8/bf16: [B,Cin/8,D,H,W,8] -> [B,Cout/8,2D,2H,2W,8]."""
     _req(x, packed, dtype=BF16)

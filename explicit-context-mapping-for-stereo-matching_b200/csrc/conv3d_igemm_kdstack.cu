@@ -72,10 +72,12 @@ struct KdWalk {
     }
 };
 
-template <int CIN, int NS>
+// COUT1: classifier tail (Cin -> 1): the weights arrive zero-padded to 32 output channels, only column 0 of every
+// accumulator block is read back and written as fp32 [B][D][H][W] (no GroupNorm follows).
+template <int CIN, int NS, bool COUT1>
 __global__ void __launch_bounds__(kIgThreads, 1)
     conv3d_igemm_kdstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ wpk,
-                                __nv_bfloat16* __restrict__ y, double* __restrict__ gn_sums, int D, int H, int W,
+                                void* __restrict__ y_out, double* __restrict__ gn_sums, int D, int H, int W,
                                 int tiles_w, int tiles_h, long long total_planes, int cout_total, int ctas_per_group) {
     using G = KdCfg<CIN, NS>;
     extern __shared__ uint8_t smem_raw[];
@@ -219,6 +221,18 @@ __global__ void __launch_bounds__(kIgThreads, 1)
                     ++acquired;
                 }
                 tc_fence_after();
+                if constexpr (COUT1) {
+                    float o0 = __uint_as_float(tmem_ld_32x32b_x1(tlane + ((g_base + d - u.pl0) & 3) * kBufCols + 32));
+                    if (d - 1 >= 0) o0 += __uint_as_float(tmem_ld_32x32b_x1(tlane + ((g_base + d - 1 - u.pl0) & 3) * kBufCols + 0));
+                    if (d + 1 < D) o0 += __uint_as_float(tmem_ld_32x32b_x1(tlane + ((g_base + d + 1 - u.pl0) & 3) * kBufCols + 64));
+                    if (d - 1 >= u.pl0) {
+                        tc_fence_before();
+                        kd_mbar_arrive(tmemEmpty + ((g_base + d - 1 - u.pl0) & 3));
+                    }
+                    if (hw_ok) reinterpret_cast<float*>(y_out)[((size_t)u.b * D + d) * plane + (size_t)h * W + w] = o0;
+                    continue;
+                }
+                __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_out);
                 float o[32];
                 {
                     uint32_t v[32];
@@ -283,7 +297,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
     }
 }
 
-template <int CIN, int NS>
+template <int CIN, int NS, bool COUT1>
 static int launch_kdstack(const void* x, const void* wpk, void* y, double* gn, int B, int Cout, int D, int H, int W,
                           cudaStream_t st) {
     using G = KdCfg<CIN, NS>;
@@ -293,7 +307,7 @@ static int launch_kdstack(const void* x, const void* wpk, void* y, double* gn, i
                                 (cuuint64_t)G::NC * D * H * W * 16};
     const cuuint32_t box[5] = {kKW * 8, kKH, 1, (cuuint32_t)G::NC, 1};
     if (int rc = encode_tmap_5d(&tmap, x, gdim, gstr, box, "conv3d_igemm_kdstack")) return rc;
-    auto kern = conv3d_igemm_kdstack_kernel<CIN, NS>;
+    auto kern = conv3d_igemm_kdstack_kernel<CIN, NS, COUT1>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
     int dev = 0, sms = kNumSMs;
     CMF_CUDA(cudaGetDevice(&dev));
@@ -305,8 +319,8 @@ static int launch_kdstack(const void* x, const void* wpk, void* y, double* gn, i
     if (per_group < 1) per_group = 1;
     if (per_group > total_planes) per_group = total_planes;  // every CTA gets at least one plane
     kern<<<(unsigned)(per_group * groups), kIgThreads, G::SMEM_BYTES, st>>>(
-        tmap, reinterpret_cast<const __nv_bfloat16*>(wpk), reinterpret_cast<__nv_bfloat16*>(y), gn, D, H, W, tiles_w,
-        tiles_h, total_planes, Cout, (int)per_group);
+        tmap, reinterpret_cast<const __nv_bfloat16*>(wpk), y, gn, D, H, W, tiles_w, tiles_h, total_planes, Cout,
+        (int)per_group);
     CMF_LAUNCH_CHECK("conv3d_igemm_kdstack_kernel");
     return CMFB200_OK;
 }
@@ -314,9 +328,18 @@ static int launch_kdstack(const void* x, const void* wpk, void* y, double* gn, i
 // used by conv3d_igemm_persistent_dispatch: 32->32, 64->32 and (as two groups of 32 output channels) 64->64
 int conv3d_igemm_kdstack_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout, int D,
                                   int H, int W, cudaStream_t st) {
-    if (Cin == 32) return launch_kdstack<32, 6>(x, wpk, y, gn, B, Cout, D, H, W, st);
-    if (Cin == 64) return launch_kdstack<64, 4>(x, wpk, y, gn, B, Cout, D, H, W, st);
+    if (Cin == 32) return launch_kdstack<32, 6, false>(x, wpk, y, gn, B, Cout, D, H, W, st);
+    if (Cin == 64) return launch_kdstack<64, 4, false>(x, wpk, y, gn, B, Cout, D, H, W, st);
     CMF_REQUIRE(false, "conv3d_igemm_kdstack: unsupported Cin=%d", Cin);
 }
 
 }  // namespace cmfb200
+
+extern "C" int cmfb200_conv3d_igemm_cout1_bf16_fwd(const void* x_c8, const void* packed_w32, float* y, int B, int Cin,
+                                                   int D, int H, int W, void* stream) {
+    using namespace cmfb200;
+    CMF_REQUIRE(x_c8 && packed_w32 && y, "conv3d_igemm_cout1_bf16_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_igemm_cout1_bf16_fwd: non-positive dimension");
+    CMF_REQUIRE(Cin == 32, "conv3d_igemm_cout1_bf16_fwd: unsupported Cin=%d (supported: 32)", Cin);
+    return launch_kdstack<32, 6, true>(x_c8, packed_w32, y, nullptr, B, 32, D, H, W, (cudaStream_t)stream);
+}

@@ -401,6 +401,21 @@ def test_conv3d_c8_cout1_vs_oracle(B, D, H, W):
     assert _rel_l2(got, want) < 1e-5  # fp32 accumulation of exactly representable bf16 inputs
 
 
+@pytest.mark.parametrize("B,D,H,W", [(1, 4, 6, 10), (2, 5, 9, 33), (1, 12, 48, 40)])
+def test_conv3d_igemm_cout1_vs_oracle(B, D, H, W):
+    """classifier tail on tensor cores: both operands bf16, fp32 accumulation, fp32 output (no output rounding)."""
+    from cmf_b200 import ops
+
+    x = _rand(B, 32, D, H, W, seed=95)
+    wgt = _rand(1, 32, 3, 3, 3, seed=96) * 0.05
+    want = F.conv3d(x.to(torch.bfloat16).double(), wgt.to(torch.bfloat16).double(), None, 1, 1).squeeze(1)
+    padded = torch.zeros(32, 32, 3, 3, 3)
+    padded[:1] = wgt
+    got = ops.conv3d_igemm_cout1(ops.f32_to_c8(x.to(DEV)), ops.pack_igemm_weight(padded.to(DEV)))
+    assert got.shape == want.shape
+    assert _rel_l2(got, want) < 1e-5
+
+
 @pytest.mark.parametrize("B,H,W", [(1, 64, 128), (2, 144, 240), (1, 96, 312)])
 def test_spp_pool_and_upsample_concat_vs_oracle(B, H, W):
     """SPP pools (floor mode) and the bilinear upsample + concat vs the ATen ops the reference calls."""
