@@ -226,6 +226,38 @@ class cmfsm(nn.Module):
         feat, _ = self._c2(fe.lastconv[2], o, False)
         return feat, full
 
+    # ---- the same extractor under autograd (training): forward = the same kernels, backward per cmf_b200.autograd_ops
+    def _features_train(self, x):
+        fe = self.feature_extraction
+
+        def cg2(block, t, residual=None, relu=False):
+            conv, gn = block[0], block[1]
+            return aops.conv2d_gn(t, conv.weight, gn.weight, gn.bias, conv.stride[0], conv.dilation[0], residual, relu)
+
+        o = cg2(fe.firstconv[0], x, relu=True)
+        o = cg2(fe.firstconv[2], o, relu=True)
+        o = cg2(fe.firstconv[4], o, relu=True)
+        full = aops.conv2d_plain(o, fe.firstconv[6].weight)
+        gn0 = fe.secondconv[0]
+        o = aops.group_norm_act(full, gn0.weight, gn0.bias, True)
+        o = cg2(fe.secondconv[2], o, relu=True)
+        o = cg2(fe.secondconv[4], o, relu=True)
+        raw = None
+        for name in ("layer1", "layer2", "layer3", "layer4"):
+            for unit in getattr(fe, name):
+                t = cg2(unit.conv1[0], o, relu=True)
+                skip = o if unit.downsample is None else cg2(unit.downsample, o)
+                o = cg2(unit.conv2, t, residual=skip)
+            if name == "layer2":
+                raw = o
+        skip = o
+        b1, b2, b3, b4 = [cg2(getattr(fe, "branch%d" % (i + 1))[1], F.avg_pool2d(skip, k, k), relu=True)
+                          for i, k in enumerate((64, 32, 16, 8))]
+        cat = aops.spp_upsample_concat(raw, skip, b4, b3, b2, b1)
+        o = cg2(fe.lastconv[0], cat, relu=True)
+        feat = aops.conv2d_plain(o, fe.lastconv[2].weight)
+        return feat, full
+
     # ---- bf16 aggregation: every 3x3x3 conv / strided conv / transposed conv of the 3-D network is a tcgen05
     # implicit GEMM on the C8 layout, including the three 32->1 classifier convs (weights zero-padded to 32
     # output channels, depth-stacked schedule, fp32 output).
@@ -497,10 +529,7 @@ class cmfsm(nn.Module):
         left, right = left.float(), right.float()
         both = torch.cat([left, right], 0)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.feature_extraction.parameters()):
-            # training: autograd through the cuDNN modules (strict fp32); our kernels are forward-only here
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                feat, _half, full = self.feature_extraction(both)
-            feat = feat.contiguous()
+            feat, full = self._features_train(both.contiguous())
         else:
             feat, full = self._features(both.contiguous())
         lfeat, rfeat = feat[:B], feat[B:]

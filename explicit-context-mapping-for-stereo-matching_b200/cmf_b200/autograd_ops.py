@@ -1,10 +1,15 @@
 """Differentiable wrappers used when `cmfsm.forward` runs under autograd (training, train.py:166-181).
 
-FORWARD always runs the libcmfb200 kernels.  BACKWARD status (round 1):
+FORWARD always runs the libcmfb200 kernels (2-D extractor included).  BACKWARD status (round 1):
   * cost volume           -- own kernel (`cmfb200_cost_volume_concat_bwd`);
   * conv/deconv+GroupNorm -- interim: ATen `convolution_backward` / `native_group_norm_backward` on the
     tensors saved by our forward (SURVEY.md section 7 step 5 allows this while dgrad/wgrad kernels are written);
-  * K5 / K4               -- interim: the closed forms below are re-evaluated with PyTorch CUDA ops inside
+    these run under the process-wide cuDNN setting (`torch.backends.cudnn.allow_tf32`, PyTorch default True --
+    what the reference's own backward would use on this GPU);
+  * SPP upsample + concat -- gradient slices + two dense products per branch (adjoint of the bilinear map);
+  * K5                    -- own kernel (`cmfb200_ctxmap_weights_bwd`) + two 1x1 GEMMs; the PyTorch closed form below
+    is the test reference and the path for scales other than 4;
+  * K4                    -- interim: the closed form below is re-evaluated with PyTorch CUDA ops inside
     `backward` only and differentiated by autograd.
 None of this is reachable on CPU tensors (the forward kernels raise first).
 """
@@ -103,6 +108,141 @@ def conv3d_plain(x, weight):
     return _ConvPlain3d.apply(x, weight)
 
 
+class _ConvGN2d(Function):
+    """2-D conv + GroupNorm (+residual) (+ReLU) of the feature extractor (convbn / BasicBlock, cmfsm.py:36-85)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, residual, stride, dilation, relu):
+        x = x.contiguous()
+        k = weight.shape[-1]
+        raw, sums = ops.conv2d(x, ops.pack_conv2d_weight(weight), k, stride, dilation, want_stats=True)
+        res = residual.contiguous() if residual is not None else None
+        out = ops.gn_apply(raw, sums, gamma, beta, res, relu)
+        ctx.cfg = (k, stride, dilation, relu, residual is not None)
+        ctx.save_for_backward(x, weight, gamma, raw, sums, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        k, stride, dilation, relu, has_res = ctx.cfg
+        x, weight, gamma, raw, sums, out = ctx.saved_tensors
+        g = g.contiguous()
+        if relu:
+            g = g * (out > 0)
+        B, C = raw.shape[:2]
+        spatial = raw[0, 0].numel()
+        mean, rstd = _mean_rstd(sums, C // ops.GN_GROUPS, spatial)
+        d_raw, d_gamma, d_beta = _aten.native_group_norm_backward(g, raw, mean, rstd, gamma, B, C, spatial,
+                                                                   ops.GN_GROUPS, [True, True, True])
+        pad = (k // 2) * dilation
+        dx, dw, _ = _aten.convolution_backward(d_raw, x, weight, None, [stride, stride], [pad, pad],
+                                               [dilation, dilation], False, [0, 0], 1,
+                                               [ctx.needs_input_grad[0], True, False])
+        return dx, dw, d_gamma, d_beta, (g if has_res else None), None, None, None
+
+
+def conv2d_gn(x, weight, gamma, beta, stride=1, dilation=1, residual=None, relu=False):
+    return _ConvGN2d.apply(x, weight, gamma, beta, residual, stride, dilation, relu)
+
+
+class _ConvPlain2d(Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        x = x.contiguous()
+        k = weight.shape[-1]
+        y, _ = ops.conv2d(x, ops.pack_conv2d_weight(weight), k, 1, 1, False)
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        pad = weight.shape[-1] // 2
+        dx, dw, _ = _aten.convolution_backward(g.contiguous(), x, weight, None, [1, 1], [pad, pad], [1, 1], False,
+                                               [0, 0], 1, [True, True, False])
+        return dx, dw
+
+
+def conv2d_plain(x, weight):
+    return _ConvPlain2d.apply(x, weight)
+
+
+class _GroupNormAct(Function):
+    """Stand-alone GroupNorm (+ReLU): feature_extraction.secondconv[0:2] on the kept full-resolution map."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, relu):
+        x = x.contiguous()
+        sums = ops.gn_stats(x)
+        out = ops.gn_apply(x, sums, gamma, beta, None, relu)
+        ctx.relu = relu
+        ctx.save_for_backward(x, gamma, sums, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, sums, out = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.relu:
+            g = g * (out > 0)
+        B, C = x.shape[:2]
+        spatial = x[0, 0].numel()
+        mean, rstd = _mean_rstd(sums, C // ops.GN_GROUPS, spatial)
+        dx, d_gamma, d_beta = _aten.native_group_norm_backward(g, x, mean, rstd, gamma, B, C, spatial, ops.GN_GROUPS,
+                                                               [True, True, True])
+        return dx, d_gamma, d_beta, None
+
+
+def group_norm_act(x, gamma, beta, relu):
+    return _GroupNormAct.apply(x, gamma, beta, relu)
+
+
+_INTERP = {}
+
+
+def _bilinear_matrix(n_in, n_out, device):
+    """[n_out, n_in] matrix of F.interpolate(mode='bilinear', align_corners=False) along one axis."""
+    key = (n_in, n_out, device)
+    m = _INTERP.get(key)
+    if m is None:
+        src = ((torch.arange(n_out, dtype=torch.float32) + 0.5) * (float(n_in) / float(n_out)) - 0.5).clamp_min(0)
+        i0 = src.floor().long().clamp_max(n_in - 1)
+        i1 = (i0 + 1).clamp_max(n_in - 1)
+        l1 = src - i0.float()
+        m = torch.zeros(n_out, n_in)
+        m.scatter_add_(1, i0.view(-1, 1), (1 - l1).view(-1, 1))
+        m.scatter_add_(1, i1.view(-1, 1), l1.view(-1, 1))
+        m = m.to(device)
+        _INTERP[key] = m
+    return m
+
+
+class _SppUpsampleConcat(Function):
+    """cat([raw, skip, up(b4), up(b3), up(b2), up(b1)]) (cmfsm.py:207-233).  Backward: the channel slices of the
+    incoming gradient; bilinear upsampling is the separable linear map Uy . b . Ux^T, so its adjoint is two small
+    dense products per branch (ATen's upsample_bilinear2d_backward took 11 ms per step here)."""
+
+    @staticmethod
+    def forward(ctx, raw, skip, b4, b3, b2, b1):
+        ctx.shapes = [tuple(t.shape[2:]) for t in (b4, b3, b2, b1)]
+        return ops.spp_upsample_concat(raw.contiguous(), skip.contiguous(), b4.contiguous(), b3.contiguous(),
+                                       b2.contiguous(), b1.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        H, W = g.shape[2:]
+        grads = [g[:, :64], g[:, 64:192]]
+        for i, (hb, wb) in enumerate(ctx.shapes):
+            gi = g[:, 192 + 32 * i:224 + 32 * i]
+            uy, ux = _bilinear_matrix(hb, H, g.device), _bilinear_matrix(wb, W, g.device)
+            grads.append(torch.matmul(torch.matmul(uy.t(), gi), ux))
+        return tuple(grads)
+
+
+def spp_upsample_concat(raw, skip, b4, b3, b2, b1):
+    return _SppUpsampleConcat.apply(raw, skip, b4, b3, b2, b1)
+
+
 # ---- backward-only closed forms (PyTorch CUDA ops; differentiated by autograd inside backward) -------
 def _position_code(scale, device):
     half = scale // 2
@@ -170,15 +310,20 @@ def _softargmin_ctxmap_torch(c1, c2, c3, weights9, scale):
 class _CtxmapWeights(Function):
     @staticmethod
     def forward(ctx, lr, hr, w0, w1, w2, w3):
-        ctx.save_for_backward(lr, hr, w0, w1, w2, w3)
-        return ops.ctxmap_weights(lr.contiguous(), hr.contiguous(), w0, w1, w2, w3)
+        lr, hr = lr.contiguous(), hr.contiguous()
+        out = ops.ctxmap_weights(lr, hr, w0, w1, w2, w3)
+        ctx.save_for_backward(lr, hr, w0, w1, w2, w3, out)
+        return out
 
     @staticmethod
     def backward(ctx, g):
-        saved = [t.detach().requires_grad_(True) for t in ctx.saved_tensors]
+        lr, hr, w0, w1, w2, w3, out = ctx.saved_tensors
+        if hr.shape[-1] // lr.shape[-1] == 4:  # own kernel (cmfsm: scale 4)
+            return ops.ctxmap_weights_bwd(lr, hr, w0, w1, w2, w3, out, g)
+        saved = [t.detach().requires_grad_(True) for t in (lr, hr, w0, w1, w2, w3)]
         with torch.enable_grad():
-            out = _ctxmap_weights_torch(*saved)
-        return torch.autograd.grad(out, saved, g, allow_unused=True)
+            ref = _ctxmap_weights_torch(*saved)
+        return torch.autograd.grad(ref, saved, g, allow_unused=True)
 
 
 def ctxmap_weights(lr, hr, w0, w1, w2, w3):

@@ -252,6 +252,35 @@ def ctxmap_weights(lr, hr, w0, w1, w2, w3, valid_rows=None):
     return out
 
 
+def ctxmap_weights_bwd(lr, hr, w0, w1, w2, w3, weights9, grad):
+    """Backward of `ctxmap_weights`: returns (d_lr, d_hr, d_w0, d_w1, d_w2, d_w3) with the weights' own shapes.
+    The kernel back-propagates the MLP per (pixel, neighbour); the two linear 1x1 maps of layer 0 are finished here
+    as plain fp32 GEMMs (torch.matmul)."""
+    shapes = [tuple(t.shape) for t in (w0, w1, w2, w3)]
+    ws = [t.detach().reshape(t.shape[0], t.shape[1]).contiguous() for t in (w0, w1, w2, w3)]
+    grad = grad.contiguous()
+    _req(lr, hr, weights9, grad, *ws)
+    B, _, h, w = lr.shape
+    H, W = hr.shape[2:]
+    d_ahr = torch.empty((B, 32, H, W), device=lr.device, dtype=torch.float32)
+    d_alr = torch.empty((B, 32, h, w), device=lr.device, dtype=torch.float32)
+    wbuf = torch.empty(712, device=lr.device, dtype=torch.float32)
+    with torch.cuda.device(lr.device), _timed("ctxmap_weights_bwd"):
+        _lib.check(_lib.load().cmfb200_ctxmap_weights_bwd(_p(lr), _p(hr), _p(ws[0]), _p(ws[1]), _p(ws[2]), _p(ws[3]),
+                                                          _p(weights9), _p(grad), _p(d_ahr), _p(d_alr), _p(wbuf), B, h, w,
+                                                          W // w, _stream()), "ctxmap_weights_bwd")
+    w0m = ws[0]
+    ga, gl = d_ahr.view(B, 32, H * W), d_alr.view(B, 32, h * w)
+    d_hr = torch.matmul(w0m[:, 32:64].t(), ga).view(B, 32, H, W)
+    d_lr = torch.matmul(w0m[:, :32].t(), gl).view(B, 32, h, w)
+    d_w0 = torch.empty((32, 66), device=lr.device, dtype=torch.float32)
+    d_w0[:, :32] = torch.bmm(gl, lr.reshape(B, 32, h * w).transpose(1, 2)).sum(0)
+    d_w0[:, 32:64] = torch.bmm(ga, hr.reshape(B, 32, H * W).transpose(1, 2)).sum(0)
+    d_w0[:, 64:] = wbuf[648:712].view(32, 2)
+    return (d_lr, d_hr, d_w0.view(shapes[0]), wbuf[:512].view(shapes[1]), wbuf[512:640].view(shapes[2]),
+            wbuf[640:648].view(shapes[3]))
+
+
 def softargmin_ctxmap(c1, c2, c3, weights9, scale, want_lowres=False):
     """cmf/models/cmfsm.py:703-769.  c_i [B,D,h,w], weights9 [B,9,H,W] -> 3 x [B,1,H,W] (+ [3,B,h,w])."""
     _req(c1, c2, c3, weights9)

@@ -155,6 +155,14 @@ int cmfb200_gn_apply(const float* x, const double* gn_sums, const float* gamma, 
 int cmfb200_ctxmap_weights_fwd(const float* lr, const float* hr, const float* w0, const float* w1,
                                const float* w2, const float* w3, float* weights9,
                                int B, int h, int w, int scale, int valid_y0, int valid_y1, void* stream);
+/* K5 backward (training; replaces autograd through cmfsm.py:443-593).  weights9 = the forward output, grad_weights9 =
+ * its incoming gradient (both [B,9,H,W]).  With a0 = W0[:,0:32].lr(cell) + W0[:,32:64].hr(pixel) + W0[:,64:66].code
+ * the kernel writes d_ahr [B,32,H,W] = dL/d(W0[:,32:64].hr), d_alr [B,32,h,w] = dL/d(W0[:,0:32].lr) and
+ * d_wbuf[712] = { dW1[16][32], dW2[8][16], dW3[8], dW0[:,64:66] as [32][2] } (fp32, summed with atomics, zeroed
+ * here).  The two remaining linear maps (d hr, d lr, dW0[:,0:64]) are 1x1 GEMMs left to the caller.  scale = 4. */
+int cmfb200_ctxmap_weights_bwd(const float* lr, const float* hr, const float* w0, const float* w1, const float* w2,
+                               const float* w3, const float* weights9, const float* grad_weights9, float* d_ahr,
+                               float* d_alr, float* d_wbuf, int B, int h, int w, int scale, void* stream);
 
 /* ---- K4: soft-argmin + x scale upsample + 9-neighbour context mapping ---------------------------
  * Replaces cmfsm.py:703-769 (3x softmax, disparityregression :111-123, ~60 slice kernels).

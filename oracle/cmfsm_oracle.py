@@ -293,12 +293,14 @@ def check_shapes(H, W, maxdisp, B=1):
         raise ValueError("image too small for the 64x64 SPP pooling branch followed by GroupNorm")
 
 
-def forward(sd, left, right, maxdisp=192, stages=None):
+def forward(sd, left, right, maxdisp=192, stages=None, grad=False):
     """cmfsm.forward -- cmfsm.py:655-775, per-sample output semantics [B,1,H,W] for each of 3 outputs.
 
     For B>1 the reference broadcasts to [B,B,H,W]; the diagonal equals this result.
+    `grad=True` keeps the autograd graph (every op above is a differentiable torch op), which makes this the
+    gradient oracle of the training path as well.
     """
-    with torch.no_grad():
+    with torch.set_grad_enabled(grad):
         sd = strip_module_prefix(sd)
         B, _, H, W = left.shape
         check_shapes(H, W, maxdisp, B)

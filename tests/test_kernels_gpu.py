@@ -430,3 +430,27 @@ def test_spp_pool_and_upsample_concat_vs_oracle(B, H, W):
     cat = ops.spp_upsample_concat(raw.to(DEV), skip.to(DEV), *[t.to(DEV) for t in bs])
     want = torch.cat([raw, skip] + [F.interpolate(t, (H, W), mode="bilinear", align_corners=False) for t in bs], 1)
     torch.testing.assert_close(cat.cpu(), want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 2, 8), (2, 5, 11), (1, 16, 24)])
+def test_k5_backward_vs_autograd(B, h, w):
+    """cmfb200_ctxmap_weights_bwd vs autograd through the PyTorch closed form of the same function (fp64 on CPU)."""
+    from cmf_b200 import autograd_ops as aops
+    from cmf_b200 import ops
+
+    lr, hr = _rand(B, 32, h, w, seed=120), _rand(B, 32, 4 * h, 4 * w, seed=121)
+    ws = [_rand(32, 66, 1, 1, seed=122) * 0.3, _rand(16, 32, 1, 1, seed=123) * 0.4, _rand(8, 16, 1, 1, seed=124) * 0.5,
+          _rand(1, 8, 1, 1, seed=125)]
+    g = _rand(B, 9, 4 * h, 4 * w, seed=126)
+    ref_in = [t.double().requires_grad_(True) for t in [lr, hr] + ws]
+    ref_out = aops._ctxmap_weights_torch(*ref_in)
+    ref_grads = torch.autograd.grad(ref_out, ref_in, g.double())
+    dev = [t.to(DEV) for t in [lr, hr] + ws]
+    out = ops.ctxmap_weights(*dev)
+    torch.testing.assert_close(out.cpu().double(), ref_out.detach(), rtol=1e-4, atol=1e-6)
+    got = ops.ctxmap_weights_bwd(*dev, out, g.to(DEV))
+    for name, a, b in zip(("d_lr", "d_hr", "d_w0", "d_w1", "d_w2", "d_w3"), got, ref_grads):
+        assert a.shape == b.shape, name
+        err = _rel_l2(a.cpu().double(), b)
+        print("K5 bwd %s rel-L2 %.2e" % (name, err))
+        assert err < 2e-5, (name, err)

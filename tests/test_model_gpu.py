@@ -143,3 +143,40 @@ def test_training_step_gradients_flow(model):
     assert not missing, missing[:5]
     assert float(net.dres0[0][0].weight.grad.abs().sum()) > 0
     assert float(net.mapping_matrix.similarity1.conv0.weight.grad.abs().sum()) > 0
+
+
+def test_training_gradients_match_fp64_oracle():
+    """Gradients of the training path (own forward kernels + the backward of cmf_b200.autograd_ops) against
+    autograd through the fp64 CPU oracle on the same weights / inputs / loss.  The network amplifies rounding
+    (fp32 vs fp64 outputs differ by up to 1e-2 px), and ATen's conv backward runs under the
+    PyTorch-default cuDNN TF32 setting, so the gate is a relative L2 distance per tensor, not bit equality."""
+    from cmf.models import get_model
+
+    torch.manual_seed(2)
+    net = get_model("cmfsm").to(DEV).train()
+    left, right = gc.seeded_pair(1, 256, 512, seed=6)
+    target = torch.rand(1, 256, 512, generator=torch.Generator().manual_seed(7)) * 100 + 1
+
+    def loss_of(outs, tgt):
+        return sum(wt * torch.nn.functional.smooth_l1_loss(o.squeeze(1), tgt) for wt, o in zip((0.5, 0.7, 1.0), outs))
+
+    loss = loss_of(net(left.to(DEV), right.to(DEV)), target.to(DEV))
+    loss.backward()
+
+    sd64 = {k: v.detach().cpu().double().requires_grad_(True) for k, v in net.state_dict().items()}
+    loss64 = loss_of(orc.forward(sd64, left.double(), right.double(), grad=True), target.double())
+    loss64.backward()
+    assert abs(float(loss) - float(loss64)) < 1e-3 * abs(float(loss64))
+    worst = {}
+    for name, p in net.named_parameters():
+        g, g64 = p.grad.detach().cpu().double(), sd64[name].grad
+        rel = float((g - g64).norm() / g64.norm().clamp_min(1e-30))
+        worst[name] = rel
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    print("loss %.6f vs fp64 %.6f; worst gradient rel-L2:" % (float(loss), float(loss64)), top)
+    # every family of the backward: 2-D extractor, SPP branches, K5 MLP, 3-D convs / transposed convs, classifier
+    for key in ("feature_extraction.firstconv.0.0.weight", "feature_extraction.branch1.1.0.weight",
+                "feature_extraction.lastconv.2.weight", "mapping_matrix.similarity1.conv0.weight",
+                "dres0.0.0.weight", "dres2.conv5.0.weight", "classif3.2.weight"):
+        assert worst[key] < 0.1, (key, worst[key])
+    assert sorted(worst.values())[len(worst) // 2] < 0.05  # median over all 272 tensors
