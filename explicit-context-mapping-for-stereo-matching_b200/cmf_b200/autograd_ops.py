@@ -2,8 +2,8 @@
 
 FORWARD always runs the libcmfb200 kernels (2-D extractor included).  BACKWARD status (round 1):
   * cost volume           -- own kernel (`cmfb200_cost_volume_concat_bwd`);
-  * conv/deconv+GroupNorm -- interim: ATen `convolution_backward` / `native_group_norm_backward` on the
-    tensors saved by our forward (SURVEY.md section 7 step 5 allows this while dgrad/wgrad kernels are written);
+  * GroupNorm (+ReLU mask, +residual gradient) -- own kernels (`cmfb200_gn_bwd`);
+  * conv/deconv           -- interim: ATen `convolution_backward` on the tensors saved by our forward (SURVEY.md section 7 step 5 allows this while dgrad/wgrad kernels are written);
     these run under the process-wide cuDNN setting (`torch.backends.cudnn.allow_tf32`, PyTorch default True --
     what the reference's own backward would use on this GPU);
   * SPP upsample + concat -- gradient slices + two dense products per branch (adjoint of the bilinear map);
@@ -39,15 +39,6 @@ def cost_volume_concat(L, R, D):
     return _CostVolume.apply(L, R, D)
 
 
-def _mean_rstd(sums, cpg, spatial, eps=ops.GN_EPS):
-    B, C, _ = sums.shape
-    s = sums.view(B, C // cpg, cpg, 2).sum(2)
-    n = float(cpg * spatial)
-    mean = s[..., 0] / n
-    var = (s[..., 1] / n - mean * mean).clamp_min(0)
-    return mean.float(), torch.rsqrt(var + eps).float()
-
-
 class _ConvGN3d(Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, stride, transposed, relu):
@@ -64,15 +55,7 @@ class _ConvGN3d(Function):
     def backward(ctx, g):
         stride, transposed, relu, has_res = ctx.cfg
         x, weight, gamma, raw, sums, out = ctx.saved_tensors
-        g = g.contiguous()
-        if relu:
-            g = g * (out > 0)
-        B, C = raw.shape[:2]
-        spatial = raw[0, 0].numel()
-        cpg = C // ops.GN_GROUPS
-        mean, rstd = _mean_rstd(sums, cpg, spatial)
-        d_raw, d_gamma, d_beta = _aten.native_group_norm_backward(g, raw, mean, rstd, gamma, B, C, spatial,
-                                                                   ops.GN_GROUPS, [True, True, True])
+        d_raw, d_gamma, d_beta, d_res = ops.gn_backward(g, raw, sums, gamma, out if relu else None, has_res)
         s3, one, zero = [stride] * 3, [1, 1, 1], [0, 0, 0]
         if transposed:
             dx, dw, _ = _aten.convolution_backward(d_raw, x, weight, None, [2, 2, 2], one, one, True, one, 1,
@@ -80,7 +63,7 @@ class _ConvGN3d(Function):
         else:
             dx, dw, _ = _aten.convolution_backward(d_raw, x, weight, None, s3, one, one, False, zero, 1,
                                                    [True, True, False])
-        return dx, dw, d_gamma, d_beta, (g if has_res else None), None, None, None
+        return dx, dw, d_gamma, d_beta, d_res, None, None, None
 
 
 def conv3d_gn(x, weight, gamma, beta, stride=1, transposed=False, residual=None, relu=False):
@@ -126,19 +109,12 @@ class _ConvGN2d(Function):
     def backward(ctx, g):
         k, stride, dilation, relu, has_res = ctx.cfg
         x, weight, gamma, raw, sums, out = ctx.saved_tensors
-        g = g.contiguous()
-        if relu:
-            g = g * (out > 0)
-        B, C = raw.shape[:2]
-        spatial = raw[0, 0].numel()
-        mean, rstd = _mean_rstd(sums, C // ops.GN_GROUPS, spatial)
-        d_raw, d_gamma, d_beta = _aten.native_group_norm_backward(g, raw, mean, rstd, gamma, B, C, spatial,
-                                                                   ops.GN_GROUPS, [True, True, True])
+        d_raw, d_gamma, d_beta, d_res = ops.gn_backward(g, raw, sums, gamma, out if relu else None, has_res)
         pad = (k // 2) * dilation
         dx, dw, _ = _aten.convolution_backward(d_raw, x, weight, None, [stride, stride], [pad, pad],
                                                [dilation, dilation], False, [0, 0], 1,
                                                [ctx.needs_input_grad[0], True, False])
-        return dx, dw, d_gamma, d_beta, (g if has_res else None), None, None, None
+        return dx, dw, d_gamma, d_beta, d_res, None, None, None
 
 
 def conv2d_gn(x, weight, gamma, beta, stride=1, dilation=1, residual=None, relu=False):
@@ -182,14 +158,7 @@ class _GroupNormAct(Function):
     @staticmethod
     def backward(ctx, g):
         x, gamma, sums, out = ctx.saved_tensors
-        g = g.contiguous()
-        if ctx.relu:
-            g = g * (out > 0)
-        B, C = x.shape[:2]
-        spatial = x[0, 0].numel()
-        mean, rstd = _mean_rstd(sums, C // ops.GN_GROUPS, spatial)
-        dx, d_gamma, d_beta = _aten.native_group_norm_backward(g, x, mean, rstd, gamma, B, C, spatial, ops.GN_GROUPS,
-                                                               [True, True, True])
+        dx, d_gamma, d_beta, _ = ops.gn_backward(g, x, sums, gamma, out if ctx.relu else None, False)
         return dx, d_gamma, d_beta, None
 
 

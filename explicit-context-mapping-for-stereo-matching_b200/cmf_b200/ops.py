@@ -232,6 +232,24 @@ def conv3d_gn(x, packed, gamma, beta, stride=1, transposed=False, residual=None,
 
 
 # ------------------------------------------------------------------------------------------ K5 / K4
+def gn_backward(grad_out, x, sums, gamma, out=None, want_dres=False, groups=GN_GROUPS, eps=GN_EPS):
+    """Backward of `gn_apply`: (dx, d_gamma, d_beta, d_residual or None).  `out` = the forward output when the forward
+    applied a ReLU (mask), else None."""
+    gamma = gamma.detach()
+    grad_out = grad_out.contiguous()
+    _req(grad_out, x, gamma, out)
+    B, C = x.shape[:2]
+    spatial = x[0, 0].numel()
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    bsums = torch.empty((B, C, 2), device=x.device, dtype=torch.float64)
+    with torch.cuda.device(x.device), _timed("gn_bwd"):
+        _lib.check(_lib.load().cmfb200_gn_bwd(_p(grad_out), _p(x), _p(out), _p(sums), _p(gamma), _p(bsums), _p(dx),
+                                              _p(dres), B, C, groups, spatial, eps, _stream()), "gn_bwd")
+    tot = bsums.sum(0)
+    return dx, tot[:, 1].float(), tot[:, 0].float(), dres
+
+
 def ctxmap_weights(lr, hr, w0, w1, w2, w3, valid_rows=None):
     """eight_related_context_mapping: [B,32,h,w],[B,32,H,W] -> [B,9,H,W] (cmf/models/cmfsm.py:443-593).
     `valid_rows` = (y0, y1): low-res rows of `lr` that lie inside the image (row bands pass halo rows)."""

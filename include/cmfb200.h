@@ -144,6 +144,14 @@ int cmfb200_gn_stats(const float* x, double* gn_sums, int B, int C, long long sp
 int cmfb200_gn_apply(const float* x, const double* gn_sums, const float* gamma, const float* beta,
                      const float* residual, float* y, int B, int C, int G, long long spatial,
                      float eps, int relu, void* stream);
+/* GroupNorm backward (training).  grad_out = gradient of out = [relu](gamma*xhat + beta [+ residual]); x = the conv
+ * output the forward normalised, gn_sums = its forward statistics; out_or_null = the forward output when a ReLU was
+ * applied (mask out > 0), else NULL.  Writes dx (gradient of x), optionally dres (= masked grad_out, the gradient of
+ * the residual input) and bwd_sums [B][C][2] doubles = { sum g', sum g'*xhat } per (b,channel) (zeroed here), from
+ * which d_beta[c] = sum_b bwd_sums[b][c][0], d_gamma[c] = sum_b bwd_sums[b][c][1]. */
+int cmfb200_gn_bwd(const float* grad_out, const float* x, const float* out_or_null, const double* gn_sums,
+                   const float* gamma, double* bwd_sums, float* dx, float* dres_or_null, int B, int C, int G,
+                   long long spatial, float eps, void* stream);
 
 /* ---- K5: context-mapping weights -----------------------------------------------------------------
  * Replaces eight_related_context_mapping.forward + similarity_measure1 (cmfsm.py:443-593, 304-358).

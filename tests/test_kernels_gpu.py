@@ -454,3 +454,33 @@ def test_k5_backward_vs_autograd(B, h, w):
         err = _rel_l2(a.cpu().double(), b)
         print("K5 bwd %s rel-L2 %.2e" % (name, err))
         assert err < 2e-5, (name, err)
+
+
+@pytest.mark.parametrize("shape,relu,res", [((2, 64, 3, 5, 7), True, True), ((1, 32, 4, 6, 8), False, False),
+                                             ((3, 128, 9, 12), True, False), ((2, 32, 10, 6), False, True)])
+def test_gn_backward_vs_autograd(shape, relu, res):
+    """cmfb200_gn_bwd vs autograd through F.group_norm (+residual)(+ReLU) in fp64."""
+    from cmf_b200 import ops
+
+    C = shape[1]
+    x, g = _rand(*shape, seed=130) * 2 + 0.3, _rand(*shape, seed=131)
+    r = _rand(*shape, seed=132) if res else None
+    gamma, beta = _rand(C, seed=133) + 1.5, _rand(C, seed=134)
+    xr, gr, br = x.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rr = r.double().requires_grad_(True) if res else None
+    y = F.group_norm(xr, 32, gr, br, 1e-5)
+    if res:
+        y = y + rr
+    if relu:
+        y = F.relu(y)
+    want = torch.autograd.grad(y, [xr, gr, br] + ([rr] if res else []), g.double())
+    xd = x.to(DEV)
+    sums = ops.gn_stats(xd)
+    out = ops.gn_apply(xd, sums, gamma.to(DEV), beta.to(DEV), r.to(DEV) if res else None, relu)
+    dx, dg, db, dres = ops.gn_backward(g.to(DEV), xd, sums, gamma.to(DEV), out if relu else None, res)
+    assert _rel_l2(dx.cpu(), want[0]) < 1e-5
+    assert _rel_l2(dg.cpu(), want[1]) < 1e-5 and _rel_l2(db.cpu(), want[2]) < 1e-5
+    if res:
+        assert _rel_l2(dres.cpu(), want[3]) < 1e-6
+    else:
+        assert dres is None
