@@ -3,6 +3,7 @@
 FORWARD always runs the libcmfb200 kernels (2-D extractor included).  BACKWARD status (round 1):
   * cost volume           -- own kernel (`cmfb200_cost_volume_concat_bwd`);
   * GroupNorm (+ReLU mask, +residual gradient) -- own kernels (`cmfb200_gn_bwd`);
+  * classifier 32->1 conv -- own dgrad/wgrad kernels (`cmfb200_conv3d_cout1_bwd`);
   * conv/deconv           -- interim: ATen `convolution_backward` on the tensors saved by our forward (SURVEY.md section 7 step 5 allows this while dgrad/wgrad kernels are written);
     these run under the process-wide cuDNN setting (`torch.backends.cudnn.allow_tf32`, PyTorch default True --
     what the reference's own backward would use on this GPU);
@@ -81,6 +82,8 @@ class _ConvPlain3d(Function):
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
+        if weight.shape[0] == 1 and weight.shape[1] == 32:  # classifier tail: own kernels
+            return ops.conv3d_cout1_backward(x, weight, g)
         one, zero = [1, 1, 1], [0, 0, 0]
         dx, dw, _ = _aten.convolution_backward(g.contiguous(), x, weight, None, one, one, one, False, zero, 1,
                                                [True, True, False])

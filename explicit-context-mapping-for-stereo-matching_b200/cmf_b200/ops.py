@@ -232,6 +232,22 @@ def conv3d_gn(x, packed, gamma, beta, stride=1, transposed=False, residual=None,
 
 
 # ------------------------------------------------------------------------------------------ K5 / K4
+def conv3d_cout1_backward(x, weight, grad_y):
+    """Backward of nn.Conv3d(32, 1, 3, padding=1, bias=False): returns (dx, dw)."""
+    weight = weight.detach().contiguous()
+    grad_y = grad_y.contiguous()
+    _req(x, weight, grad_y)
+    B, Cin, D, H, W = x.shape
+    if tuple(weight.shape) != (1, Cin, 3, 3, 3) or grad_y.numel() != B * D * H * W:
+        raise ValueError("conv3d_cout1_backward: weight %s / grad %s do not match x %s"
+                         % (tuple(weight.shape), tuple(grad_y.shape), tuple(x.shape)))
+    dx, dw = torch.empty_like(x), torch.empty_like(weight)
+    with torch.cuda.device(x.device), _timed("conv3d_cout1_bwd"):
+        _lib.check(_lib.load().cmfb200_conv3d_cout1_bwd(_p(x), _p(weight), _p(grad_y), _p(dx), _p(dw), B, Cin, D, H, W,
+                                                        _stream()), "conv3d_cout1_bwd")
+    return dx, dw
+
+
 def gn_backward(grad_out, x, sums, gamma, out=None, want_dres=False, groups=GN_GROUPS, eps=GN_EPS):
     """Backward of `gn_apply`: (dx, d_gamma, d_beta, d_residual or None).  `out` = the forward output when the forward
     applied a ReLU (mask), else None."""

@@ -64,6 +64,10 @@ int cmfb200_pack_conv3d_weight(const float* weight, float* packed, int Cout, int
  * (b,channel) sum and sum-of-squares of y into it (GroupNorm statistics fused into the epilogue). */
 int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
                           int B, int Cin, int Cout, int D, int H, int W, int stride, void* stream);
+/* Backward of the classifier tail conv nn.Conv3d(Cin, 1, 3, padding=1) (training): x [B,Cin,D,H,W], weight
+ * [1,Cin,3,3,3] (unpacked), grad_y [B,1,D,H,W] -> dx [B,Cin,D,H,W], dw [1,Cin,3,3,3] (zeroed here).  Cin = 32. */
+int cmfb200_conv3d_cout1_bwd(const float* x, const float* weight, const float* grad_y, float* dx, float* dw, int B,
+                             int Cin, int D, int H, int W, void* stream);
 /* Transposed conv k3 s2 p1 op1: y: [B,Cout,2D,2H,2W].  Cout in {32,64}; same gn_sums contract. */
 int cmfb200_deconv3d_k3s2_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
                               int B, int Cin, int Cout, int D, int H, int W, void* stream);

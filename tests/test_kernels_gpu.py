@@ -484,3 +484,14 @@ def test_gn_backward_vs_autograd(shape, relu, res):
         assert _rel_l2(dres.cpu(), want[3]) < 1e-6
     else:
         assert dres is None
+
+
+@pytest.mark.parametrize("B,D,H,W", [(1, 3, 5, 7), (2, 6, 9, 20), (1, 4, 7, 4), (2, 5, 16, 64)])
+def test_conv3d_cout1_backward_vs_autograd(B, D, H, W):
+    from cmf_b200 import ops
+
+    x, wgt, g = _rand(B, 32, D, H, W, seed=140), _rand(1, 32, 3, 3, 3, seed=141) * 0.1, _rand(B, 1, D, H, W, seed=142)
+    xr, wr = x.double().requires_grad_(True), wgt.double().requires_grad_(True)
+    want = torch.autograd.grad(F.conv3d(xr, wr, None, 1, 1), [xr, wr], g.double())
+    dx, dw = ops.conv3d_cout1_backward(x.to(DEV), wgt.to(DEV), g.to(DEV))
+    assert _rel_l2(dx.cpu(), want[0]) < 1e-5 and _rel_l2(dw.cpu(), want[1]) < 1e-5
