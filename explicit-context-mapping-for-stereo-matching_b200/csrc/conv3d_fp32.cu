@@ -649,6 +649,9 @@ static int launch_deconv(const float* x, const float* wp, float* y, double* gn, 
     return CMFB200_OK;
 }
 
+int conv3d_cout1_fp32_dispatch(const float* x, const float* wp, float* y, int B, int Cin, int D, int H, int W,
+                               cudaStream_t st);  // conv3d_cout1_fp32.cu
+
 }  // namespace cmfb200
 
 using namespace cmfb200;
@@ -678,7 +681,13 @@ extern "C" int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, floa
     if (Cout == 64 && stride == 1) return launch_conv_best<64, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
     if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
     if (Cout == 64 && stride == 2) return launch_conv<64, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 1 && stride == 1) return launch_conv_best<1, 1, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    if (Cout == 1 && stride == 1) {
+        if (gn_sums == nullptr && !one_row) {  // classifier tail: TMA-staged 4x4-outputs-per-thread kernel
+            const int rc = conv3d_cout1_fp32_dispatch(x, packed_w, y, B, Cin, D, H, W, st);
+            if (rc >= 0) return rc;
+        }
+        return launch_conv_best<1, 1, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
+    }
     CMF_REQUIRE(false, "conv3d_k3_fwd: unsupported (Cout=%d, stride=%d); Cout in {1,32,64}", Cout, stride);
 }
 

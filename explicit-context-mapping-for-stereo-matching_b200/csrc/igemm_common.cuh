@@ -117,13 +117,14 @@ static inline EncodeTiledFn get_encode_fn() {
 }
 
 
-// rank-5 bf16 tensor map, no swizzle, zero OOB fill
+// rank-5 tensor map (bf16 unless stated), no swizzle, zero OOB fill
 static inline int encode_tmap_5d(CUtensorMap* tmap, const void* base, const cuuint64_t (&gdim)[5],
-                                 const cuuint64_t (&gstr)[4], const cuuint32_t (&box)[5], const char* who) {
+                                 const cuuint64_t (&gstr)[4], const cuuint32_t (&box)[5], const char* who,
+                                 CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
     EncodeTiledFn encode = get_encode_fn();
     CMF_REQUIRE(encode != nullptr, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
+    const CUresult r = encode(tmap, dtype, 5, const_cast<void*>(base), gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CMF_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed with CUresult %d", who, (int)r);

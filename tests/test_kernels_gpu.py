@@ -81,7 +81,7 @@ def test_k1_backward_vs_oracle():
 # ------------------------------------------------------------------------------------------ K2 / K3
 CONV_CASES = [  # B, Cin, Cout, D, H, W, stride
     (1, 64, 32, 6, 8, 20, 1), (2, 32, 32, 5, 9, 36, 1), (1, 32, 64, 8, 8, 16, 2), (1, 32, 64, 7, 9, 18, 2),
-    (1, 64, 64, 6, 10, 40, 2), (1, 64, 64, 3, 5, 34, 1), (2, 32, 1, 6, 8, 12, 1), (1, 32, 1, 9, 17, 70, 1),
+    (1, 64, 64, 6, 10, 40, 2), (1, 64, 64, 3, 5, 34, 1), (2, 32, 1, 6, 8, 12, 1), (1, 32, 1, 9, 17, 70, 1), (2, 32, 1, 17, 19, 72, 1),
     (1, 32, 32, 4, 16, 64, 1),
 ]
 
