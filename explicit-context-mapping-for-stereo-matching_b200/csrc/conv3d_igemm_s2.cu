@@ -443,6 +443,8 @@ static int launch_s2_igemm(const void* xs, const void* wpk, void* y, double* gn,
     return CMFB200_OK;
 }
 
+int conv3d_s2_igemm_persistent_dispatch(const void* xs, const void* wpk, void* y, double* gn, int B, int Cin, int Cout,
+                                        int Do, int Ho, int Wo, cudaStream_t st);  // conv3d_s2_igemm_persistent.cu
 int deconv3d_igemm_persistent_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout,
                                        int D, int H, int W, cudaStream_t st);  // deconv3d_igemm_persistent.cu
 
@@ -469,6 +471,9 @@ extern "C" int cmfb200_conv3d_s2_igemm_bf16_fwd(const void* x_split_c8, const vo
     CMF_REQUIRE(x_split_c8 && packed_w && y_c8, "conv3d_s2_igemm_bf16_fwd: null pointer");
     CMF_REQUIRE(B > 0 && Do > 0 && Ho > 0 && Wo > 0, "conv3d_s2_igemm_bf16_fwd: non-positive dimension");
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool simple_schedule = getenv("CMFB200_IGEMM_SIMPLE") != nullptr;  // A/B switch: one tile per CTA
+    if (!simple_schedule && Cout == 64 && (Cin == 32 || Cin == 64))
+        return conv3d_s2_igemm_persistent_dispatch(x_split_c8, packed_w, y_c8, gn_sums, B, Cin, Cout, Do, Ho, Wo, st);
     if (Cin == 32 && Cout == 64)
         return launch_s2_igemm<32, 64, 2, 2, 10>(x_split_c8, packed_w, y_c8, gn_sums, B, Do, Ho, Wo, st);
     if (Cin == 64 && Cout == 64)

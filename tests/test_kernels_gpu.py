@@ -371,7 +371,8 @@ def test_deconv3d_igemm_tcgen05_vs_oracle(B, Cout, D, H, W):
     torch.testing.assert_close(sums.cpu()[..., 0], got.sum((2, 3, 4)), rtol=1e-6, atol=1e-3)
 
 
-@pytest.mark.parametrize("B,Cin,D,H,W", [(1, 32, 4, 32, 16), (2, 64, 4, 20, 24), (1, 32, 6, 36, 44), (1, 64, 10, 66, 18)])
+@pytest.mark.parametrize("B,Cin,D,H,W", [(1, 32, 4, 32, 16), (2, 64, 4, 20, 24), (1, 32, 6, 36, 44), (1, 64, 10, 66, 18),
+                                          (3, 32, 8, 48, 80), (2, 64, 6, 40, 56)])
 def test_conv3d_s2_igemm_tcgen05_vs_oracle(B, Cin, D, H, W):
     from cmf_b200 import ops
 
