@@ -267,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
                         "h2d_bytes_per_step": 2 * 3 * H_PAD * W_IMG * 4, "d2h_bytes_per_step": H_IMG * W_IMG * 4},
                 "gpu_launches": int(launches) * args.steps,
                 "launch_mode": {"timed_region": "one CUDA-graph replay per step (%d kernel nodes of libcmfb200 + ATen "
-                                                "pool/upsample/cat nodes)" % launches if use_graph else "eager launches",
+                                                "cat / zero-fill / copy nodes)" % launches if use_graph else "eager launches",
                                 "ms_per_step_eager_with_events": ms_eager / args.steps},
                 "roofline": {"kernel": k1_name + " (K1)", "bound": "hbm", "achieved": k1_gbs,
                              "peak": hbm_peak, "unit": "GB/s", "frac": (k1_gbs / hbm_peak) if k1_gbs else None,

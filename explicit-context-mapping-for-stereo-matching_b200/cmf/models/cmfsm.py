@@ -445,6 +445,10 @@ class cmfsm(nn.Module):
     def forward_row_bands(self, left, right, gather=True):
         """Sharded inference of ONE pair over all ranks (every rank passes the same images).  Returns the three
         disparity maps ([B,1,H,W] when `gather`, else this rank's rows [B,1,H/world,W])."""
+        with ops.sums_pool():
+            return self._forward_row_bands_body(left, right, gather)
+
+    def _forward_row_bands_body(self, left, right, gather):
         self._check(left, right, self.maxdisp)
         n, r = par.world(), par.rank()
         B, _, H, W = left.shape
@@ -525,6 +529,10 @@ class cmfsm(nn.Module):
         return self._forward_impl(left, right)
 
     def _forward_impl(self, left, right):
+        with ops.sums_pool():  # one zero fill per forward for all GroupNorm-statistics buffers
+            return self._forward_body(left, right)
+
+    def _forward_body(self, left, right):
         B = left.shape[0]
         left, right = left.float(), right.float()
         both = torch.cat([left, right], 0)

@@ -6,6 +6,8 @@ library raises.
 """
 import ctypes
 
+import threading
+
 import torch
 
 from . import lib as _lib
@@ -101,6 +103,47 @@ def cost_volume_concat_bwd(g, C):
 
 
 # ------------------------------------------------------------------------------------------ K2 / K3
+class _SumsPool:
+    """One zeroed fp64 buffer per forward pass from which the GroupNorm-statistics buffers [B,C,2] are sliced, instead
+    of one `torch.zeros` (= one fill launch) per conv layer (~190 launches per forward)."""
+
+    def __init__(self):
+        self.buf, self.used = None, 0
+
+    def take(self, B, C, device):
+        n = B * C * 2
+        if self.buf is None or self.buf.device != device or self.used + n > self.buf.numel():
+            self.buf = torch.zeros(max(1 << 16, 4 * n), device=device, dtype=torch.float64)
+            self.used = 0
+        out = self.buf[self.used:self.used + n].view(B, C, 2)
+        self.used += n
+        return out
+
+
+_POOL = threading.local()
+
+
+class sums_pool:
+    """Context manager: inside it `_new_sums` slices from one pooled zero buffer (re-created on every entry, so the
+    statistics of different forward passes never alias).  Without it every call allocates its own zeros."""
+
+    def __enter__(self):
+        self.prev = getattr(_POOL, "pool", None)
+        _POOL.pool = _SumsPool()
+        return self
+
+    def __exit__(self, *exc):
+        _POOL.pool = self.prev
+        return False
+
+
+def _new_sums(B, C, device):
+    pool = getattr(_POOL, "pool", None)
+    if pool is not None:
+        return pool.take(B, C, device)
+    return torch.zeros((B, C, 2), device=device, dtype=torch.float64)
+
+
 def pack_conv3d_weight(weight, transposed=False):
     """nn.Conv3d [Cout,Cin,3,3,3] (or nn.ConvTranspose3d [Cin,Cout,3,3,3]) -> packed [Cin,27,Cout]."""
     weight = weight.detach()
@@ -125,7 +168,7 @@ def conv3d_k3(x, packed, stride=1, transposed=False, want_stats=False):
     if packed.shape[0] != Cin:
         raise ValueError("weight Cin %d != input channels %d" % (packed.shape[0], Cin))
     Cout = packed.shape[2]
-    sums = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    sums = _new_sums(B, Cout, x.device) if want_stats else None
     L = _lib.load()
     if transposed:
         y = torch.empty((B, Cout, 2 * D, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
@@ -166,7 +209,7 @@ def conv2d(x, packed, ksize, stride=1, dilation=1, want_stats=False):
     pad = (ksize // 2) * dilation
     Ho = (H + 2 * pad - (ksize - 1) * dilation - 1) // stride + 1
     Wo = (W + 2 * pad - (ksize - 1) * dilation - 1) // stride + 1
-    sums = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    sums = _new_sums(B, Cout, x.device) if want_stats else None
     y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device), _timed("conv2d_fwd"):
         _lib.check(_lib.load().cmfb200_conv2d_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, H, W, ksize, stride,
@@ -204,7 +247,7 @@ def gn_stats(x):
     _req(x)
     B, C = x.shape[:2]
     spatial = x[0, 0].numel()
-    sums = torch.zeros((B, C, 2), device=x.device, dtype=torch.float64)
+    sums = _new_sums(B, C, x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().cmfb200_gn_stats(_p(x), _p(sums), B, C, spatial, _stream()), "gn_stats")
     return sums
@@ -390,7 +433,7 @@ def conv3d_igemm(x, packed, want_stats=True):
     if packed.shape[1] != NC:
         raise ValueError("weight Cin %d != input channels %d" % (packed.shape[1] * 8, Cin))
     y = torch.empty((B, Cout // 8, D, H, W, 8), device=x.device, dtype=BF16)
-    sums = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    sums = _new_sums(B, Cout, x.device) if want_stats else None
     with torch.cuda.device(x.device), _timed("conv3d_igemm_bf16_fwd"):
         _lib.check(_lib.load().cmfb200_conv3d_igemm_bf16_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W,
                                                              _stream()), "conv3d_igemm_bf16_fwd")
@@ -433,7 +476,7 @@ def deconv3d_igemm(x, packed, want_stats=True):
     B, NC, D, H, W, _ = x.shape
     Cin, Cout = NC * 8, packed.shape[2]
     y = torch.empty((B, Cout // 8, 2 * D, 2 * H, 2 * W, 8), device=x.device, dtype=BF16)
-    sums = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    sums = _new_sums(B, Cout, x.device) if want_stats else None
     with torch.cuda.device(x.device), _timed("deconv3d_igemm_bf16_fwd"):
         _lib.check(_lib.load().cmfb200_deconv3d_igemm_bf16_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W,
                                                                _stream()), "deconv3d_igemm_bf16_fwd")
@@ -456,7 +499,7 @@ def conv3d_s2_igemm(x_split, packed, want_stats=True):
     B, _, NC, Do, Ho, Wo, _ = x_split.shape
     Cin, Cout = NC * 8, packed.shape[2]
     y = torch.empty((B, Cout // 8, Do, Ho, Wo, 8), device=x_split.device, dtype=BF16)
-    sums = torch.zeros((B, Cout, 2), device=x_split.device, dtype=torch.float64) if want_stats else None
+    sums = _new_sums(B, Cout, x_split.device) if want_stats else None
     with torch.cuda.device(x_split.device), _timed("conv3d_s2_igemm_bf16_fwd"):
         _lib.check(_lib.load().cmfb200_conv3d_s2_igemm_bf16_fwd(_p(x_split), _p(packed), _p(y), _p(sums), B, Cin, Cout, Do,
                                                                 Ho, Wo, _stream()), "conv3d_s2_igemm_bf16_fwd")
