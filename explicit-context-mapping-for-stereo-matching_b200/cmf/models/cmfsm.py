@@ -160,6 +160,9 @@ class cmfsm(nn.Module):
                 for k in m.kernel_size:
                     n *= k
                 m.weight.data.normal_(0, math.sqrt(2.0 / n))
+        self._finish_init()
+
+    def _finish_init(self):
         # packed-weight cache: stable per-layer name (survives DataParallel's shallow replicas) + device
         for name, m in self.named_modules():
             if isinstance(m, (nn.Conv2d, nn.Conv3d, nn.ConvTranspose3d)):
@@ -319,6 +322,21 @@ class cmfsm(nn.Module):
         out3, _pre3, _post3 = self._hourglass_bf16(self.dres4, out2, out2_split, pre1, post2, cost0, False)
         return (self._classify_bf16(self.classif1, out1), self._classify_bf16(self.classif2, out2),
                 self._classify_bf16(self.classif3, out3))
+
+    def _aggregate_fp32(self, lfeat, rfeat, D):
+        """Inference-only fp32 aggregation: cost volume -> dres0/1 -> three hourglasses -> raw classifier volumes."""
+        cost = ops.cost_volume_concat(lfeat, rfeat, D)
+        cost0 = self._cg(self.dres0[0], cost, relu=True)
+        del cost
+        cost0 = self._cg(self.dres0[2], cost0, relu=True)
+        t = self._cg(self.dres1[0], cost0, relu=True)
+        cost0 = self._cg(self.dres1[2], t, residual=cost0)
+        del t
+        out1, pre1, post1 = self._hourglass(self.dres2, cost0, None, None, cost0)
+        out2, _pre2, post2 = self._hourglass(self.dres3, out1, pre1, post1, cost0)
+        out3, _pre3, _post3 = self._hourglass(self.dres4, out2, pre1, post2, cost0)
+        return (self._classify(self.classif1, out1), self._classify(self.classif2, out2),
+                self._classify(self.classif3, out3))
 
     def _hourglass(self, hg, x, presqu, postsqu, out_residual):
         # reference hourglass.forward, cmfsm.py:283-303 (+ the caller's `out + cost0`, :687,690,693)

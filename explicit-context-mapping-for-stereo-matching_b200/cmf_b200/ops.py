@@ -521,3 +521,53 @@ def gn_apply_c8(x, sums, gamma, beta, residual=None, relu=False, out=None, want_
                                                         _p(split), B, NC * 8, groups, D, H, W, eps, int(relu),
                                                         _stream()), "gn_apply_c8_bf16")
     return (y, split) if want_split else y
+
+
+# ---- cmfsm_sub_8 variant ---------------------------------------------------------------------------
+def ctxmap_weights5(lr, hr, w0, w1, w2, w3):
+    """six_related_context_mapping (reference-image half, cmf/models/cmfsm_sub_8.py:440-572):
+    [B,32,h,w],[B,32,H,W] -> [B,5,H,W] = softmax(logits)*logits, neighbours c,r,l,t,b."""
+    ws = [w.detach().reshape(w.shape[0], w.shape[1]).contiguous() for w in (w0, w1, w2, w3)]
+    _req(lr, hr, *ws)
+    B, C, h, w = lr.shape
+    H, W = hr.shape[2:]
+    if C != 32 or hr.shape[1] != 32 or tuple(ws[0].shape) != (32, 66):
+        raise ValueError("context mapping expects 32-channel features and a 66-input similarity MLP")
+    scale = W // w
+    if H != h * scale or W != w * scale:
+        raise ValueError("hr %dx%d is not an integer multiple of lr %dx%d" % (H, W, h, w))
+    out = torch.empty((B, 5, H, W), device=lr.device, dtype=torch.float32)
+    with torch.cuda.device(lr.device), _timed("ctxmap_weights5_fwd"):
+        _lib.check(_lib.load().cmfb200_ctxmap_weights5_fwd(_p(lr), _p(hr), _p(ws[0]), _p(ws[1]), _p(ws[2]), _p(ws[3]),
+                                                           _p(out), B, h, w, scale, _stream()), "ctxmap_weights5_fwd")
+    return out
+
+
+def softargmin_ctxmap5(c1, c2, c3, weights5, scale):
+    """cmf/models/cmfsm_sub_8.py:757-802.  c_i [B,D,h,w] (independent), weights5 [B,5,H,W] -> 3 x [B,1,H,W]."""
+    _req(c1, c2, c3, weights5)
+    B, D, h, w = c1.shape
+    H, W = h * scale, w * scale
+    if tuple(weights5.shape) != (B, 5, H, W):
+        raise ValueError("weights5 shape %s != %s" % (tuple(weights5.shape), (B, 5, H, W)))
+    outs = [torch.empty((B, 1, H, W), device=c1.device, dtype=torch.float32) for _ in range(3)]
+    with torch.cuda.device(c1.device), _timed("softargmin_ctxmap5_fwd"):
+        _lib.check(_lib.load().cmfb200_softargmin_ctxmap5_fwd(_p(c1), _p(c2), _p(c3), _p(weights5), _p(outs[0]),
+                                                              _p(outs[1]), _p(outs[2]), None, B, D, h, w, scale,
+                                                              _stream()), "softargmin_ctxmap5_fwd")
+    return tuple(outs)
+
+
+def spp_upsample_concat_sized(raw, skip, branches):
+    """cat([raw, skip, up(b) for b in branches], 1) for four branch maps of arbitrary size (cmfsm_sub_8)."""
+    _req(raw, skip, *branches)
+    B, _, H, W = skip.shape
+    if raw.shape[1] != 64 or skip.shape[1] != 128 or len(branches) != 4 or any(t.shape[1] != 32 for t in branches):
+        raise ValueError("spp_upsample_concat_sized expects 64 + 128 + 4 x 32 channels")
+    cat = torch.empty((B, 320, H, W), device=skip.device, dtype=torch.float32)
+    sizes = [int(v) for t in branches for v in t.shape[2:]]
+    with torch.cuda.device(skip.device), _timed("spp_upsample_concat_fwd"):
+        _lib.check(_lib.load().cmfb200_spp_upsample_concat_sized_fwd(_p(raw), _p(skip), *[_p(t) for t in branches], _p(cat),
+                                                                     B, H, W, *sizes, _stream()),
+                   "spp_upsample_concat_sized_fwd")
+    return cat

@@ -435,7 +435,7 @@ static int dispatch_conv2d(const float* x, const float* wp, float* y, double* gn
         CMF_REQUIRE(false, "conv2d: Cin=3 only for the 3x3 s1 stem conv with Cout=32");
     }
     CMF_REQUIRE(Cin % 8 == 0, "conv2d: Cin=%d must be 3 or a multiple of 8", Cin);
-    if constexpr (KS == 3 && S == 1) {  // the bulk of the MACs: two output rows per thread
+    if constexpr (KS == 3 && S == 1 && DIL <= 2) {  // the bulk of the MACs: two output rows per thread
         if (Cout == 32) return launch_conv2d_r2<DIL, 32, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st);
         if (Cout % 64 == 0) return launch_conv2d_r2<DIL, 64, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st);
     }
@@ -467,6 +467,7 @@ extern "C" int cmfb200_conv2d_fwd(const float* x, const float* packed_w, float* 
     if (ksize == 3 && stride == 1 && dilation == 1) return dispatch_conv2d<3, 1, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
     if (ksize == 3 && stride == 2 && dilation == 1) return dispatch_conv2d<3, 2, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
     if (ksize == 3 && stride == 1 && dilation == 2) return dispatch_conv2d<3, 1, 2>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
+    if (ksize == 3 && stride == 1 && dilation == 4) return dispatch_conv2d<3, 1, 4>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
     if (ksize == 1 && stride == 1 && dilation == 1) return dispatch_conv2d<1, 1, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
     if (ksize == 1 && stride == 2 && dilation == 1) return dispatch_conv2d<1, 2, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
     CMF_REQUIRE(false, "conv2d_fwd: unsupported (ksize=%d, stride=%d, dilation=%d)", ksize, stride, dilation);

@@ -28,10 +28,37 @@ __device__ __forceinline__ float pos_code(int kind, int i, int s) {
     return (float)(i < half ? i - half : i - half + 1);
 }
 
+// Neighbour sets.  VARIANT 0 = cmfsm (eight_related_context_mapping, cmfsm.py:443-593): nine neighbours in the order
+// c,l,r,t,b,lt,rt,lb,rb, logit -100 where the neighbour cell is outside the image, output = softmax.
+// VARIANT 1 = cmfsm_sub_8 (six_related_context_mapping, cmfsm_sub_8.py:440-572, reference-image half): five
+// neighbours c,r,l,t,b, a trailing LeakyReLU on the MLP output, logit 0 outside the image, output = softmax * logit.
+template <int VARIANT>
+struct K5Set;
+template <>
+struct K5Set<0> {
+    static constexpr int NK = 9;
+    __device__ static int dy(int k) { return (k == 3 || k == 5 || k == 6) ? -1 : ((k == 4 || k == 7 || k == 8) ? 1 : 0); }
+    __device__ static int dx(int k) { return (k == 1 || k == 5 || k == 7) ? -1 : ((k == 2 || k == 6 || k == 8) ? 1 : 0); }
+    // code kinds per SURVEY.md A.3 (the diagonals reuse the axis encodings, cmfsm.py:459-462)
+    __device__ static int kx(int k) { return (k == 1 || k == 5) ? 2 : ((k == 2 || k == 6) ? 1 : 0); }
+    __device__ static int ky(int k) { return (k == 3 || k == 7) ? 2 : ((k == 4 || k == 8) ? 1 : 0); }
+};
+template <>
+struct K5Set<1> {
+    static constexpr int NK = 5;
+    __device__ static int dy(int k) { return k == 3 ? -1 : (k == 4 ? 1 : 0); }
+    __device__ static int dx(int k) { return k == 1 ? 1 : (k == 2 ? -1 : 0); }
+    __device__ static int kx(int k) { return k == 1 ? 2 : (k == 2 ? 1 : 0); }  // right: dec, left: inc (sub8.py:497,516)
+    __device__ static int ky(int k) { return k == 3 ? 2 : (k == 4 ? 1 : 0); }  // top: dec, bottom: inc (sub8.py:534,546)
+};
+
+template <int VARIANT>
 __global__ void __launch_bounds__(kK5Threads) ctxmap_weights_kernel(
     const float* __restrict__ lr, const float* __restrict__ hr, const float* __restrict__ w0,
     const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3,
     float* __restrict__ out, int h, int w, int scale, int vy0, int vy1) {
+    using NS = K5Set<VARIANT>;
+    constexpr int NK = NS::NK;
     __shared__ __align__(16) float sW0lr[32][32];  // [in][out]
     __shared__ __align__(16) float sW0hr[32][32];  // [in][out]
     __shared__ __align__(16) float sW0c[2][32];    // code channels 64,65
@@ -40,7 +67,7 @@ __global__ void __launch_bounds__(kK5Threads) ctxmap_weights_kernel(
     __shared__ __align__(16) float sW3[8];
     __shared__ __align__(16) float sLr[32][kK5Halo];
     __shared__ __align__(16) float sAlr[kK5Halo][kPad];
-    __shared__ float sLogit[9][kK5Threads];
+    __shared__ float sLogit[NK][kK5Threads];
 
     const int tid = threadIdx.x;
     const int b = blockIdx.z;
@@ -106,15 +133,11 @@ __global__ void __launch_bounds__(kK5Threads) ctxmap_weights_kernel(
             }
         }
 
-        // neighbours in the reference order c,l,r,t,b,lt,rt,lb,rb; code kinds per SURVEY.md A.3
-        // (the diagonals reuse the axis encodings, cmfsm.py:459-462)
-        for (int k = 0; k < 9; ++k) {
-            const int dy = (k == 3 || k == 5 || k == 6) ? -1 : ((k == 4 || k == 7 || k == 8) ? 1 : 0);
-            const int dx = (k == 1 || k == 5 || k == 7) ? -1 : ((k == 2 || k == 6 || k == 8) ? 1 : 0);
-            const int kx = (k == 1 || k == 5) ? 2 : ((k == 2 || k == 6) ? 1 : 0);  // code over x (channel 64)
-            const int ky = (k == 3 || k == 7) ? 2 : ((k == 4 || k == 8) ? 1 : 0);  // code over y (channel 65)
+        for (int k = 0; k < NK; ++k) {
+            const int dy = NS::dy(k), dx = NS::dx(k);
+            const int kx = NS::kx(k), ky = NS::ky(k);  // code over x (channel 64) / over y (channel 65)
             const int ny = cy + dy, nx = cx + dx;
-            float logit = -100.0f;
+            float logit = VARIANT == 0 ? -100.0f : 0.0f;
             if (ny >= vy0 && ny < vy1 && nx >= 0 && nx < w) {  // [vy0,vy1): cell rows inside the IMAGE (row bands pass halos)
                 const float p0 = pos_code(kx, px, scale), p1 = pos_code(ky, py, scale);
                 const float* alr = &sAlr[(ly + dy) * kK5HaloX + lx + dx][0];
@@ -155,21 +178,22 @@ __global__ void __launch_bounds__(kK5Threads) ctxmap_weights_kernel(
                 logit = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) logit = fmaf(sW3[i], leaky(h2[i]), logit);
+                if (VARIANT == 1) logit = leaky(logit);
             }
             sLogit[k][tid] = logit;
         }
         float m = sLogit[0][tid];
 #pragma unroll
-        for (int k = 1; k < 9; ++k) m = fmaxf(m, sLogit[k][tid]);
-        float e[9], s = 0.f;
+        for (int k = 1; k < NK; ++k) m = fmaxf(m, sLogit[k][tid]);
+        float e[NK], s = 0.f;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
+        for (int k = 0; k < NK; ++k) {
             e[k] = expf(sLogit[k][tid] - m);
             s += e[k];
         }
-        float* po = out + (size_t)b * 9 * hplane + (size_t)y * W + x;
+        float* po = out + (size_t)b * NK * hplane + (size_t)y * W + x;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) po[k * hplane] = e[k] / s;
+        for (int k = 0; k < NK; ++k) po[k * hplane] = VARIANT == 0 ? e[k] / s : (e[k] / s) * sLogit[k][tid];
     }
 }
 
@@ -531,9 +555,23 @@ extern "C" int cmfb200_ctxmap_weights_fwd(const float* lr, const float* hr, cons
     CMF_REQUIRE(B <= 65535, "ctxmap_weights_fwd: B exceeds grid limit");
     dim3 grid((unsigned)cdiv(w, kK5CellsX), (unsigned)cdiv(h, kK5CellsY), (unsigned)B);
     CMF_REQUIRE(valid_y0 >= 0 && valid_y1 <= h && valid_y0 < valid_y1, "ctxmap_weights_fwd: bad valid row range [%d,%d) for h=%d", valid_y0, valid_y1, h);
-    ctxmap_weights_kernel<<<grid, kK5Threads, 0, (cudaStream_t)stream>>>(lr, hr, w0, w1, w2, w3, weights9, h, w, scale,
-                                                                          valid_y0, valid_y1);
+    ctxmap_weights_kernel<0><<<grid, kK5Threads, 0, (cudaStream_t)stream>>>(lr, hr, w0, w1, w2, w3, weights9, h, w, scale,
+                                                                             valid_y0, valid_y1);
     CMF_LAUNCH_CHECK("ctxmap_weights_kernel");
+    return CMFB200_OK;
+}
+
+extern "C" int cmfb200_ctxmap_weights5_fwd(const float* lr, const float* hr, const float* w0, const float* w1,
+                                           const float* w2, const float* w3, float* weights5, int B, int h, int w,
+                                           int scale, void* stream) {
+    CMF_REQUIRE(lr && hr && w0 && w1 && w2 && w3 && weights5, "ctxmap_weights5_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && h > 0 && w > 0, "ctxmap_weights5_fwd: non-positive dimension");
+    CMF_REQUIRE(scale >= 2 && scale % 2 == 0, "ctxmap_weights5_fwd: odd scale %d (the reference exit()s)", scale);
+    CMF_REQUIRE(B <= 65535, "ctxmap_weights5_fwd: B exceeds grid limit");
+    dim3 grid((unsigned)cdiv(w, kK5CellsX), (unsigned)cdiv(h, kK5CellsY), (unsigned)B);
+    ctxmap_weights_kernel<1><<<grid, kK5Threads, 0, (cudaStream_t)stream>>>(lr, hr, w0, w1, w2, w3, weights5, h, w, scale,
+                                                                             0, h);
+    CMF_LAUNCH_CHECK("ctxmap_weights_kernel<1>");
     return CMFB200_OK;
 }
 

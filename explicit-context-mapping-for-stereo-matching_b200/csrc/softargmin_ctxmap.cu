@@ -38,6 +38,10 @@ struct Online {
     __device__ __forceinline__ float result() const { return t / s; }
 };
 
+// VARIANT 0 = cmfsm: cumulative costs, nine weights in the order c,l,r,t,b,lt,rt,lb,rb (cmfsm.py:703-769).
+// VARIANT 1 = cmfsm_sub_8: three independent regressions (no cumulative sums), five weights in the order c,r,l,t,b
+// (cmfsm_sub_8.py:757-802).
+template <int VARIANT>
 __global__ void __launch_bounds__(kK4Threads) softargmin_ctxmap_kernel(
     const float* __restrict__ c1, const float* __restrict__ c2, const float* __restrict__ c3,
     const float* __restrict__ wts, float* __restrict__ out1, float* __restrict__ out2, float* __restrict__ out3,
@@ -60,8 +64,8 @@ __global__ void __launch_bounds__(kK4Threads) softargmin_ctxmap_kernel(
             o3.init();
             for (int d = 0; d < D; ++d) {
                 const float v1 = c1[off + d * plane];
-                const float v2 = __fadd_rn(c2[off + d * plane], v1);
-                const float v3 = __fadd_rn(c3[off + d * plane], v2);
+                const float v2 = VARIANT == 0 ? __fadd_rn(c2[off + d * plane], v1) : c2[off + d * plane];
+                const float v3 = VARIANT == 0 ? __fadd_rn(c3[off + d * plane], v2) : c3[off + d * plane];
                 const float fd = (float)d;
                 o1.push(v1, fd);
                 o2.push(v2, fd);
@@ -88,18 +92,19 @@ __global__ void __launch_bounds__(kK4Threads) softargmin_ctxmap_kernel(
     const size_t oplane = (size_t)H * W;
     const int tile_h = kTCY * scale, tile_w4 = (kTCX * scale) >> 2;
     const float fs = (float)scale;
+    constexpr int NK = VARIANT == 0 ? 9 : 5;
     const int dys[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
-    const int dxs[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+    const int dxs[9] = {0, VARIANT == 0 ? -1 : 1, VARIANT == 0 ? 1 : -1, 0, 0, -1, 1, -1, 1};
     for (int i = threadIdx.x; i < tile_h * tile_w4; i += kK4Threads) {
         const int ty = i / tile_w4, tx = (i - ty * tile_w4) << 2;
         const int y = cy0 * scale + ty, x = cx0 * scale + tx;
         if (y >= H || x >= W) continue;
         const int ly = ty / scale + 1, lx = tx / scale + 1;  // halo coordinates of the centre cell
         const int cy = cy0 + ly - 1, cx = cx0 + lx - 1;
-        const float* wp = wts + (size_t)b * 9 * oplane + (size_t)y * W + x;
+        const float* wp = wts + (size_t)b * NK * oplane + (size_t)y * W + x;
         float4 acc[3];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
+        for (int k = 0; k < NK; ++k) {
             const int ny = cy + dys[k], nx = cx + dxs[k];
             if (ny < 0 || ny >= h || nx < 0 || nx >= w) continue;  // the reference adds nothing there
             const float4 wk = ld_streaming_f4(wp + k * oplane);
@@ -136,8 +141,22 @@ extern "C" int cmfb200_softargmin_ctxmap_fwd(const float* c1, const float* c2, c
     CMF_REQUIRE(scale >= 4 && scale % 4 == 0, "softargmin_ctxmap_fwd: scale=%d must be a positive multiple of 4", scale);
     CMF_REQUIRE(B <= 65535, "softargmin_ctxmap_fwd: B exceeds grid limit");
     dim3 grid((unsigned)cdiv(w, kTCX), (unsigned)cdiv(h, kTCY), (unsigned)B);
-    softargmin_ctxmap_kernel<<<grid, kK4Threads, 0, (cudaStream_t)stream>>>(c1, c2, c3, weights9, out1, out2, out3,
-                                                                             pred_lr, B, D, h, w, scale);
+    softargmin_ctxmap_kernel<0><<<grid, kK4Threads, 0, (cudaStream_t)stream>>>(c1, c2, c3, weights9, out1, out2, out3,
+                                                                                pred_lr, B, D, h, w, scale);
     CMF_LAUNCH_CHECK("softargmin_ctxmap_kernel");
+    return CMFB200_OK;
+}
+
+extern "C" int cmfb200_softargmin_ctxmap5_fwd(const float* c1, const float* c2, const float* c3, const float* weights5,
+                                              float* out1, float* out2, float* out3, float* pred_lr, int B, int D, int h,
+                                              int w, int scale, void* stream) {
+    CMF_REQUIRE(c1 && c2 && c3 && weights5 && out1 && out2 && out3, "softargmin_ctxmap5_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0, "softargmin_ctxmap5_fwd: non-positive dimension");
+    CMF_REQUIRE(scale >= 4 && scale % 4 == 0, "softargmin_ctxmap5_fwd: scale=%d must be a positive multiple of 4", scale);
+    CMF_REQUIRE(B <= 65535, "softargmin_ctxmap5_fwd: B exceeds grid limit");
+    dim3 grid((unsigned)cdiv(w, kTCX), (unsigned)cdiv(h, kTCY), (unsigned)B);
+    softargmin_ctxmap_kernel<1><<<grid, kK4Threads, 0, (cudaStream_t)stream>>>(c1, c2, c3, weights5, out1, out2, out3,
+                                                                                pred_lr, B, D, h, w, scale);
+    CMF_LAUNCH_CHECK("softargmin_ctxmap_kernel<1>");
     return CMFB200_OK;
 }

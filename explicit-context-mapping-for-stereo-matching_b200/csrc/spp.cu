@@ -119,3 +119,20 @@ extern "C" int cmfb200_spp_upsample_concat_fwd(const float* raw, const float* sk
     CMF_LAUNCH_CHECK("spp_upsample_concat_kernel");
     return CMFB200_OK;
 }
+
+// Same kernel with explicit branch-map sizes (cmfsm_sub_8: pools 8/16/32/4 on the 1/8-resolution map,
+// cmfsm_sub_8.py:152-170, 207-231): cat = [raw(64) | skip(128) | up(ba) | up(bb) | up(bc) | up(bd)].
+extern "C" int cmfb200_spp_upsample_concat_sized_fwd(const float* raw, const float* skip, const float* ba,
+                                                     const float* bb, const float* bc, const float* bd, float* cat,
+                                                     int B, int H, int W, int ha, int wa, int hb, int wb, int hc, int wc,
+                                                     int hd, int wd, void* stream) {
+    CMF_REQUIRE(raw && skip && ba && bb && bc && bd && cat, "spp_upsample_concat_sized_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "spp_upsample_concat_sized_fwd: bad shape");
+    CMF_REQUIRE(ha > 0 && wa > 0 && hb > 0 && wb > 0 && hc > 0 && wc > 0 && hd > 0 && wd > 0,
+                "spp_upsample_concat_sized_fwd: empty branch map");
+    const BranchMap ma{ba, ha, wa}, mb{bb, hb, wb}, mc{bc, hc, wc}, md{bd, hd, wd};
+    dim3 grid((unsigned)min((long long)16, cdiv((long long)H * W, 1024)), 320, (unsigned)B);
+    spp_upsample_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, skip, ma, mb, mc, md, cat, H, W, H, 0);
+    CMF_LAUNCH_CHECK("spp_upsample_concat_kernel");
+    return CMFB200_OK;
+}

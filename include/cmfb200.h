@@ -119,7 +119,7 @@ int cmfb200_f32_to_c8_bf16(const float* x, void* y_c8, int B, int C, long long s
  * Replace nn.Conv2d(bias=False) in convbn / BasicBlock / feature_extraction (cmfsm.py:36-46, 61-85, 126-236).
  * Packed weights wp[Cin][k*k][Cout] from nn.Conv2d's [Cout,Cin,k,k].
  * x: [B,Cin,H,W] NCHW; y: [B,Cout,Ho,Wo]; padding = (k/2)*dilation (what convbn() computes);
- * (ksize,stride,dilation) in {(3,1,1),(3,2,1),(3,1,2),(1,1,1),(1,2,1)}; Cin = 3 (stem, Cout 32) or a multiple
+ * (ksize,stride,dilation) in {(3,1,1),(3,2,1),(3,1,2),(3,1,4),(1,1,1),(1,2,1)}; Cin = 3 (stem, Cout 32) or a multiple
  * of 8; Cout = 32 or a multiple of 64.  gn_sums: same contract as cmfb200_conv3d_k3_fwd. */
 int cmfb200_pack_conv2d_weight(const float* weight, float* packed, int Cout, int Cin, int ksize, void* stream);
 int cmfb200_conv2d_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
@@ -135,6 +135,11 @@ int cmfb200_spp_pool_fwd(const float* x, float* p8, float* p16, float* p32, floa
 int cmfb200_spp_upsample_concat_fwd(const float* raw, const float* skip, const float* b4, const float* b3,
                                     const float* b2, const float* b1, float* cat, int B, int H, int W,
                                     int H_full, int y_off, void* stream);
+/* The same op with explicit branch-map sizes [B,32,h*,w*] (cmfsm_sub_8: SPP pools 8/16/32/4 at 1/8 resolution,
+ * cmfsm_sub_8.py:152-170, 207-231): cat = [raw | skip | up(ba) | up(bb) | up(bc) | up(bd)]. */
+int cmfb200_spp_upsample_concat_sized_fwd(const float* raw, const float* skip, const float* ba, const float* bb,
+                                          const float* bc, const float* bd, float* cat, int B, int H, int W, int ha,
+                                          int wa, int hb, int wb, int hc, int wc, int hd, int wd, void* stream);
 
 /* ---- K3: GroupNorm (+ residual add) (+ ReLU) ---------------------------------------------------
  * Replaces nn.GroupNorm(32,C) (cmfsm.py:58,269,280), the residual adds (:288,297,299,685,687,690,693)
@@ -175,6 +180,11 @@ int cmfb200_ctxmap_weights_fwd(const float* lr, const float* hr, const float* w0
 int cmfb200_ctxmap_weights_bwd(const float* lr, const float* hr, const float* w0, const float* w1, const float* w2,
                                const float* w3, const float* weights9, const float* grad_weights9, float* d_ahr,
                                float* d_alr, float* d_wbuf, int B, int h, int w, int scale, void* stream);
+/* cmfsm_sub_8 variant (six_related_context_mapping, cmfsm_sub_8.py:440-572, reference-image half): five neighbours
+ * centre, right, left, top, bottom; the MLP ends in a LeakyReLU; logit 0 where the neighbour cell is outside the
+ * image; weights5 [B,5,H,W] = softmax(logits) * logits (NOT normalised).  Any even scale. */
+int cmfb200_ctxmap_weights5_fwd(const float* lr, const float* hr, const float* w0, const float* w1, const float* w2,
+                                const float* w3, float* weights5, int B, int h, int w, int scale, void* stream);
 
 /* ---- K4: soft-argmin + x scale upsample + 9-neighbour context mapping ---------------------------
  * Replaces cmfsm.py:703-769 (3x softmax, disparityregression :111-123, ~60 slice kernels).
@@ -185,6 +195,11 @@ int cmfb200_ctxmap_weights_bwd(const float* lr, const float* hr, const float* w0
 int cmfb200_softargmin_ctxmap_fwd(const float* c1, const float* c2, const float* c3,
                                   const float* weights9, float* out1, float* out2, float* out3,
                                   float* pred_lr, int B, int D, int h, int w, int scale, void* stream);
+/* cmfsm_sub_8 variant (cmfsm_sub_8.py:757-802): the three volumes are regressed independently (no cumulative sums)
+ * and mapped with the five weights of cmfb200_ctxmap_weights5_fwd (order c,r,l,t,b). */
+int cmfb200_softargmin_ctxmap5_fwd(const float* c1, const float* c2, const float* c3, const float* weights5,
+                                   float* out1, float* out2, float* out3, float* pred_lr, int B, int D, int h, int w,
+                                   int scale, void* stream);
 
 #ifdef __cplusplus
 }

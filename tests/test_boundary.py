@@ -18,8 +18,10 @@ def test_registry_names():
 
     m = get_model("cmfsm")
     assert type(m).__name__ == "cmfsm" and m.maxdisp == 192
+    m8 = get_model("cmfsm_sub_8")
+    assert type(m8).__name__ == "cmfsm_sub_8" and m8.maxdisp == 192
     with pytest.raises(NotImplementedError):
-        get_model("cmfsm_sub_8")
+        get_model("cmfsm_sub_16")
     with pytest.raises(KeyError):
         get_model("no_such_model")
 
@@ -33,6 +35,21 @@ def test_state_dict_contract_and_seeded_init(golden_dir):
     sd = cmfsm(maxdisp=192).state_dict()
     assert len(sd) == contract["n_tensors"] == 272
     assert sum(v.numel() for v in sd.values()) == contract["n_params"] == 5255368
+    for (k, v), t in zip(sd.items(), contract["tensors"]):
+        assert k == t["key"] and list(v.shape) == t["shape"]
+        assert abs(float(v.double().sum()) - t["sum"]) < 1e-9, k
+        assert abs(float(v.double().abs().sum()) - t["abssum"]) < 1e-9, k
+
+
+def test_sub8_state_dict_contract_and_seeded_init(golden_dir):
+    """The 1/8-resolution variant: keys, order, shapes and seed-0 values equal the reference's cmfsm_sub_8."""
+    from cmf.models import get_model
+
+    contract = json.load(open(os.path.join(golden_dir, "cmfsm_sub8_state_dict.json")))
+    torch.manual_seed(contract["weight_seed"])
+    sd = get_model("cmfsm_sub_8").state_dict()
+    assert len(sd) == contract["n_tensors"] == 276
+    assert sum(v.numel() for v in sd.values()) == contract["n_params"]
     for (k, v), t in zip(sd.items(), contract["tensors"]):
         assert k == t["key"] and list(v.shape) == t["shape"]
         assert abs(float(v.double().sum()) - t["sum"]) < 1e-9, k

@@ -496,3 +496,55 @@ def test_conv3d_cout1_backward_vs_autograd(B, D, H, W):
     want = torch.autograd.grad(F.conv3d(xr, wr, None, 1, 1), [xr, wr], g.double())
     dx, dw = ops.conv3d_cout1_backward(x.to(DEV), wgt.to(DEV), g.to(DEV))
     assert _rel_l2(dx.cpu(), want[0]) < 1e-5 and _rel_l2(dw.cpu(), want[1]) < 1e-5
+
+
+# ---- cmfsm_sub_8 variant kernels ------------------------------------------------------------------------
+def _sub8_sd(seed):
+    proto = {"mapping_matrix.similarity1.conv0.weight": torch.empty(32, 66, 1, 1),
+             "mapping_matrix.similarity1.conv1.weight": torch.empty(16, 32, 1, 1),
+             "mapping_matrix.similarity1.conv2.weight": torch.empty(8, 16, 1, 1),
+             "mapping_matrix.similarity1.conv3.weight": torch.empty(1, 8, 1, 1)}
+    return gc.seeded_weights(proto, seed)
+
+
+@pytest.mark.parametrize("B,h,w,scale", [(1, 3, 5, 8), (2, 6, 10, 8), (1, 4, 9, 4)])
+def test_k5_five_neighbour_variant_vs_oracle(B, h, w, scale):
+    """cmfb200_ctxmap_weights5_fwd vs the restatement of six_related_context_mapping (pinned to the reference)."""
+    import cmfsm_sub8_oracle as orc8
+    from cmf_b200 import ops
+
+    sd = _sub8_sd(150)
+    lr, hr = _rand(B, 32, h, w, seed=151), _rand(B, 32, h * scale, w * scale, seed=152)
+    want = orc8.context_mapping_weights5({k: v.double() for k, v in sd.items()}, lr.double(), hr.double())
+    got = ops.ctxmap_weights5(lr.to(DEV), hr.to(DEV), *[sd["mapping_matrix.similarity1.conv%d.weight" % i].to(DEV) for i in range(4)])
+    assert got.shape == want.shape
+    torch.testing.assert_close(got.cpu().double(), want, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,D,h,w,scale", [(1, 6, 5, 7, 8), (2, 24, 9, 18, 8), (1, 12, 8, 16, 4)])
+def test_k4_five_neighbour_variant_vs_oracle(B, D, h, w, scale):
+    import cmfsm_sub8_oracle as orc8
+    from cmf_b200 import ops
+
+    cs = [_rand(B, D, h, w, seed=160 + i) * 3 for i in range(3)]
+    w5 = _rand(B, 5, h * scale, w * scale, seed=164)
+    want = orc8.softargmin_ctxmap5(*[c.double() for c in cs], w5.double(), scale)
+    got = ops.softargmin_ctxmap5(*[c.to(DEV) for c in cs], w5.to(DEV), scale)
+    for a, b in zip(got, want):
+        torch.testing.assert_close(a.cpu().double(), b, rtol=1e-5, atol=1e-4)
+
+
+def test_conv2d_dilation4_and_sized_spp_concat():
+    from cmf_b200 import ops
+
+    x = _rand(2, 128, 20, 36, seed=170)
+    wgt = _rand(128, 128, 3, 3, seed=171) * (2.0 / (9 * 128)) ** 0.5
+    want = F.conv2d(x.double(), wgt.double(), None, 1, 4, 4)
+    y, sums = ops.conv2d(x.to(DEV), ops.pack_conv2d_weight(wgt.to(DEV)), 3, 1, 4, want_stats=True)
+    assert _rel_l2(y, want) < 1e-5
+    torch.testing.assert_close(sums.cpu()[..., 0], want.sum((2, 3)), rtol=1e-6, atol=1e-4)
+    raw, skip = _rand(1, 64, 32, 64, seed=172), _rand(1, 128, 32, 64, seed=173)
+    br = [_rand(1, 32, 32 // k, 64 // k, seed=174 + i) for i, k in enumerate((8, 16, 32, 4))]
+    want = torch.cat([raw, skip] + [F.interpolate(b, (32, 64), mode="bilinear", align_corners=False) for b in br], 1)
+    got = ops.spp_upsample_concat_sized(raw.to(DEV), skip.to(DEV), [b.to(DEV) for b in br])
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-6)

@@ -180,3 +180,37 @@ def test_training_gradients_match_fp64_oracle():
                 "dres0.0.0.weight", "dres2.conv5.0.weight", "classif3.2.weight"):
         assert worst[key] < 0.1, (key, worst[key])
     assert sorted(worst.values())[len(worst) // 2] < 0.05  # median over all 272 tensors
+
+
+def test_sub8_variant_matches_fp64_oracle():
+    """cmfsm_sub_8 (the 1/8-resolution "downsample config") on the CUDA kernels vs its fp64 CPU oracle, which
+    oracle/gen_golden_sub8.py pinned to the real reference module.  Random-init outputs of this variant are large
+    (un-normalised softmax*logit weights), so the gate is relative: ours-vs-fp64 <= 2x the distance of the oracle's
+    own fp32 run from fp64 (+ a floor), the same rule as for cmfsm."""
+    import cmfsm_sub8_oracle as orc8
+    from cmf.models import get_model
+
+    torch.manual_seed(gc.WEIGHT_SEED)
+    net = get_model("cmfsm_sub_8").to(DEV).eval()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    left, right = gc.seeded_pair(1, 256, 512, seed=5)
+    with torch.no_grad():
+        ours = net(left.to(DEV), right.to(DEV))
+    ref32 = orc8.forward(sd, left, right, 192)
+    ref64 = orc8.forward({k: v.double() for k, v in sd.items()}, left.double(), right.double(), 192)
+    for i, (a, r32, r64) in enumerate(zip(ours, ref32, ref64), 1):
+        assert tuple(a.shape) == (1, 1, 256, 512)
+        scale = float(r64.abs().mean())
+        d_ours = (a.cpu().double() - r64).abs()
+        d_ref = (r32.double() - r64).abs()
+        print("sub_8 pred%d: |mean| %.1f  ours-vs-fp64 max %.3e mean %.3e ; ref32-vs-fp64 max %.3e mean %.3e"
+              % (i, scale, d_ours.max(), d_ours.mean(), d_ref.max(), d_ref.mean()))
+        assert float(d_ours.mean()) <= 2 * float(d_ref.mean()) + 1e-5 * scale
+        assert float(d_ours.max()) <= 3 * float(d_ref.max()) + 1e-4 * scale
+    net.aggregation = "bf16"
+    with torch.no_grad():
+        b = net(left.to(DEV), right.to(DEV))
+    for a, c in zip(ours, b):
+        rel = float((a - c).norm() / a.norm())
+        print("sub_8 bf16 aggregation vs fp32: rel-L2 %.3e" % rel)
+        assert torch.isfinite(c).all() and rel < 0.2

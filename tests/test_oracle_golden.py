@@ -94,6 +94,27 @@ def test_full_forward_c1_against_reference(golden_dir):
     torch.testing.assert_close(stages["L"][0, ::4, ::4, ::4], g["L_sub"], rtol=1e-3, atol=1e-4)
 
 
+def test_sub8_full_forward_against_reference(golden_dir):
+    """cmfsm_sub_8 oracle at 256x512 vs the outputs of the real reference module (oracle/gen_golden_sub8.py asserted
+    exact equality when the fixtures were written; thread counts move fp32 results a little).  The variant's
+    un-normalised softmax*logit weights make random-init outputs large, so the gates are relative."""
+    import cmfsm_sub8_oracle as orc8
+    from cmf.models import get_model
+
+    g = _npz(golden_dir, "cmfsm_sub8_c1.npz")
+    torch.manual_seed(gc.WEIGHT_SEED)
+    sd = get_model("cmfsm_sub_8").state_dict()
+    left, right = gc.seeded_pair(1, 256, 512)
+    stages = {}
+    p1, p2, p3 = orc8.forward(sd, left, right, 192, stages)
+    for got, key in ((p1, "pred1_sub"), (p2, "pred2_sub"), (p3, "pred3_sub")):
+        want = g[key]
+        rel = float((got[0, 0, ::4, ::4] - want).norm() / want.norm())
+        assert rel < 1e-3, (key, rel)
+    torch.testing.assert_close(stages["weights"][0, :, ::8, ::8], g["weights_sub"], rtol=2e-3, atol=1e-3)
+    torch.testing.assert_close(stages["L"][0, ::4, ::2, ::2], g["L_sub"], rtol=1e-3, atol=1e-4)
+
+
 def test_shape_validation():
     import pytest
 

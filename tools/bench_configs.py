@@ -2,6 +2,7 @@
   C1  256x512  B1  fp32           (the reference's CPU-runnable case)
   C4  384x1248 B16 bf16 aggregation (KITTI-2015 shape)
   C5  2048x3072 B1 maxdisp 384 fp32 / bf16 (un-sharded; row bands: tools/check_row_bands.py)
+  C2-sub_8  576x960 B1, the cmfsm_sub_8 variant
 Prints one JSON line per config."""
 import json
 import os
@@ -12,11 +13,12 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "explicit-context-mapping-for-stereo-matching_b200"))
 from cmf.models.cmfsm import cmfsm  # noqa: E402
+from cmf.models.cmfsm_sub_8 import cmfsm_sub_8  # noqa: E402
 
 
-def run(name, B, H, W, maxdisp, agg, steps):
+def run(name, B, H, W, maxdisp, agg, steps, cls=cmfsm):
     torch.manual_seed(0)
-    model = cmfsm(maxdisp=maxdisp).cuda().eval()
+    model = cls(maxdisp=maxdisp).cuda().eval()
     model.aggregation = agg
     g = torch.Generator().manual_seed(1)
     left = torch.rand(B, 3, H, W, generator=g).cuda()
@@ -48,3 +50,5 @@ if __name__ == "__main__":
     run("C4-fp32", 16, 384, 1248, 192, "fp32", 2)
     run("C5", 1, 2048, 3072, 384, "fp32", 2)
     run("C5-bf16", 1, 2048, 3072, 384, "bf16", 2)
+    run("C2-sub_8", 1, 576, 960, 192, "fp32", 10, cmfsm_sub_8)  # the 1/8-resolution variant on the config-2 pair
+    run("C2-sub_8-bf16", 1, 576, 960, 192, "bf16", 10, cmfsm_sub_8)
