@@ -1,15 +1,16 @@
 """Model registry with the reference's entry point (reference cmf/models/__init__.py:19-41).
 
 `get_model(name)` instantiates the class with NO arguments, exactly like the reference.  Scope of this
-build: `cmfsm` is the B200-native hot path and `cmfsm_sub_8` (the 1/8-resolution
-"downsample config") runs on the same kernels (inference).  The other eight registered names of the
-reference (baselines / ablations / the 1/16 variant) are listed so that a typo and an out-of-scope name
-produce different, explicit errors instead of the reference's bare `print`.
+build: `cmfsm` is the B200-native hot path; `cmfsm_sub_8` and `cmfsm_sub_16` (the 1/8- and
+1/16-resolution "downsample configs") run on the same kernels (inference).  The other seven registered names of
+the reference (baselines / ablations) are listed so that a typo and an out-of-scope name produce different,
+explicit errors instead of the reference's bare `print`.
 """
 from cmf.models.cmfsm import cmfsm
 from cmf.models.cmfsm_sub_8 import cmfsm_sub_8
+from cmf.models.cmfsm_sub_16 import cmfsm_sub_16
 
-_IMPLEMENTED = {"cmfsm": cmfsm, "cmfsm_sub_8": cmfsm_sub_8}
+_IMPLEMENTED = {"cmfsm": cmfsm, "cmfsm_sub_8": cmfsm_sub_8, "cmfsm_sub_16": cmfsm_sub_16}
 _REFERENCE_NAMES = ("cmf", "cmfsm", "bilinear_cmf", "cmfsm_sub_8", "cmfsm_sub_16", "bilinear_cmf_sub_8",
                     "bilinear_cmf_sub_16", "cm_sub_16", "cm_sub_8", "cm_sub_4")
 

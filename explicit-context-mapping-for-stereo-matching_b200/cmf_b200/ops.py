@@ -562,12 +562,47 @@ def spp_upsample_concat_sized(raw, skip, branches):
     """cat([raw, skip, up(b) for b in branches], 1) for four branch maps of arbitrary size (cmfsm_sub_8)."""
     _req(raw, skip, *branches)
     B, _, H, W = skip.shape
-    if raw.shape[1] != 64 or skip.shape[1] != 128 or len(branches) != 4 or any(t.shape[1] != 32 for t in branches):
-        raise ValueError("spp_upsample_concat_sized expects 64 + 128 + 4 x 32 channels")
-    cat = torch.empty((B, 320, H, W), device=skip.device, dtype=torch.float32)
+    raw_c = raw.shape[1]
+    if raw_c not in (64, 128) or skip.shape[1] != 128 or len(branches) != 4 or any(t.shape[1] != 32 for t in branches):
+        raise ValueError("spp_upsample_concat_sized expects (64|128) + 128 + 4 x 32 channels")
+    cat = torch.empty((B, raw_c + 256, H, W), device=skip.device, dtype=torch.float32)
     sizes = [int(v) for t in branches for v in t.shape[2:]]
     with torch.cuda.device(skip.device), _timed("spp_upsample_concat_fwd"):
         _lib.check(_lib.load().cmfb200_spp_upsample_concat_sized_fwd(_p(raw), _p(skip), *[_p(t) for t in branches], _p(cat),
-                                                                     B, H, W, *sizes, _stream()),
+                                                                     B, raw_c, H, W, *sizes, _stream()),
                    "spp_upsample_concat_sized_fwd")
     return cat
+
+
+# ---- cmfsm_sub_16 variant --------------------------------------------------------------------------
+def ctxmap_weights3(lr, hr, w0, w1, w2, w3):
+    """Target-image half of six_related_context_mapping (cmf/models/cmfsm_sub_16.py:488-573): the right image's
+    [B,32,h,w],[B,32,H,W] -> [B,3,H,W] = softmax(logits)*logits, neighbours centre, right, left."""
+    ws = [w.detach().reshape(w.shape[0], w.shape[1]).contiguous() for w in (w0, w1, w2, w3)]
+    _req(lr, hr, *ws)
+    B, C, h, w = lr.shape
+    H, W = hr.shape[2:]
+    scale = W // w
+    if C != 32 or hr.shape[1] != 32 or H != h * scale or W != w * scale:
+        raise ValueError("ctxmap_weights3: bad shapes %s / %s" % (tuple(lr.shape), tuple(hr.shape)))
+    out = torch.empty((B, 3, H, W), device=lr.device, dtype=torch.float32)
+    with torch.cuda.device(lr.device), _timed("ctxmap_weights3_fwd"):
+        _lib.check(_lib.load().cmfb200_ctxmap_weights3_fwd(_p(lr), _p(hr), _p(ws[0]), _p(ws[1]), _p(ws[2]), _p(ws[3]),
+                                                           _p(out), B, h, w, scale, _stream()), "ctxmap_weights3_fwd")
+    return out
+
+
+def volume_mapping(c1, c2, c3, weights5, weights3, scale):
+    """cmf/models/cmfsm_sub_16.py:760-850: raw classifier volumes [B,D',h,w] + spatial / target weights -> 3 x [B,H,W]."""
+    _req(c1, c2, c3, weights5, weights3)
+    B, Dl, h, w = c1.shape
+    H, W = h * scale, w * scale
+    if tuple(weights5.shape) != (B, 5, H, W) or tuple(weights3.shape) != (B, 3, H, W):
+        raise ValueError("volume_mapping: weights %s / %s do not match %s at scale %d"
+                         % (tuple(weights5.shape), tuple(weights3.shape), tuple(c1.shape), scale))
+    outs = [torch.empty((B, H, W), device=c1.device, dtype=torch.float32) for _ in range(3)]
+    with torch.cuda.device(c1.device), _timed("volume_mapping_fwd"):
+        _lib.check(_lib.load().cmfb200_volume_mapping_fwd(_p(c1), _p(c2), _p(c3), _p(weights5), _p(weights3), _p(outs[0]),
+                                                          _p(outs[1]), _p(outs[2]), B, Dl, h, w, scale, _stream()),
+                   "volume_mapping_fwd")
+    return tuple(outs)

@@ -52,6 +52,15 @@ struct K5Set<1> {
     __device__ static int ky(int k) { return k == 3 ? 2 : (k == 4 ? 1 : 0); }  // top: dec, bottom: inc (sub8.py:534,546)
 };
 
+template <>
+struct K5Set<2> {  // target-image half of six_related_context_mapping: centre, right, left (cmfsm_sub_16.py:488-573)
+    static constexpr int NK = 3;
+    __device__ static int dy(int) { return 0; }
+    __device__ static int dx(int k) { return k == 1 ? 1 : (k == 2 ? -1 : 0); }
+    __device__ static int kx(int k) { return k == 1 ? 2 : (k == 2 ? 1 : 0); }
+    __device__ static int ky(int) { return 0; }
+};
+
 template <int VARIANT>
 __global__ void __launch_bounds__(kK5Threads) ctxmap_weights_kernel(
     const float* __restrict__ lr, const float* __restrict__ hr, const float* __restrict__ w0,
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(kK5Threads) ctxmap_weights_kernel(
                 logit = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) logit = fmaf(sW3[i], leaky(h2[i]), logit);
-                if (VARIANT == 1) logit = leaky(logit);
+                if (VARIANT != 0) logit = leaky(logit);
             }
             sLogit[k][tid] = logit;
         }
@@ -599,5 +608,19 @@ extern "C" int cmfb200_ctxmap_weights_bwd(const float* lr, const float* hr, cons
                                                                             grad_weights9, d_ahr, d_alr, d_wbuf, B, h, w,
                                                                             tiles_x, tiles_y);
     CMF_LAUNCH_CHECK("ctxmap_weights_bwd_kernel");
+    return CMFB200_OK;
+}
+
+extern "C" int cmfb200_ctxmap_weights3_fwd(const float* lr, const float* hr, const float* w0, const float* w1,
+                                           const float* w2, const float* w3, float* weights3, int B, int h, int w,
+                                           int scale, void* stream) {
+    CMF_REQUIRE(lr && hr && w0 && w1 && w2 && w3 && weights3, "ctxmap_weights3_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && h > 0 && w > 0, "ctxmap_weights3_fwd: non-positive dimension");
+    CMF_REQUIRE(scale >= 2 && scale % 2 == 0, "ctxmap_weights3_fwd: odd scale %d (the reference exit()s)", scale);
+    CMF_REQUIRE(B <= 65535, "ctxmap_weights3_fwd: B exceeds grid limit");
+    dim3 grid((unsigned)cdiv(w, kK5CellsX), (unsigned)cdiv(h, kK5CellsY), (unsigned)B);
+    ctxmap_weights_kernel<2><<<grid, kK5Threads, 0, (cudaStream_t)stream>>>(lr, hr, w0, w1, w2, w3, weights3, h, w, scale,
+                                                                             0, h);
+    CMF_LAUNCH_CHECK("ctxmap_weights_kernel<2>");
     return CMFB200_OK;
 }

@@ -57,12 +57,13 @@ __device__ __forceinline__ float bilinear_at(const float* __restrict__ m, int h,
 // cat[b][0:64] = raw, [64:192] = skip, [192:224] = up(branch4), [224:256] = up(b3), [256:288] = up(b2), [288:320] = up(b1)
 __global__ void spp_upsample_concat_kernel(const float* __restrict__ raw, const float* __restrict__ skip, BranchMap b4,
                                            BranchMap b3, BranchMap b2, BranchMap b1, float* __restrict__ cat, int H,
-                                           int W, int H_full, int y_off) {
-    const int b = blockIdx.z, c = blockIdx.y;  // c in [0,320)
+                                           int W, int H_full, int y_off, int raw_c) {
+    const int b = blockIdx.z, c = blockIdx.y;  // c in [0, raw_c + 128 + 128)
+    const int ctot = raw_c + 256, cplain = raw_c + 128;
     const size_t plane = (size_t)H * W;
-    float* dst = cat + ((size_t)b * 320 + c) * plane;
-    if (c < 192) {  // plain copies (128-bit when the plane allows)
-        const float* src = c < 64 ? raw + ((size_t)b * 64 + c) * plane : skip + ((size_t)b * 128 + (c - 64)) * plane;
+    float* dst = cat + ((size_t)b * ctot + c) * plane;
+    if (c < cplain) {  // plain copies (128-bit when the plane allows)
+        const float* src = c < raw_c ? raw + ((size_t)b * raw_c + c) * plane : skip + ((size_t)b * 128 + (c - raw_c)) * plane;
         if ((plane & 3) == 0) {
             for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < plane; i += (size_t)gridDim.x * blockDim.x * 4)
                 *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(src + i);
@@ -72,7 +73,7 @@ __global__ void spp_upsample_concat_kernel(const float* __restrict__ raw, const 
         }
         return;
     }
-    const int k = (c - 192) >> 5, ch = (c - 192) & 31;
+    const int k = (c - cplain) >> 5, ch = (c - cplain) & 31;
     const BranchMap bm = k == 0 ? b4 : (k == 1 ? b3 : (k == 2 ? b2 : b1));
     const float* m = bm.ptr + ((size_t)b * 32 + ch) * bm.h * bm.w;
     const float ry = (float)bm.h / (float)H_full, rx = (float)bm.w / (float)W;  // branch maps cover the FULL image
@@ -115,24 +116,25 @@ extern "C" int cmfb200_spp_upsample_concat_fwd(const float* raw, const float* sk
     CMF_REQUIRE(y_off >= 0 && y_off + H <= H_full, "spp_upsample_concat_fwd: rows [%d,%d) outside the image height %d", y_off, y_off + H, H_full);
     const BranchMap m4{b4, H_full / 8, W / 8}, m3{b3, H_full / 16, W / 16}, m2{b2, H_full / 32, W / 32}, m1{b1, H_full / 64, W / 64};
     dim3 grid((unsigned)min((long long)16, cdiv((long long)H * W, 1024)), 320, (unsigned)B);
-    spp_upsample_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, skip, m4, m3, m2, m1, cat, H, W, H_full, y_off);
+    spp_upsample_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, skip, m4, m3, m2, m1, cat, H, W, H_full, y_off, 64);
     CMF_LAUNCH_CHECK("spp_upsample_concat_kernel");
     return CMFB200_OK;
 }
 
-// Same kernel with explicit branch-map sizes (cmfsm_sub_8: pools 8/16/32/4 on the 1/8-resolution map,
-// cmfsm_sub_8.py:152-170, 207-231): cat = [raw(64) | skip(128) | up(ba) | up(bb) | up(bc) | up(bd)].
+// Same kernel with explicit branch-map sizes and raw-channel count (cmfsm_sub_8: pools 8/16/32/4 on the 1/8 map, 64 raw
+// channels, cmfsm_sub_8.py:152-170, 207-231; cmfsm_sub_16: pools 8/16/2/4 on the 1/16 map, 128 raw channels):
+// cat = [raw(raw_c) | skip(128) | up(ba) | up(bb) | up(bc) | up(bd)].
 extern "C" int cmfb200_spp_upsample_concat_sized_fwd(const float* raw, const float* skip, const float* ba,
                                                      const float* bb, const float* bc, const float* bd, float* cat,
-                                                     int B, int H, int W, int ha, int wa, int hb, int wb, int hc, int wc,
-                                                     int hd, int wd, void* stream) {
+                                                     int B, int raw_c, int H, int W, int ha, int wa, int hb, int wb, int hc,
+                                                     int wc, int hd, int wd, void* stream) {
     CMF_REQUIRE(raw && skip && ba && bb && bc && bd && cat, "spp_upsample_concat_sized_fwd: null pointer");
-    CMF_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "spp_upsample_concat_sized_fwd: bad shape");
+    CMF_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (raw_c == 64 || raw_c == 128), "spp_upsample_concat_sized_fwd: bad shape");
     CMF_REQUIRE(ha > 0 && wa > 0 && hb > 0 && wb > 0 && hc > 0 && wc > 0 && hd > 0 && wd > 0,
                 "spp_upsample_concat_sized_fwd: empty branch map");
     const BranchMap ma{ba, ha, wa}, mb{bb, hb, wb}, mc{bc, hc, wc}, md{bd, hd, wd};
-    dim3 grid((unsigned)min((long long)16, cdiv((long long)H * W, 1024)), 320, (unsigned)B);
-    spp_upsample_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, skip, ma, mb, mc, md, cat, H, W, H, 0);
+    dim3 grid((unsigned)min((long long)16, cdiv((long long)H * W, 1024)), (unsigned)(raw_c + 256), (unsigned)B);
+    spp_upsample_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, skip, ma, mb, mc, md, cat, H, W, H, 0, raw_c);
     CMF_LAUNCH_CHECK("spp_upsample_concat_kernel");
     return CMFB200_OK;
 }

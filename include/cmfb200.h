@@ -135,11 +135,12 @@ int cmfb200_spp_pool_fwd(const float* x, float* p8, float* p16, float* p32, floa
 int cmfb200_spp_upsample_concat_fwd(const float* raw, const float* skip, const float* b4, const float* b3,
                                     const float* b2, const float* b1, float* cat, int B, int H, int W,
                                     int H_full, int y_off, void* stream);
-/* The same op with explicit branch-map sizes [B,32,h*,w*] (cmfsm_sub_8: SPP pools 8/16/32/4 at 1/8 resolution,
- * cmfsm_sub_8.py:152-170, 207-231): cat = [raw | skip | up(ba) | up(bb) | up(bc) | up(bd)]. */
+/* The same op with explicit branch-map sizes [B,32,h*,w*] and raw-channel count raw_c in {64,128} (cmfsm_sub_8: SPP
+ * pools 8/16/32/4 at 1/8 resolution, cmfsm_sub_8.py:152-170, 207-231; cmfsm_sub_16: 128 raw channels,
+ * cmfsm_sub_16.py:207-236): cat [B, raw_c+256, H, W] = [raw | skip | up(ba) | up(bb) | up(bc) | up(bd)]. */
 int cmfb200_spp_upsample_concat_sized_fwd(const float* raw, const float* skip, const float* ba, const float* bb,
-                                          const float* bc, const float* bd, float* cat, int B, int H, int W, int ha,
-                                          int wa, int hb, int wb, int hc, int wc, int hd, int wd, void* stream);
+                                          const float* bc, const float* bd, float* cat, int B, int raw_c, int H, int W,
+                                          int ha, int wa, int hb, int wb, int hc, int wc, int hd, int wd, void* stream);
 
 /* ---- K3: GroupNorm (+ residual add) (+ ReLU) ---------------------------------------------------
  * Replaces nn.GroupNorm(32,C) (cmfsm.py:58,269,280), the residual adds (:288,297,299,685,687,690,693)
@@ -185,6 +186,19 @@ int cmfb200_ctxmap_weights_bwd(const float* lr, const float* hr, const float* w0
  * image; weights5 [B,5,H,W] = softmax(logits) * logits (NOT normalised).  Any even scale. */
 int cmfb200_ctxmap_weights5_fwd(const float* lr, const float* hr, const float* w0, const float* w1, const float* w2,
                                 const float* w3, float* weights5, int B, int h, int w, int scale, void* stream);
+/* The TARGET-image half of the same module (three neighbours centre, right, left of the right image's own feature
+ * maps; used by cmfsm_sub_16, cmfsm_sub_16.py:488-573): weights3 [B,3,H,W] = softmax(logits) * logits. */
+int cmfb200_ctxmap_weights3_fwd(const float* lr, const float* hr, const float* w0, const float* w1, const float* w2,
+                                const float* w3, float* weights3, int B, int h, int w, int scale, void* stream);
+/* cmfsm_sub_16 epilogue (cmfsm_sub_16.py:760-850): the three classifier volumes c_n [B,D',h,w] are accumulated
+ * (c2 += c1, c3 += c2), nearest-upsampled by `scale` along d, y, x, mixed over the five spatial neighbours with
+ * weights5, then over the disparity axis with the target weights shifted by the disparity
+ * (v[d,y,x] = weights3[.,y,x-d] for x >= d, 1 elsewhere; taps d, d+scale (left weight), d-scale (right weight)),
+ * and regressed by a softmax over all maxdisp = D'*scale planes.  out_n: [B,H,W].  One launch, nothing of the
+ * [B,maxdisp,H,W] volumes is materialised. */
+int cmfb200_volume_mapping_fwd(const float* c1, const float* c2, const float* c3, const float* weights5,
+                               const float* weights3, float* out1, float* out2, float* out3, int B, int Dl, int h,
+                               int w, int scale, void* stream);
 
 /* ---- K4: soft-argmin + x scale upsample + 9-neighbour context mapping ---------------------------
  * Replaces cmfsm.py:703-769 (3x softmax, disparityregression :111-123, ~60 slice kernels).

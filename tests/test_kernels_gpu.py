@@ -548,3 +548,32 @@ def test_conv2d_dilation4_and_sized_spp_concat():
     want = torch.cat([raw, skip] + [F.interpolate(b, (32, 64), mode="bilinear", align_corners=False) for b in br], 1)
     got = ops.spp_upsample_concat_sized(raw.to(DEV), skip.to(DEV), [b.to(DEV) for b in br])
     torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,Dl,h,w,scale", [(1, 3, 4, 6, 8), (2, 12, 5, 9, 16), (1, 4, 6, 20, 4)])
+def test_volume_mapping_vs_oracle(B, Dl, h, w, scale):
+    """cmfb200_volume_mapping_fwd (cmfsm_sub_16 epilogue) vs the restatement that materialises the volumes."""
+    import cmfsm_sub16_oracle as orc16
+    from cmf_b200 import ops
+
+    cs = [_rand(B, Dl, h, w, seed=180 + i) * 2 for i in range(3)]
+    w5 = _rand(B, 5, h * scale, w * scale, seed=184) * 0.5
+    w3 = _rand(B, 3, h * scale, w * scale, seed=185) * 0.5 + 0.3
+    want = orc16.volume_mapping(*[c.double() for c in cs], w5.double(), w3.double(), scale, Dl * scale)
+    got = ops.volume_mapping(*[c.to(DEV) for c in cs], w5.to(DEV), w3.to(DEV), scale)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        torch.testing.assert_close(a.cpu().double(), b, rtol=1e-4, atol=1e-3)
+
+
+def test_k5_target_three_neighbour_variant_vs_oracle():
+    import cmfsm_sub16_oracle as orc16
+    from cmf_b200 import ops
+
+    sd = _sub8_sd(190)
+    lr, hr = _rand(2, 32, 4, 7, seed=191), _rand(2, 32, 64, 112, seed=192)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    w5, w3 = orc16.context_mapping_weights(sd64, lr.double(), hr.double(), lr.double(), hr.double())
+    ws = [sd["mapping_matrix.similarity1.conv%d.weight" % i].to(DEV) for i in range(4)]
+    torch.testing.assert_close(ops.ctxmap_weights3(lr.to(DEV), hr.to(DEV), *ws).cpu().double(), w3, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(ops.ctxmap_weights5(lr.to(DEV), hr.to(DEV), *ws).cpu().double(), w5, rtol=1e-4, atol=1e-5)

@@ -214,3 +214,27 @@ def test_sub8_variant_matches_fp64_oracle():
         rel = float((a - c).norm() / a.norm())
         print("sub_8 bf16 aggregation vs fp32: rel-L2 %.3e" % rel)
         assert torch.isfinite(c).all() and rel < 0.2
+
+
+def test_sub16_variant_matches_fp64_oracle():
+    """cmfsm_sub_16 on the CUDA kernels vs its fp64 CPU oracle (pinned to the real reference module by
+    oracle/gen_golden_sub16.py); same relative rule as the other models."""
+    import cmfsm_sub16_oracle as orc16
+    from cmf.models import get_model
+
+    torch.manual_seed(gc.WEIGHT_SEED)
+    net = get_model("cmfsm_sub_16").to(DEV).eval()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    left, right = gc.seeded_pair(1, 256, 512, seed=5)
+    with torch.no_grad():
+        ours = net(left.to(DEV), right.to(DEV))
+    ref32 = orc16.forward(sd, left, right, 192)
+    ref64 = orc16.forward({k: v.double() for k, v in sd.items()}, left.double(), right.double(), 192)
+    for i, (a, r32, r64) in enumerate(zip(ours, ref32, ref64), 1):
+        assert tuple(a.shape) == (1, 256, 512)
+        d_ours = (a.cpu().double() - r64).abs()
+        d_ref = (r32.double() - r64).abs()
+        print("sub_16 pred%d: ours-vs-fp64 max %.3e mean %.3e ; ref32-vs-fp64 max %.3e mean %.3e"
+              % (i, d_ours.max(), d_ours.mean(), d_ref.max(), d_ref.mean()))
+        assert float(d_ours.mean()) <= 2 * float(d_ref.mean()) + 1e-3
+        assert float(d_ours.max()) <= 3 * float(d_ref.max()) + 5e-2

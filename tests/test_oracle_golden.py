@@ -115,6 +115,25 @@ def test_sub8_full_forward_against_reference(golden_dir):
     torch.testing.assert_close(stages["L"][0, ::4, ::2, ::2], g["L_sub"], rtol=1e-3, atol=1e-4)
 
 
+def test_sub16_full_forward_against_reference(golden_dir):
+    """cmfsm_sub_16 oracle at 256x512 vs the outputs of the real reference module (exact when the fixtures were made)."""
+    import cmfsm_sub16_oracle as orc16
+    from cmf.models import get_model
+
+    g = _npz(golden_dir, "cmfsm_sub16_c1.npz")
+    torch.manual_seed(gc.WEIGHT_SEED)
+    sd = get_model("cmfsm_sub_16").state_dict()
+    left, right = gc.seeded_pair(1, 256, 512)
+    stages = {}
+    p1, p2, p3 = orc16.forward(sd, left, right, 192, stages)
+    for got, key in ((p1, "pred1_sub"), (p2, "pred2_sub"), (p3, "pred3_sub")):
+        assert tuple(got.shape) == (1, 256, 512)
+        d = (got[0, ::4, ::4] - g[key]).abs()
+        assert float(d.max()) < 0.5 and float(d.mean()) < 2e-2, (key, float(d.max()), float(d.mean()))
+    torch.testing.assert_close(stages["w3"][0, :, ::8, ::8], g["w3_sub"], rtol=2e-3, atol=1e-3)
+    torch.testing.assert_close(stages["c1"][0], g["c1_sub"], rtol=1e-3, atol=1e-3)
+
+
 def test_shape_validation():
     import pytest
 

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "explicit-context-mapping-for-stereo-matching_b200"))
 from cmf.models.cmfsm import cmfsm  # noqa: E402
 from cmf.models.cmfsm_sub_8 import cmfsm_sub_8  # noqa: E402
+from cmf.models.cmfsm_sub_16 import cmfsm_sub_16  # noqa: E402
 
 
 def run(name, B, H, W, maxdisp, agg, steps, cls=cmfsm):
@@ -35,7 +36,7 @@ def run(name, B, H, W, maxdisp, agg, steps, cls=cmfsm):
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    assert bool(torch.isfinite(out[2]).all()) and tuple(out[2].shape) == (B, 1, H, W)
+    assert bool(torch.isfinite(out[2]).all()) and tuple(out[2].shape) in ((B, 1, H, W), (B, H, W))
     print(json.dumps({"config": name, "B": B, "H": H, "W": W, "maxdisp": maxdisp, "aggregation": agg,
                       "ms_per_forward": ms, "pairs_per_s": B / ms * 1e3,
                       "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
@@ -52,3 +53,5 @@ if __name__ == "__main__":
     run("C5-bf16", 1, 2048, 3072, 384, "bf16", 2)
     run("C2-sub_8", 1, 576, 960, 192, "fp32", 10, cmfsm_sub_8)  # the 1/8-resolution variant on the config-2 pair
     run("C2-sub_8-bf16", 1, 576, 960, 192, "bf16", 10, cmfsm_sub_8)
+    run("C2-sub_16", 1, 576, 960, 192, "fp32", 10, cmfsm_sub_16)  # 576x960 is a multiple of 64 as well
+    run("C2-sub_16-bf16", 1, 576, 960, 192, "bf16", 10, cmfsm_sub_16)
