@@ -9,7 +9,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcmfb200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _c = ctypes
 _P = _c.c_void_p

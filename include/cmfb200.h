@@ -27,7 +27,7 @@ extern "C" {
 #define CMFB200_ERR_INVALID (-1) /* bad shape / null pointer / unsupported configuration */
 #define CMFB200_ERR_CUDA (-2)    /* a CUDA runtime call failed (message has the cudaError string) */
 
-#define CMFB200_ABI_VERSION 1
+#define CMFB200_ABI_VERSION 2
 
 /* ABI version of the loaded library (== CMFB200_ABI_VERSION of the header it was built from). */
 int cmfb200_abi_version(void);
