@@ -10,8 +10,8 @@ FORWARD always runs the libcmfb200 kernels (2-D extractor included).  BACKWARD s
   * SPP upsample + concat -- gradient slices + two dense products per branch (adjoint of the bilinear map);
   * K5                    -- own kernel (`cmfb200_ctxmap_weights_bwd`) + two 1x1 GEMMs; the PyTorch closed form below
     is the test reference and the path for scales other than 4;
-  * K4                    -- interim: the closed form below is re-evaluated with PyTorch CUDA ops inside
-    `backward` only and differentiated by autograd.
+  * K4                    -- own kernel (`cmfb200_softargmin_ctxmap_bwd`); the PyTorch closed form below is its test
+    reference.
 None of this is reachable on CPU tensors (the forward kernels raise first).
 """
 import torch
@@ -306,16 +306,15 @@ class _SoftargminCtxmap(Function):
     @staticmethod
     def forward(ctx, c1, c2, c3, weights9, scale):
         ctx.scale = scale
+        c1, c2, c3, weights9 = c1.contiguous(), c2.contiguous(), c3.contiguous(), weights9.contiguous()
         ctx.save_for_backward(c1, c2, c3, weights9)
-        return ops.softargmin_ctxmap(c1.contiguous(), c2.contiguous(), c3.contiguous(), weights9.contiguous(), scale)
+        return ops.softargmin_ctxmap(c1, c2, c3, weights9, scale)
 
     @staticmethod
     def backward(ctx, g1, g2, g3):
-        saved = [t.detach().requires_grad_(True) for t in ctx.saved_tensors]
-        with torch.enable_grad():
-            outs = _softargmin_ctxmap_torch(*saved, ctx.scale)
-        grads = torch.autograd.grad(outs, saved, (g1, g2, g3), allow_unused=True)
-        return grads + (None,)
+        c1, c2, c3, weights9 = ctx.saved_tensors
+        gs = [g if g is not None else torch.zeros_like(weights9[:, :1]) for g in (g1, g2, g3)]
+        return ops.softargmin_ctxmap_bwd(c1, c2, c3, weights9, gs[0], gs[1], gs[2], ctx.scale) + (None,)
 
 
 def softargmin_ctxmap(c1, c2, c3, weights9, scale):

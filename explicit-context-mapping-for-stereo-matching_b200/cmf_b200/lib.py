@@ -48,6 +48,7 @@ SIGNATURES = {
     "cmfb200_gn_bwd": [_P] * 8 + [_I, _I, _I, _LL, _F, _P],
     "cmfb200_ctxmap_weights_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_ctxmap_weights5_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "cmfb200_softargmin_ctxmap_bwd": [_P] * 11 + [_I] * 5 + [_P],
     "cmfb200_softargmin_ctxmap5_fwd": [_P] * 8 + [_I] * 5 + [_P],
     "cmfb200_spp_upsample_concat_sized_fwd": [_P] * 7 + [_I] * 12 + [_P],
     "cmfb200_ctxmap_weights3_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

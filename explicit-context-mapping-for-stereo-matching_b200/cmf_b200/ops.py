@@ -523,6 +523,20 @@ def gn_apply_c8(x, sums, gamma, beta, residual=None, relu=False, out=None, want_
     return (y, split) if want_split else y
 
 
+def softargmin_ctxmap_bwd(c1, c2, c3, weights9, g1, g2, g3, scale):
+    """Backward of `softargmin_ctxmap`: returns (dc1, dc2, dc3, dweights9)."""
+    gs = [g.contiguous() for g in (g1, g2, g3)]
+    _req(c1, c2, c3, weights9, *gs)
+    B, D, h, w = c1.shape
+    dcs = [torch.empty_like(c1) for _ in range(3)]
+    dw = torch.empty_like(weights9)
+    with torch.cuda.device(c1.device), _timed("softargmin_ctxmap_bwd"):
+        _lib.check(_lib.load().cmfb200_softargmin_ctxmap_bwd(_p(c1), _p(c2), _p(c3), _p(weights9), _p(gs[0]), _p(gs[1]),
+                                                             _p(gs[2]), _p(dcs[0]), _p(dcs[1]), _p(dcs[2]), _p(dw), B, D, h,
+                                                             w, scale, _stream()), "softargmin_ctxmap_bwd")
+    return dcs[0], dcs[1], dcs[2], dw
+
+
 # ---- cmfsm_sub_8 variant ---------------------------------------------------------------------------
 def ctxmap_weights5(lr, hr, w0, w1, w2, w3):
     """six_related_context_mapping (reference-image half, cmf/models/cmfsm_sub_8.py:440-572):

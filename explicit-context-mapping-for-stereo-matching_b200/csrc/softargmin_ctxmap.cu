@@ -129,6 +129,152 @@ __global__ void __launch_bounds__(kK4Threads) softargmin_ctxmap_kernel(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K4 backward (training, cmfsm): gradients of the three mapped outputs w.r.t. the raw classifier volumes and the nine
+// weights.  One launch, no atomics (gather formulation), same tiling as the forward.
+//   phase 1  p_n, running max m_n and normaliser s_n of the three cumulative volumes for the block + 1-cell halo
+//   phase 2  per output pixel: dw_k = scale * sum_n g_n p_n[cell+off_k]   (0 where the neighbour cell is outside)
+//   phase 3  per interior cell c and neighbour k: sum over the pixels of cell c-off_k of g_n w_k  -> dp_n[c]
+//   phase 4  per interior cell: dcost_n[d] = softmax_n[d] (d - p_n) dp_n;  dc3 = dcost3, dc2 = dcost2 + dcost3,
+//            dc1 = dcost1 + dcost2 + dcost3 (the cumulative sums of the forward)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kK4Threads) softargmin_ctxmap_bwd_kernel(
+    const float* __restrict__ c1, const float* __restrict__ c2, const float* __restrict__ c3,
+    const float* __restrict__ wts, const float* __restrict__ g1, const float* __restrict__ g2,
+    const float* __restrict__ g3, float* __restrict__ dc1, float* __restrict__ dc2, float* __restrict__ dc3,
+    float* __restrict__ dw, int B, int D, int h, int w, int scale) {
+    __shared__ float sp[3][kHY][kHX];
+    __shared__ float sm[3][kTCY][kTCX], ss[3][kTCY][kTCX];
+    __shared__ float sdp[3][kTCY * kTCX][9];
+    const int b = blockIdx.z;
+    const int cy0 = blockIdx.y * kTCY, cx0 = blockIdx.x * kTCX;
+    const size_t plane = (size_t)h * w;
+    const int H = h * scale, W = w * scale;
+    const size_t oplane = (size_t)H * W;
+    const float fs = (float)scale;
+    const int dys[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+    const int dxs[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+
+    // ---- phase 1
+    for (int t = threadIdx.x; t < kHY * kHX; t += kK4Threads) {
+        const int hy = t / kHX, hx = t - hy * kHX;
+        const int cy = cy0 + hy - 1, cx = cx0 + hx - 1;
+        float p[3] = {0.f, 0.f, 0.f};
+        if (cy >= 0 && cy < h && cx >= 0 && cx < w) {
+            const size_t off = (size_t)b * D * plane + (size_t)cy * w + cx;
+            Online o[3];
+            o[0].init(); o[1].init(); o[2].init();
+            for (int d = 0; d < D; ++d) {
+                const float v1 = c1[off + d * plane];
+                const float v2 = __fadd_rn(c2[off + d * plane], v1);
+                const float v3 = __fadd_rn(c3[off + d * plane], v2);
+                const float fd = (float)d;
+                o[0].push(v1, fd); o[1].push(v2, fd); o[2].push(v3, fd);
+            }
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+                p[n] = o[n].result();
+                if (hy >= 1 && hy <= kTCY && hx >= 1 && hx <= kTCX) {
+                    sm[n][hy - 1][hx - 1] = o[n].m;
+                    ss[n][hy - 1][hx - 1] = o[n].s;
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 3; ++n) sp[n][hy][hx] = p[n];
+    }
+    __syncthreads();
+
+    // ---- phase 2: dweights of the tile's pixels (4 adjacent pixels = one cell's row segment per thread)
+    const int tile_h = kTCY * scale, tile_w4 = (kTCX * scale) >> 2;
+    for (int i = threadIdx.x; i < tile_h * tile_w4; i += kK4Threads) {
+        const int ty = i / tile_w4, tx = (i - ty * tile_w4) << 2;
+        const int y = cy0 * scale + ty, x = cx0 * scale + tx;
+        if (y >= H || x >= W) continue;
+        const int ly = ty / scale + 1, lx = tx / scale + 1;
+        const int cy = cy0 + ly - 1, cx = cx0 + lx - 1;
+        const size_t oo = (size_t)b * oplane + (size_t)y * W + x;
+        const float4 ga = *reinterpret_cast<const float4*>(g1 + oo);
+        const float4 gb = *reinterpret_cast<const float4*>(g2 + oo);
+        const float4 gc = *reinterpret_cast<const float4*>(g3 + oo);
+        float* pd = dw + (size_t)b * 9 * oplane + (size_t)y * W + x;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int ny = cy + dys[k], nx = cx + dxs[k];
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ny >= 0 && ny < h && nx >= 0 && nx < w) {
+                const float u1 = fs * sp[0][ly + dys[k]][lx + dxs[k]], u2 = fs * sp[1][ly + dys[k]][lx + dxs[k]];
+                const float u3 = fs * sp[2][ly + dys[k]][lx + dxs[k]];
+                r.x = fmaf(ga.x, u1, fmaf(gb.x, u2, gc.x * u3));
+                r.y = fmaf(ga.y, u1, fmaf(gb.y, u2, gc.y * u3));
+                r.z = fmaf(ga.z, u1, fmaf(gb.z, u2, gc.z * u3));
+                r.w = fmaf(ga.w, u1, fmaf(gb.w, u2, gc.w * u3));
+            }
+            *reinterpret_cast<float4*>(pd + k * oplane) = r;
+        }
+    }
+
+    // ---- phase 3: dp_n[c] = scale * sum_k sum_{pixels of cell c-off_k} g_n w_k   (thread per (cell, k) pair)
+    for (int i = threadIdx.x; i < kTCY * kTCX * 9; i += kK4Threads) {
+        const int k = i % 9, cell = i / 9;
+        const int ly = cell / kTCX, lx = cell - ly * kTCX;
+        const int cy = cy0 + ly, cx = cx0 + lx;          // the cell that receives the gradient
+        const int sy = cy - dys[k], sx = cx - dxs[k];    // the cell whose pixels use (cy,cx) as neighbour k
+        float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (cy < h && cx < w && sy >= 0 && sy < h && sx >= 0 && sx < w) {
+            const size_t base = (size_t)b * oplane + (size_t)(sy * scale) * W + (size_t)sx * scale;
+            const float* pw = wts + ((size_t)b * 9 + k) * oplane + (size_t)(sy * scale) * W + (size_t)sx * scale;
+            for (int py = 0; py < scale; ++py)
+                for (int px = 0; px < scale; px += 4) {
+                    const size_t o = (size_t)py * W + px;
+                    const float4 wv = *reinterpret_cast<const float4*>(pw + o);
+                    const float4 ga = *reinterpret_cast<const float4*>(g1 + base + o);
+                    const float4 gb = *reinterpret_cast<const float4*>(g2 + base + o);
+                    const float4 gc = *reinterpret_cast<const float4*>(g3 + base + o);
+                    a1 += (ga.x * wv.x + ga.y * wv.y) + (ga.z * wv.z + ga.w * wv.w);
+                    a2 += (gb.x * wv.x + gb.y * wv.y) + (gb.z * wv.z + gb.w * wv.w);
+                    a3 += (gc.x * wv.x + gc.y * wv.y) + (gc.z * wv.z + gc.w * wv.w);
+                }
+        }
+        sdp[0][cell][k] = a1;
+        sdp[1][cell][k] = a2;
+        sdp[2][cell][k] = a3;
+    }
+    __syncthreads();
+
+    // ---- phase 4: softmax backward down the disparity axis (thread per interior cell)
+    for (int cell = threadIdx.x; cell < kTCY * kTCX; cell += kK4Threads) {
+        const int ly = cell / kTCX, lx = cell - ly * kTCX;
+        const int cy = cy0 + ly, cx = cx0 + lx;
+        if (cy >= h || cx >= w) continue;
+        float dp[3], pn[3], mn[3], rs[3];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a += sdp[n][cell][k];
+            dp[n] = a * fs;
+            pn[n] = sp[n][ly + 1][lx + 1];
+            mn[n] = sm[n][ly][lx];
+            rs[n] = 1.f / ss[n][ly][lx];
+        }
+        const size_t off = (size_t)b * D * plane + (size_t)cy * w + cx;
+        for (int d = 0; d < D; ++d) {
+            const float v1 = c1[off + d * plane];
+            const float v2 = __fadd_rn(c2[off + d * plane], v1);
+            const float v3 = __fadd_rn(c3[off + d * plane], v2);
+            const float fd = (float)d;
+            const float t1 = expf(v1 - mn[0]) * rs[0] * (fd - pn[0]) * dp[0];
+            const float t2 = expf(v2 - mn[1]) * rs[1] * (fd - pn[1]) * dp[1];
+            const float t3 = expf(v3 - mn[2]) * rs[2] * (fd - pn[2]) * dp[2];
+            dc3[off + d * plane] = t3;
+            dc2[off + d * plane] = t2 + t3;
+            dc1[off + d * plane] = t1 + (t2 + t3);
+        }
+    }
+}
+
 }  // namespace cmfb200
 
 using namespace cmfb200;
@@ -158,5 +304,21 @@ extern "C" int cmfb200_softargmin_ctxmap5_fwd(const float* c1, const float* c2, 
     softargmin_ctxmap_kernel<1><<<grid, kK4Threads, 0, (cudaStream_t)stream>>>(c1, c2, c3, weights5, out1, out2, out3,
                                                                                 pred_lr, B, D, h, w, scale);
     CMF_LAUNCH_CHECK("softargmin_ctxmap_kernel<1>");
+    return CMFB200_OK;
+}
+
+extern "C" int cmfb200_softargmin_ctxmap_bwd(const float* c1, const float* c2, const float* c3, const float* weights9,
+                                             const float* g1, const float* g2, const float* g3, float* dc1, float* dc2,
+                                             float* dc3, float* dweights9, int B, int D, int h, int w, int scale,
+                                             void* stream) {
+    CMF_REQUIRE(c1 && c2 && c3 && weights9 && g1 && g2 && g3 && dc1 && dc2 && dc3 && dweights9,
+                "softargmin_ctxmap_bwd: null pointer");
+    CMF_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0, "softargmin_ctxmap_bwd: non-positive dimension");
+    CMF_REQUIRE(scale >= 4 && scale % 4 == 0, "softargmin_ctxmap_bwd: scale=%d must be a positive multiple of 4", scale);
+    CMF_REQUIRE(B <= 65535, "softargmin_ctxmap_bwd: B exceeds grid limit");
+    dim3 grid((unsigned)cdiv(w, kTCX), (unsigned)cdiv(h, kTCY), (unsigned)B);
+    softargmin_ctxmap_bwd_kernel<<<grid, kK4Threads, 0, (cudaStream_t)stream>>>(c1, c2, c3, weights9, g1, g2, g3, dc1, dc2,
+                                                                                dc3, dweights9, B, D, h, w, scale);
+    CMF_LAUNCH_CHECK("softargmin_ctxmap_bwd_kernel");
     return CMFB200_OK;
 }

@@ -209,6 +209,12 @@ int cmfb200_volume_mapping_fwd(const float* c1, const float* c2, const float* c3
 int cmfb200_softargmin_ctxmap_fwd(const float* c1, const float* c2, const float* c3,
                                   const float* weights9, float* out1, float* out2, float* out3,
                                   float* pred_lr, int B, int D, int h, int w, int scale, void* stream);
+/* K4 backward (training): g_n = gradients of the three outputs [B,1,H,W]; writes dc_n [B,D,h,w] (gradients of the RAW
+ * classifier volumes, i.e. the cumulative sums of the forward are back-propagated too) and dweights9 [B,9,H,W].
+ * One launch, no atomics, every output element written. */
+int cmfb200_softargmin_ctxmap_bwd(const float* c1, const float* c2, const float* c3, const float* weights9,
+                                  const float* g1, const float* g2, const float* g3, float* dc1, float* dc2, float* dc3,
+                                  float* dweights9, int B, int D, int h, int w, int scale, void* stream);
 /* cmfsm_sub_8 variant (cmfsm_sub_8.py:757-802): the three volumes are regressed independently (no cumulative sums)
  * and mapped with the five weights of cmfb200_ctxmap_weights5_fwd (order c,r,l,t,b). */
 int cmfb200_softargmin_ctxmap5_fwd(const float* c1, const float* c2, const float* c3, const float* weights5,

@@ -577,3 +577,22 @@ def test_k5_target_three_neighbour_variant_vs_oracle():
     ws = [sd["mapping_matrix.similarity1.conv%d.weight" % i].to(DEV) for i in range(4)]
     torch.testing.assert_close(ops.ctxmap_weights3(lr.to(DEV), hr.to(DEV), *ws).cpu().double(), w3, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(ops.ctxmap_weights5(lr.to(DEV), hr.to(DEV), *ws).cpu().double(), w5, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,D,h,w,scale", [(1, 6, 3, 5, 4), (2, 12, 9, 20, 4), (1, 8, 17, 33, 4)])
+def test_k4_backward_vs_autograd(B, D, h, w, scale):
+    """cmfb200_softargmin_ctxmap_bwd vs autograd through the PyTorch closed form of K4 in fp64."""
+    from cmf_b200 import autograd_ops as aops
+    from cmf_b200 import ops
+
+    cs = [_rand(B, D, h, w, seed=200 + i) * 2 for i in range(3)]
+    w9 = torch.softmax(_rand(B, 9, h * scale, w * scale, seed=204), 1)
+    gs = [_rand(B, 1, h * scale, w * scale, seed=205 + i) for i in range(3)]
+    ins = [t.double().requires_grad_(True) for t in cs + [w9]]
+    outs = aops._softargmin_ctxmap_torch(*ins, scale)
+    want = torch.autograd.grad(outs, ins, [g.double() for g in gs])
+    got = ops.softargmin_ctxmap_bwd(*[c.to(DEV) for c in cs], w9.to(DEV), *[g.to(DEV) for g in gs], scale)
+    for name, a, b in zip(("dc1", "dc2", "dc3", "dw9"), got, want):
+        err = _rel_l2(a.cpu().double(), b)
+        print("K4 bwd %s rel-L2 %.2e" % (name, err))
+        assert a.shape == b.shape and err < 2e-5, (name, err)
