@@ -238,3 +238,32 @@ def test_sub16_variant_matches_fp64_oracle():
               % (i, d_ours.max(), d_ours.mean(), d_ref.max(), d_ref.mean()))
         assert float(d_ours.mean()) <= 2 * float(d_ref.mean()) + 1e-3
         assert float(d_ours.max()) <= 3 * float(d_ref.max()) + 5e-2
+
+
+def test_ragged_shape_and_other_maxdisp_vs_fp64_oracle():
+    """A shape whose 1/4, 1/8 and 1/16 levels are not multiples of any tile size (272x528 -> 68x132, 34x66, 17x33) with
+    maxdisp 80 (D' = 20 / 10 / 5): fp32 mode against the fp64 oracle with the usual gate, bf16 mode against fp32, CUDA
+    graph replay against eager."""
+    from cmf.models.cmfsm import cmfsm
+
+    torch.manual_seed(3)
+    net = cmfsm(maxdisp=80).to(DEV).eval()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    left, right = gc.seeded_pair(1, 272, 528, seed=21)
+    ref32 = orc.forward(sd, left, right, 80)
+    ref64 = orc.forward({k: v.double() for k, v in sd.items()}, left.double(), right.double(), 80)
+    with torch.no_grad():
+        got = net(left.to(DEV), right.to(DEV))
+        net.enable_cuda_graph(True)
+        replay = net(left.to(DEV), right.to(DEV))
+        net.enable_cuda_graph(False)
+        net.aggregation = "bf16"
+        got16 = net(left.to(DEV), right.to(DEV))
+    for i, (a, r, b16, b32, b64) in enumerate(zip(got, replay, got16, ref32, ref64), 1):
+        assert tuple(a.shape) == (1, 1, 272, 528) and torch.equal(a, r)
+        ours, theirs = (a.cpu().double() - b64).abs(), (b32.double() - b64).abs()
+        print("ragged pred%d |ours-fp64| max %.2e mean %.2e  |ref32-fp64| max %.2e mean %.2e  bf16-fp32 mean %.3f"
+              % (i, ours.max(), ours.mean(), theirs.max(), theirs.mean(), (b16 - a).abs().mean()))
+        assert float(ours.max()) <= 2 * float(theirs.max()) + 2e-3
+        assert float(ours.mean()) <= 2 * float(theirs.mean()) + 1e-4
+        assert torch.isfinite(b16).all() and float((b16 - a).abs().mean()) < 1.0
