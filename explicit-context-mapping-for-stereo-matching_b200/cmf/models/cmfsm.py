@@ -378,19 +378,18 @@ class cmfsm(nn.Module):
         """conv/deconv + GroupNorm(+residual)(+ReLU) on a row band.  `full_rows`: rows of the UN-sharded output."""
         conv, gn = block[0], block[1]
         packed = self._pack(conv)
+        rows = x.shape[3]
         if isinstance(conv, nn.ConvTranspose3d):  # out rows 2i, 2i+1 need input rows i, i+1: bottom halo only
             ext = par.exchange_row_halo(x, 0, 1, dim=3)
-            y, _ = ops.conv3d_k3(ext, packed, transposed=True)
-            y = y[:, :, :, :2 * x.shape[3]].contiguous()
+            y, sums = ops.conv3d_k3_rows(ext, packed, rows, transposed=True)
         elif stride == 2:  # out row m reads input rows 2m-1..2m+1: two top halo rows re-align the padded windows
             ext = par.exchange_row_halo(x, 2, 0, dim=3)
-            y, _ = ops.conv3d_k3(ext, packed, 2)
-            y = y[:, :, :, 1:1 + x.shape[3] // 2].contiguous()
+            y, sums = ops.conv3d_k3_rows(ext, packed, rows // 2, stride=2, row_offset=2)
         else:
             ext = par.exchange_row_halo(x, 1, 1, dim=3)
-            y, _ = ops.conv3d_k3(ext, packed, 1)
-            y = y[:, :, :, 1:-1].contiguous()
-        sums = par.allreduce_gn_sums(ops.gn_stats(y))
+            y, sums = ops.conv3d_k3_rows(ext, packed, rows, stride=1, row_offset=1)
+        # the row-window kernels produce only this band's rows, so their fused statistics are the band's statistics
+        sums = par.allreduce_gn_sums(sums)
         # gn_apply derives mean/var from (sums, elements of THIS tensor): rescale the global sums so that the band's
         # element count reproduces the statistics of the whole volume
         sums = sums * (float(y.shape[3]) / float(full_rows))
@@ -408,26 +407,25 @@ class cmfsm(nn.Module):
     def _classify_band(self, head, x, rows):
         t = self._cg_band(head[0], x, rows, 1, relu=True)
         ext = par.exchange_row_halo(t, 1, 1, dim=3)
-        y, _ = ops.conv3d_k3(ext, self._pack(head[2]), 1)
-        return y[:, 0, :, 1:-1].contiguous()
+        y, _ = ops.conv3d_k3_rows(ext, self._pack(head[2]), t.shape[3], stride=1, row_offset=1, want_stats=False)
+        return y[:, 0]
 
     # 2-D extractor on a row band: every 3x3 conv exchanges `dilation` halo rows (stride 2: two top rows), every
     # GroupNorm all-reduces its sums; the SPP pools are computed per band (bands are multiples of 64 rows at 1/4
     # resolution, so every pooling window lies inside one band) and the tiny pooled maps are all-gathered.
-    def _conv2_band(self, conv, x):
+    def _conv2_band(self, conv, x, want_stats=False):
+        """Returns (y, gn_sums of this band or None)."""
         k, s, d = conv.kernel_size[0], conv.stride[0], conv.dilation[0]
         packed = self._pack(conv)
         if k == 1:
-            return ops.conv2d(x, packed, 1, s, 1)[0]
+            return ops.conv2d(x, packed, 1, s, 1, want_stats)
         if s == 2:
-            y, _ = ops.conv2d(par.exchange_row_halo(x, 2, 0, dim=2), packed, 3, 2, 1)
-            return y[:, :, 1:1 + x.shape[2] // 2].contiguous()
-        y, _ = ops.conv2d(par.exchange_row_halo(x, d, d, dim=2), packed, 3, 1, d)
-        return y[:, :, d:-d].contiguous()
+            return ops.conv2d_rows(par.exchange_row_halo(x, 2, 0, dim=2), packed, 3, x.shape[2] // 2, 2, 1, 2, want_stats)
+        return ops.conv2d_rows(par.exchange_row_halo(x, d, d, dim=2), packed, 3, x.shape[2], 1, d, d, want_stats)
 
     def _cg2_band(self, block, x, full_rows, residual=None, relu=False):
-        y = self._conv2_band(block[0], x)
-        sums = par.allreduce_gn_sums(ops.gn_stats(y)) * (float(y.shape[2]) / float(full_rows))
+        y, sums = self._conv2_band(block[0], x, True)
+        sums = par.allreduce_gn_sums(sums) * (float(y.shape[2]) / float(full_rows))
         return ops.gn_apply(y, sums, block[1].weight, block[1].bias, residual, relu, out=y)
 
     def _features_band(self, both, r0, r1):
@@ -438,9 +436,9 @@ class cmfsm(nn.Module):
         o = self._cg2_band(fe.firstconv[0], x, H, relu=True)
         o = self._cg2_band(fe.firstconv[2], o, H, relu=True)
         o = self._cg2_band(fe.firstconv[4], o, H, relu=True)
-        full = self._conv2_band(fe.firstconv[6], o)
+        full, fsums = self._conv2_band(fe.firstconv[6], o, True)
         gn0 = fe.secondconv[0]
-        sums = par.allreduce_gn_sums(ops.gn_stats(full)) * (float(full.shape[2]) / float(H))
+        sums = par.allreduce_gn_sums(fsums) * (float(full.shape[2]) / float(H))
         o = ops.gn_apply(full, sums, gn0.weight, gn0.bias, None, True)
         o = self._cg2_band(fe.secondconv[2], o, H // 2, relu=True)
         o = self._cg2_band(fe.secondconv[4], o, H // 2, relu=True)
@@ -457,7 +455,7 @@ class cmfsm(nn.Module):
         b1, b2, b3, b4 = [self._cg2(getattr(fe, "branch%d" % (i + 1))[1], p, relu=True) for i, p in enumerate(pooled)]
         cat = ops.spp_upsample_concat(raw, skip, b4, b3, b2, b1, full_rows=h, row_offset=r0)
         o = self._cg2_band(fe.lastconv[0], cat, h, relu=True)
-        return self._conv2_band(fe.lastconv[2], o), full
+        return self._conv2_band(fe.lastconv[2], o)[0], full
 
     @torch.no_grad()
     def forward_row_bands(self, left, right, gather=True):

@@ -44,6 +44,9 @@ SIGNATURES = {
     "cmfb200_spp_upsample_concat_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_gn_stats": [_P, _P, _I, _I, _LL, _P],
     "cmfb200_gn_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _F, _I, _P],
+    "cmfb200_conv2d_rows_fwd": [_P, _P, _P, _P] + [_I] * 10 + [_P],
+    "cmfb200_conv3d_k3_rows_fwd": [_P, _P, _P, _P] + [_I] * 9 + [_P],
+    "cmfb200_deconv3d_k3s2_rows_fwd": [_P, _P, _P, _P] + [_I] * 7 + [_P],
     "cmfb200_conv3d_cout1_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_gn_bwd": [_P] * 8 + [_I, _I, _I, _LL, _F, _P],
     "cmfb200_ctxmap_weights_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -185,6 +185,29 @@ def conv3d_k3(x, packed, stride=1, transposed=False, want_stats=False):
     return y, sums
 
 
+def conv3d_k3_rows(x, packed, out_rows, stride=1, transposed=False, row_offset=0, want_stats=True):
+    """Row-window conv for row-band sharding: `x` [B,Cin,D,H_in,W] carries halo rows; only the band's rows are produced.
+    conv: output row m reads input rows m*stride - 1 + row_offset + kh, `out_rows` output rows;
+    transposed: `out_rows` = number of INPUT rows that produce output (the last row of x may be a halo row)."""
+    _req(x, packed)
+    B, Cin, D, H, W = x.shape
+    Cout = packed.shape[2]
+    sums = _new_sums(B, Cout, x.device) if want_stats else None
+    L = _lib.load()
+    if transposed:
+        y = torch.empty((B, Cout, 2 * D, 2 * out_rows, 2 * W), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device), _timed("deconv3d_k3s2_fwd"):
+            _lib.check(L.cmfb200_deconv3d_k3s2_rows_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, out_rows, W,
+                                                        _stream()), "deconv3d_k3s2_rows_fwd")
+    else:
+        Do, Wo = (D - 1) // stride + 1, (W - 1) // stride + 1
+        y = torch.empty((B, Cout, Do, out_rows, Wo), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device), _timed("conv3d_k3_fwd"):
+            _lib.check(L.cmfb200_conv3d_k3_rows_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W, stride,
+                                                    row_offset, out_rows, _stream()), "conv3d_k3_rows_fwd")
+    return y, sums
+
+
 def pack_conv2d_weight(weight):
     """nn.Conv2d [Cout,Cin,k,k] -> packed [Cin,k*k,Cout]."""
     weight = weight.detach()
@@ -214,6 +237,22 @@ def conv2d(x, packed, ksize, stride=1, dilation=1, want_stats=False):
     with torch.cuda.device(x.device), _timed("conv2d_fwd"):
         _lib.check(_lib.load().cmfb200_conv2d_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, H, W, ksize, stride,
                                                   dilation, _stream()), "conv2d_fwd")
+    return y, sums
+
+
+def conv2d_rows(x, packed, ksize, out_rows, stride=1, dilation=1, row_offset=0, want_stats=True):
+    """Row-window 2-D conv for row-band sharding: `x` carries halo rows, output row m reads input rows
+    m*stride - pad + row_offset + kh*dilation; `out_rows` rows are produced (and only they enter the statistics)."""
+    _req(x, packed)
+    B, Cin, H, W = x.shape
+    Cout = packed.shape[2]
+    pad = (ksize // 2) * dilation
+    Wo = (W + 2 * pad - (ksize - 1) * dilation - 1) // stride + 1
+    sums = _new_sums(B, Cout, x.device) if want_stats else None
+    y = torch.empty((B, Cout, out_rows, Wo), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _timed("conv2d_fwd"):
+        _lib.check(_lib.load().cmfb200_conv2d_rows_fwd(_p(x), _p(packed), _p(y), _p(sums), B, Cin, Cout, H, W, ksize, stride,
+                                                       dilation, row_offset, out_rows, _stream()), "conv2d_rows_fwd")
     return y, sums
 
 

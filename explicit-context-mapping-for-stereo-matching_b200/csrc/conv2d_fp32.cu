@@ -35,7 +35,7 @@ struct Conv2dCfg {
 template <int KS, int S, int DIL, int COUT_TILE, int CC>
 __global__ void __launch_bounds__(kConvThreads, 2)
     conv2d_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
-                  double* __restrict__ gn_sums, int Cin, int Cout, int H, int W, int Ho, int Wo, int tiles_w) {
+                  double* __restrict__ gn_sums, int Cin, int Cout, int H, int W, int Ho, int Wo, int tiles_w, int hoff) {
     using G = Conv2dCfg<KS, S, DIL, COUT_TILE>;
     constexpr int CPT = G::CPT;
     constexpr int STAGE = CC * (G::PATCH + G::WSL);  // floats per pipeline stage
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     // ---- staging slots of this thread (same for every input channel)
     int goff[G::NSLOT], soff[G::NSLOT];
     bool ok[G::NSLOT];
-    const int hi0 = h0 * S - PAD, wi0 = w0 * S - PAD;
+    const int hi0 = h0 * S - PAD + hoff, wi0 = w0 * S - PAD;  // hoff: row window (row-band sharding)
 #pragma unroll
     for (int j = 0; j < G::NSLOT; ++j) {
         const int e = tid + j * kConvThreads;
@@ -210,7 +210,7 @@ struct Conv2dR2Cfg {
 template <int DIL, int COUT_TILE, int CC, int TW>
 __global__ void __launch_bounds__(kConvThreads, 2)
     conv2d_r2_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
-                     double* __restrict__ gn_sums, int Cin, int Cout, int H, int W, int tiles_w) {
+                     double* __restrict__ gn_sums, int Cin, int Cout, int H, int W, int tiles_w, int hoff, int Ho) {
     using G = Conv2dR2Cfg<DIL, COUT_TILE, TW>;
     constexpr int CPT = G::CPT;
     constexpr int STAGE = CC * (G::PATCH + G::WSL);
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 
     int goff[G::NSLOT], soff[G::NSLOT];
     bool ok[G::NSLOT];
-    const int hi0 = h0 - DIL, wi0 = w0 - DIL;
+    const int hi0 = h0 - DIL + hoff, wi0 = w0 - DIL;  // hoff / Ho: row window (row-band sharding)
 #pragma unroll
     for (int j = 0; j < G::NSLOT; ++j) {
         const int e = tid + j * kConvThreads;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 #pragma unroll
             for (int v = 0; v < kVPT; ++v) acc[r][c][v] = (c & 1) ? acc2[r][c >> 1][v].y : acc2[r][c >> 1][v].x;
     const int ow = w0 + qx * kVPT;
-    const size_t out_plane = in_plane;  // stride 1, "same" padding
+    const size_t out_plane = (size_t)Ho * W;  // stride 1, "same" padding along W; Ho rows (row window)
     double s[CPT], ss[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int oh = h0 + r0 + r * DIL;
-        if (oh < H && ow < W) {
+        if (oh < Ho && ow < W) {
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
                 const int co = cb + cg * CPT + c;
@@ -366,33 +366,39 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     if (gn_sums != nullptr) gn_epilogue<COUT_TILE, CPT>(s, ss, cg, smem, gn_sums, b, Cout, cb);
 }
 
+struct RowWin2 {  // row window for row-band sharding (see conv3d_fp32.cu): hoff = 0 / Ho = -1 = ordinary convolution
+    int hoff = 0, Ho = -1;
+};
+
 template <int DIL, int COUT_TILE, int CC, int TW>
 static int launch_conv2d_r2_tw(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int Cout, int H, int W,
-                            cudaStream_t st) {
+                            cudaStream_t st, RowWin2 rw) {
     using G = Conv2dR2Cfg<DIL, COUT_TILE, TW>;
     constexpr size_t smem = 2 * (size_t)CC * (G::PATCH + G::WSL) * sizeof(float);
     static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
-    const int tiles_w = (int)cdiv(W, TW), tiles_h = (int)cdiv(H, G::TH);
+    const int Ho = rw.Ho >= 0 ? rw.Ho : H;
+    const int tiles_w = (int)cdiv(W, TW), tiles_h = (int)cdiv(Ho, G::TH);
     auto kern = conv2d_r2_kernel<DIL, COUT_TILE, CC, TW>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(Cout / COUT_TILE), (unsigned)B);
     CMF_REQUIRE(grid.z <= 65535, "conv2d: batch too large");
-    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, Cout, H, W, tiles_w);
+    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, Cout, H, W, tiles_w, rw.hoff, Ho);
     CMF_LAUNCH_CHECK("conv2d_r2_kernel");
     return CMFB200_OK;
 }
 
 template <int DIL, int COUT_TILE, int CC>
 static int launch_conv2d_r2(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int Cout, int H, int W,
-                            cudaStream_t st) {
+                            cudaStream_t st, RowWin2 rw) {
     // tile width 32 or 16: whichever wastes fewer lanes on the ragged edges (w = 240 = 15 x 16 = 7.5 x 32)
-    const long long c32 = cdiv(W, 32) * 32 * cdiv(H, Conv2dR2Cfg<DIL, COUT_TILE, 32>::TH) * Conv2dR2Cfg<DIL, COUT_TILE, 32>::TH;
-    const long long c16 = cdiv(W, 16) * 16 * cdiv(H, Conv2dR2Cfg<DIL, COUT_TILE, 16>::TH) * Conv2dR2Cfg<DIL, COUT_TILE, 16>::TH;
+    const long long Hr = rw.Ho >= 0 ? rw.Ho : H;
+    const long long c32 = cdiv(W, 32) * 32 * cdiv(Hr, Conv2dR2Cfg<DIL, COUT_TILE, 32>::TH) * Conv2dR2Cfg<DIL, COUT_TILE, 32>::TH;
+    const long long c16 = cdiv(W, 16) * 16 * cdiv(Hr, Conv2dR2Cfg<DIL, COUT_TILE, 16>::TH) * Conv2dR2Cfg<DIL, COUT_TILE, 16>::TH;
     // measured at w=240 (6.7 % fewer lanes): 16-wide tiles are 1.4 % SLOWER here (smaller halo reuse, 2-way bank
     // conflicts on the 80-byte row pitch), so they are only used when they save more than 10 %
     if ((DIL == 1 && c16 < c32) || c16 * 10 < c32 * 9)
-        return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 16>(x, wp, y, gn, B, Cin, Cout, H, W, st);
-    return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 32>(x, wp, y, gn, B, Cin, Cout, H, W, st);
+        return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 16>(x, wp, y, gn, B, Cin, Cout, H, W, st, rw);
+    return launch_conv2d_r2_tw<DIL, COUT_TILE, CC, 32>(x, wp, y, gn, B, Cin, Cout, H, W, st, rw);
 }
 
 // weight packing: [Cout][Cin][KS*KS] -> [Cin][KS*KS][Cout]
@@ -409,38 +415,39 @@ __global__ void pack_conv2d_weight_kernel(const float* __restrict__ w, float* __
 
 template <int KS, int S, int DIL, int COUT_TILE, int CC>
 static int launch_conv2d(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int Cout, int H, int W,
-                         cudaStream_t st) {
+                         cudaStream_t st, RowWin2 rw) {
     using G = Conv2dCfg<KS, S, DIL, COUT_TILE>;
     constexpr size_t smem = 2 * (size_t)CC * (G::PATCH + G::WSL) * sizeof(float);
     static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
     constexpr int PAD = (KS / 2) * DIL;
-    const int Ho = (H + 2 * PAD - (KS - 1) * DIL - 1) / S + 1, Wo = (W + 2 * PAD - (KS - 1) * DIL - 1) / S + 1;
+    const int Ho = rw.Ho >= 0 ? rw.Ho : (H + 2 * PAD - (KS - 1) * DIL - 1) / S + 1;
+    const int Wo = (W + 2 * PAD - (KS - 1) * DIL - 1) / S + 1;
     const int tiles_w = (int)cdiv(Wo, kTW), tiles_h = (int)cdiv(Ho, G::TH);
     auto kern = conv2d_kernel<KS, S, DIL, COUT_TILE, CC>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(Cout / COUT_TILE), (unsigned)B);
     CMF_REQUIRE(grid.z <= 65535, "conv2d: batch too large");
-    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, Cout, H, W, Ho, Wo, tiles_w);
+    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, Cout, H, W, Ho, Wo, tiles_w, rw.hoff);
     CMF_LAUNCH_CHECK("conv2d_kernel");
     return CMFB200_OK;
 }
 
 template <int KS, int S, int DIL>
 static int dispatch_conv2d(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int Cout, int H,
-                           int W, cudaStream_t st) {
+                           int W, cudaStream_t st, RowWin2 rw) {
     if (Cin == 3) {
         if constexpr (KS == 3 && S == 1 && DIL == 1) {
-            if (Cout == 32) return launch_conv2d<3, 1, 1, 32, 3>(x, wp, y, gn, B, Cin, Cout, H, W, st);
+            if (Cout == 32) return launch_conv2d<3, 1, 1, 32, 3>(x, wp, y, gn, B, Cin, Cout, H, W, st, rw);
         }
         CMF_REQUIRE(false, "conv2d: Cin=3 only for the 3x3 s1 stem conv with Cout=32");
     }
     CMF_REQUIRE(Cin % 8 == 0, "conv2d: Cin=%d must be 3 or a multiple of 8", Cin);
     if constexpr (KS == 3 && S == 1 && DIL <= 2) {  // the bulk of the MACs: two output rows per thread
-        if (Cout == 32) return launch_conv2d_r2<DIL, 32, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st);
-        if (Cout % 64 == 0) return launch_conv2d_r2<DIL, 64, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st);
+        if (Cout == 32) return launch_conv2d_r2<DIL, 32, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st, rw);
+        if (Cout % 64 == 0) return launch_conv2d_r2<DIL, 64, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st, rw);
     }
-    if (Cout == 32) return launch_conv2d<KS, S, DIL, 32, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st);
-    if (Cout % 64 == 0) return launch_conv2d<KS, S, DIL, 64, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st);
+    if (Cout == 32) return launch_conv2d<KS, S, DIL, 32, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st, rw);
+    if (Cout % 64 == 0) return launch_conv2d<KS, S, DIL, 64, 8>(x, wp, y, gn, B, Cin, Cout, H, W, st, rw);
     CMF_REQUIRE(false, "conv2d: Cout=%d must be 32 or a multiple of 64", Cout);
 }
 
@@ -459,16 +466,32 @@ extern "C" int cmfb200_pack_conv2d_weight(const float* weight, float* packed, in
     return CMFB200_OK;
 }
 
+static int conv2d_any(const float* x, const float* packed_w, float* y, double* gn_sums, int B, int Cin, int Cout, int H,
+                      int W, int ksize, int stride, int dilation, RowWin2 rw, cudaStream_t st) {
+    if (ksize == 3 && stride == 1 && dilation == 1) return dispatch_conv2d<3, 1, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st, rw);
+    if (ksize == 3 && stride == 2 && dilation == 1) return dispatch_conv2d<3, 2, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st, rw);
+    if (ksize == 3 && stride == 1 && dilation == 2) return dispatch_conv2d<3, 1, 2>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st, rw);
+    if (ksize == 3 && stride == 1 && dilation == 4) return dispatch_conv2d<3, 1, 4>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st, rw);
+    if (ksize == 1 && stride == 1 && dilation == 1) return dispatch_conv2d<1, 1, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st, rw);
+    if (ksize == 1 && stride == 2 && dilation == 1) return dispatch_conv2d<1, 2, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st, rw);
+    CMF_REQUIRE(false, "conv2d_fwd: unsupported (ksize=%d, stride=%d, dilation=%d)", ksize, stride, dilation);
+}
+
 extern "C" int cmfb200_conv2d_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B, int Cin,
                                   int Cout, int H, int W, int ksize, int stride, int dilation, void* stream) {
     CMF_REQUIRE(x && packed_w && y, "conv2d_fwd: null pointer");
     CMF_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "conv2d_fwd: non-positive dimension");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (ksize == 3 && stride == 1 && dilation == 1) return dispatch_conv2d<3, 1, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
-    if (ksize == 3 && stride == 2 && dilation == 1) return dispatch_conv2d<3, 2, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
-    if (ksize == 3 && stride == 1 && dilation == 2) return dispatch_conv2d<3, 1, 2>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
-    if (ksize == 3 && stride == 1 && dilation == 4) return dispatch_conv2d<3, 1, 4>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
-    if (ksize == 1 && stride == 1 && dilation == 1) return dispatch_conv2d<1, 1, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
-    if (ksize == 1 && stride == 2 && dilation == 1) return dispatch_conv2d<1, 2, 1>(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, st);
-    CMF_REQUIRE(false, "conv2d_fwd: unsupported (ksize=%d, stride=%d, dilation=%d)", ksize, stride, dilation);
+    return conv2d_any(x, packed_w, y, gn_sums, B, Cin, Cout, H, W, ksize, stride, dilation, RowWin2(), (cudaStream_t)stream);
+}
+
+extern "C" int cmfb200_conv2d_rows_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B, int Cin,
+                                       int Cout, int H_in, int W, int ksize, int stride, int dilation, int h_offset,
+                                       int H_out, void* stream) {
+    CMF_REQUIRE(x && packed_w && y, "conv2d_rows_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && H_in > 0 && W > 0 && H_out > 0 && h_offset >= 0,
+                "conv2d_rows_fwd: bad dimension");
+    RowWin2 rw;
+    rw.hoff = h_offset;
+    rw.Ho = H_out;
+    return conv2d_any(x, packed_w, y, gn_sums, B, Cin, Cout, H_in, W, ksize, stride, dilation, rw, (cudaStream_t)stream);
 }

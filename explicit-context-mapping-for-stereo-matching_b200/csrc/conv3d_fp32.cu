@@ -25,7 +25,8 @@ namespace cmfb200 {
 template <int COUT, int CPT, int S, int CC, int TW>
 __global__ void __launch_bounds__(kConvThreads, 2)
     conv3d_k3_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
-                     double* __restrict__ gn_sums, int Cin, int D, int H, int W, int Do, int Ho, int Wo, int tiles_w) {
+                     double* __restrict__ gn_sums, int Cin, int D, int H, int W, int Do, int Ho, int Wo, int tiles_w,
+                     int hoff) {
     using T = ConvTile<COUT, CPT, TW>;
     constexpr int PD = (T::TD - 1) * S + 3, PH = (T::TH - 1) * S + 3, PW = (TW - 1) * S + 3;
     constexpr int PWP = (PW + 3) & ~3;
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     const size_t in_plane = (size_t)H * W;
     const size_t in_vol = (size_t)D * in_plane;
     const float* xb = x + (size_t)b * Cin * in_vol;
-    const int di0 = d0 * S - 1, hi0 = h0 * S - 1, wi0 = w0 * S - 1;
+    const int di0 = d0 * S - 1, hi0 = h0 * S - 1 + hoff, wi0 = w0 * S - 1;  // hoff: row window (row-band sharding)
 
     // ---- staging slots of this thread (identical for every input channel): computed once
     int goff[NSLOT], soff[NSLOT];
@@ -227,7 +228,7 @@ struct Conv3dR2Cfg {
 template <int COUT, int CC, int TW>
 __global__ void __launch_bounds__(kConvThreads, 2)
     conv3d_k3_r2_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
-                        double* __restrict__ gn_sums, int Cin, int D, int H, int W, int tiles_w) {
+                        double* __restrict__ gn_sums, int Cin, int D, int H, int W, int tiles_w, int hoff, int Ho) {
     using G = Conv3dR2Cfg<COUT, TW>;
     constexpr int CPT = G::CPT;
     constexpr int STAGE = CC * (G::PATCH + G::WSL);
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     const size_t in_plane = (size_t)H * W;
     const size_t in_vol = (size_t)D * in_plane;
     const float* xb = x + (size_t)b * Cin * in_vol;
-    const int di0 = d0 - 1, hi0 = h0 - 1, wi0 = w0 - 1;
+    const int di0 = d0 - 1, hi0 = h0 - 1 + hoff, wi0 = w0 - 1;  // hoff / Ho: row window (row-band sharding)
 
     int goff[G::NSLOT], soff[G::NSLOT];
     bool ok[G::NSLOT];
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     }
 
     const int od = d0 + td, ow = w0 + qx * kVPT;
-    const size_t out_plane = in_plane;
+    const size_t out_plane = (size_t)Ho * W;
     double s[CPT], ss[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int oh = h0 + r0 + r;
-        if (od < D && oh < H && ow < W) {
+        if (od < D && oh < Ho && ow < W) {
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
                 float a[kVPT];
@@ -380,18 +381,25 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     if (gn_sums != nullptr) gn_epilogue<COUT, CPT>(s, ss, cg, smem, gn_sums, b);
 }
 
+// Row window (row-band sharding of one image pair): the input holds halo rows, output row m reads input rows
+// m*S - 1 + hoff + kh and only Ho output rows exist.  hoff = 0 / Ho = -1: the ordinary padded convolution.
+struct RowWin {
+    int hoff = 0, Ho = -1;
+};
+
 template <int COUT, int CC, int TW>
 static int launch_conv_r2(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
-                          cudaStream_t st) {
+                          cudaStream_t st, RowWin rw = RowWin()) {
     using G = Conv3dR2Cfg<COUT, TW>;
     constexpr size_t smem = 2 * (size_t)CC * (G::PATCH + G::WSL) * sizeof(float);
     static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
-    const int tiles_w = (int)cdiv(W, TW), tiles_h = (int)cdiv(H, G::TH);
+    const int Ho = rw.Ho >= 0 ? rw.Ho : H;
+    const int tiles_w = (int)cdiv(W, TW), tiles_h = (int)cdiv(Ho, G::TH);
     auto kern = conv3d_k3_r2_kernel<COUT, CC, TW>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)cdiv(D, G::TD), (unsigned)B);
     CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d: grid too large");
-    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, D, H, W, tiles_w);
+    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, D, H, W, tiles_w, rw.hoff, Ho);
     CMF_LAUNCH_CHECK("conv3d_k3_r2_kernel");
     return CMFB200_OK;
 }
@@ -399,13 +407,14 @@ static int launch_conv_r2(const float* x, const float* wp, float* y, double* gn,
 // stride-1, Cout in {32,64}: two-rows-per-thread kernel with the tile width that wastes fewer lanes
 template <int COUT, int CC>
 static int launch_conv_r2_best(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
-                               cudaStream_t st) {
+                               cudaStream_t st, RowWin rw = RowWin()) {
     using G32 = Conv3dR2Cfg<COUT, 32>;
     using G16 = Conv3dR2Cfg<COUT, 16>;
-    const long long c32 = cdiv(W, 32) * 32 * cdiv(H, G32::TH) * G32::TH;
-    const long long c16 = cdiv(W, 16) * 16 * cdiv(H, G16::TH) * G16::TH;
-    if (c16 < c32) return launch_conv_r2<COUT, CC, 16>(x, wp, y, gn, B, Cin, D, H, W, st);
-    return launch_conv_r2<COUT, CC, 32>(x, wp, y, gn, B, Cin, D, H, W, st);
+    const long long Hr = rw.Ho >= 0 ? rw.Ho : H;
+    const long long c32 = cdiv(W, 32) * 32 * cdiv(Hr, G32::TH) * G32::TH;
+    const long long c16 = cdiv(W, 16) * 16 * cdiv(Hr, G16::TH) * G16::TH;
+    if (c16 < c32) return launch_conv_r2<COUT, CC, 16>(x, wp, y, gn, B, Cin, D, H, W, st, rw);
+    return launch_conv_r2<COUT, CC, 32>(x, wp, y, gn, B, Cin, D, H, W, st, rw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -418,7 +427,7 @@ static int launch_conv_r2_best(const float* x, const float* wp, float* y, double
 template <int COUT, int CPT, int CC>
 __global__ void __launch_bounds__(kConvThreads, 2)
     deconv3d_k3s2_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y,
-                         double* __restrict__ gn_sums, int Cin, int D, int H, int W, int tiles_w) {
+                         double* __restrict__ gn_sums, int Cin, int D, int H, int W, int tiles_w, int Hc) {
     using T = ConvTile<COUT, CPT>;
     static_assert(T::TD == 1, "deconv tile is one depth slice");
     constexpr int PD = 2, PH = T::TH + 1, PW = kTW + 1;
@@ -559,7 +568,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     for (int c = 0; c < CPT; ++c)
 #pragma unroll
         for (int v = 0; v < NO; ++v) acc[c][v] = (c & 1) ? acc2[c >> 1][v].y : acc2[c >> 1][v].x;
-    const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+    const int Do = 2 * D, Ho = 2 * Hc, Wo = 2 * W;  // Hc: input rows that produce output (row bands: H - 1 halo row)
     const int od = 2 * id + pd, oh = 2 * (ih0 + th) + ph, ow = 2 * (iw0 + qx * kVPT);
     const size_t out_plane = (size_t)Ho * Wo;
     double s[CPT], ss[CPT];
@@ -605,19 +614,19 @@ __global__ void pack_conv3d_weight_kernel(const float* __restrict__ w, float* __
 
 template <int COUT, int CPT, int S, int CC, int TW>
 static int launch_conv(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
-                       cudaStream_t st) {
+                       cudaStream_t st, RowWin rw = RowWin()) {
     using T = ConvTile<COUT, CPT, TW>;
     constexpr int PD = (T::TD - 1) * S + 3, PH = (T::TH - 1) * S + 3, PW = (TW - 1) * S + 3;
     constexpr int PWP = (PW + 3) & ~3;
     constexpr size_t smem = 2 * (size_t)CC * (PD * PH * PWP + 27 * COUT) * sizeof(float);
     static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
-    const int Do = (D - 1) / S + 1, Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+    const int Do = (D - 1) / S + 1, Ho = rw.Ho >= 0 ? rw.Ho : (H - 1) / S + 1, Wo = (W - 1) / S + 1;
     const int tiles_w = (int)cdiv(Wo, TW), tiles_h = (int)cdiv(Ho, T::TH);
     auto kern = conv3d_k3_kernel<COUT, CPT, S, CC, TW>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)cdiv(Do, T::TD), (unsigned)B);
     CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d: grid too large");
-    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, D, H, W, Do, Ho, Wo, tiles_w);
+    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, D, H, W, Do, Ho, Wo, tiles_w, rw.hoff);
     CMF_LAUNCH_CHECK("conv3d_k3_kernel");
     return CMFB200_OK;
 }
@@ -625,26 +634,27 @@ static int launch_conv(const float* x, const float* wp, float* y, double* gn, in
 // picks the tile width (32 or 16 voxels) that wastes fewer lanes on the ragged right / bottom edge
 template <int COUT, int CPT, int S, int CC>
 static int launch_conv_best(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
-                            cudaStream_t st) {
-    const long long Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+                            cudaStream_t st, RowWin rw = RowWin()) {
+    const long long Ho = rw.Ho >= 0 ? rw.Ho : (H - 1) / S + 1, Wo = (W - 1) / S + 1;
     const long long c32 = cdiv(Wo, 32) * 32 * cdiv(Ho, ConvTile<COUT, CPT, 32>::TH) * ConvTile<COUT, CPT, 32>::TH;
     const long long c16 = cdiv(Wo, 16) * 16 * cdiv(Ho, ConvTile<COUT, CPT, 16>::TH) * ConvTile<COUT, CPT, 16>::TH;
-    if (c16 < c32) return launch_conv<COUT, CPT, S, CC, 16>(x, wp, y, gn, B, Cin, D, H, W, st);
-    return launch_conv<COUT, CPT, S, CC, 32>(x, wp, y, gn, B, Cin, D, H, W, st);
+    if (c16 < c32) return launch_conv<COUT, CPT, S, CC, 16>(x, wp, y, gn, B, Cin, D, H, W, st, rw);
+    return launch_conv<COUT, CPT, S, CC, 32>(x, wp, y, gn, B, Cin, D, H, W, st, rw);
 }
 
 template <int COUT, int CPT, int CC>
 static int launch_deconv(const float* x, const float* wp, float* y, double* gn, int B, int Cin, int D, int H, int W,
-                         cudaStream_t st) {
+                         cudaStream_t st, int Hc = -1) {
     using T = ConvTile<COUT, CPT>;
     constexpr size_t smem = 2 * (size_t)CC * (2 * (T::TH + 1) * 36 + 12 * COUT) * sizeof(float);
     static_assert(smem <= 110 * 1024, "two CTAs per SM must fit");
-    const int tiles_w = (int)cdiv(W, kTW), tiles_h = (int)cdiv(H, T::TH);
+    if (Hc < 0) Hc = H;
+    const int tiles_w = (int)cdiv(W, kTW), tiles_h = (int)cdiv(Hc, T::TH);
     auto kern = deconv3d_k3s2_kernel<COUT, CPT, CC>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(D * 4), (unsigned)B);
     CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "deconv3d: grid too large");
-    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, D, H, W, tiles_w);
+    kern<<<grid, kConvThreads, smem, st>>>(x, wp, y, gn, Cin, D, H, W, tiles_w, Hc);
     CMF_LAUNCH_CHECK("deconv3d_k3s2_kernel");
     return CMFB200_OK;
 }
@@ -667,28 +677,48 @@ extern "C" int cmfb200_pack_conv3d_weight(const float* weight, float* packed, in
     return CMFB200_OK;
 }
 
+static int conv3d_k3_dispatch(const float* x, const float* packed_w, float* y, double* gn_sums, int B, int Cin, int Cout,
+                             int D, int H, int W, int stride, RowWin rw, cudaStream_t st) {
+    static const bool one_row = getenv("CMFB200_CONV3D_ONE_ROW") != nullptr;  // A/B switch for profiling
+    if (Cout == 32 && stride == 1 && !one_row) return launch_conv_r2_best<32, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
+    if (Cout == 64 && stride == 1 && !one_row) return launch_conv_r2_best<64, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
+    if (Cout == 32 && stride == 1) return launch_conv_best<32, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
+    if (Cout == 64 && stride == 1) return launch_conv_best<64, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
+    if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
+    if (Cout == 64 && stride == 2) return launch_conv<64, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
+    if (Cout == 1 && stride == 1) {
+        if (gn_sums == nullptr && !one_row && rw.Ho < 0) {  // classifier tail: TMA-staged 4x4-outputs-per-thread kernel
+            const int rc = conv3d_cout1_fp32_dispatch(x, packed_w, y, B, Cin, D, H, W, st);
+            if (rc >= 0) return rc;
+        }
+        return launch_conv_best<1, 1, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
+    }
+    CMF_REQUIRE(false, "conv3d_k3_fwd: unsupported (Cout=%d, stride=%d); Cout in {1,32,64}", Cout, stride);
+}
+
 extern "C" int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B, int Cin,
                                      int Cout, int D, int H, int W, int stride, void* stream) {
     CMF_REQUIRE(x && packed_w && y, "conv3d_k3_fwd: null pointer");
     CMF_REQUIRE(B > 0 && Cin > 0 && D > 0 && H > 0 && W > 0, "conv3d_k3_fwd: non-positive dimension");
     CMF_REQUIRE(Cin % 8 == 0, "conv3d_k3_fwd: Cin=%d must be a multiple of 8", Cin);
     CMF_REQUIRE(stride == 1 || stride == 2, "conv3d_k3_fwd: stride=%d not in {1,2}", stride);
-    cudaStream_t st = (cudaStream_t)stream;
-    static const bool one_row = getenv("CMFB200_CONV3D_ONE_ROW") != nullptr;  // A/B switch for profiling
-    if (Cout == 32 && stride == 1 && !one_row) return launch_conv_r2_best<32, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 64 && stride == 1 && !one_row) return launch_conv_r2_best<64, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 32 && stride == 1) return launch_conv_best<32, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 64 && stride == 1) return launch_conv_best<64, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 64 && stride == 2) return launch_conv<64, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    if (Cout == 1 && stride == 1) {
-        if (gn_sums == nullptr && !one_row) {  // classifier tail: TMA-staged 4x4-outputs-per-thread kernel
-            const int rc = conv3d_cout1_fp32_dispatch(x, packed_w, y, B, Cin, D, H, W, st);
-            if (rc >= 0) return rc;
-        }
-        return launch_conv_best<1, 1, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
-    }
-    CMF_REQUIRE(false, "conv3d_k3_fwd: unsupported (Cout=%d, stride=%d); Cout in {1,32,64}", Cout, stride);
+    return conv3d_k3_dispatch(x, packed_w, y, gn_sums, B, Cin, Cout, D, H, W, stride, RowWin(), (cudaStream_t)stream);
+}
+
+extern "C" int cmfb200_conv3d_k3_rows_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B,
+                                          int Cin, int Cout, int D, int H_in, int W, int stride, int h_offset, int H_out,
+                                          void* stream) {
+    CMF_REQUIRE(x && packed_w && y, "conv3d_k3_rows_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && Cin > 0 && D > 0 && H_in > 0 && W > 0 && H_out > 0, "conv3d_k3_rows_fwd: non-positive dimension");
+    CMF_REQUIRE(Cin % 8 == 0, "conv3d_k3_rows_fwd: Cin=%d must be a multiple of 8", Cin);
+    CMF_REQUIRE(stride == 1 || stride == 2, "conv3d_k3_rows_fwd: stride=%d not in {1,2}", stride);
+    CMF_REQUIRE(h_offset >= 0 && (H_out - 1) * stride + h_offset - 1 < H_in + 1,
+                "conv3d_k3_rows_fwd: row window (offset %d, %d rows, stride %d) leaves the %d input rows", h_offset, H_out,
+                stride, H_in);
+    RowWin rw;
+    rw.hoff = h_offset;
+    rw.Ho = H_out;
+    return conv3d_k3_dispatch(x, packed_w, y, gn_sums, B, Cin, Cout, D, H_in, W, stride, rw, (cudaStream_t)stream);
 }
 
 extern "C" int cmfb200_deconv3d_k3s2_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B,
@@ -701,4 +731,17 @@ extern "C" int cmfb200_deconv3d_k3s2_fwd(const float* x, const float* packed_w, 
     if (Cout == 32) return launch_deconv<32, 8, 8>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
     if (Cout == 64) return launch_deconv<64, 8, 8>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st);
     CMF_REQUIRE(false, "deconv3d_k3s2_fwd: unsupported Cout=%d (32 or 64)", Cout);
+}
+
+extern "C" int cmfb200_deconv3d_k3s2_rows_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B,
+                                              int Cin, int Cout, int D, int H_in, int H_compute, int W, void* stream) {
+    CMF_REQUIRE(x && packed_w && y, "deconv3d_k3s2_rows_fwd: null pointer");
+    CMF_REQUIRE(B > 0 && Cin > 0 && D > 0 && H_in > 0 && W > 0, "deconv3d_k3s2_rows_fwd: non-positive dimension");
+    CMF_REQUIRE(Cin % 8 == 0, "deconv3d_k3s2_rows_fwd: Cin=%d must be a multiple of 8", Cin);
+    CMF_REQUIRE(H_compute > 0 && H_compute <= H_in, "deconv3d_k3s2_rows_fwd: H_compute=%d outside (0, %d]", H_compute, H_in);
+    CMF_REQUIRE(D * 4 <= 65535, "deconv3d_k3s2_rows_fwd: depth too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cout == 32) return launch_deconv<32, 8, 8>(x, packed_w, y, gn_sums, B, Cin, D, H_in, W, st, H_compute);
+    if (Cout == 64) return launch_deconv<64, 8, 8>(x, packed_w, y, gn_sums, B, Cin, D, H_in, W, st, H_compute);
+    CMF_REQUIRE(false, "deconv3d_k3s2_rows_fwd: unsupported Cout=%d (32 or 64)", Cout);
 }

@@ -68,6 +68,18 @@ int cmfb200_conv3d_k3_fwd(const float* x, const float* packed_w, float* y, doubl
  * [1,Cin,3,3,3] (unpacked), grad_y [B,1,D,H,W] -> dx [B,Cin,D,H,W], dw [1,Cin,3,3,3] (zeroed here).  Cin = 32. */
 int cmfb200_conv3d_cout1_bwd(const float* x, const float* weight, const float* grad_y, float* dx, float* dw, int B,
                              int Cin, int D, int H, int W, void* stream);
+
+/* Row-window variants for row-band sharding of ONE image pair (cmf_b200.parallel): the input tensor carries
+ * halo rows received from the neighbouring ranks, and only the rows this rank owns are produced, so the GroupNorm
+ * sums fused into the epilogue cover exactly the band (no crop copy, no separate statistics pass).
+ *   conv:   x [B,Cin,D,H_in,W], y [B,Cout,Do,H_out,Wo]; output row m reads input rows m*stride - 1 + h_offset + kh
+ *           (h_offset = 1 with one halo row on top for stride 1, 2 with two halo rows for stride 2); rows outside
+ *           [0,H_in) read zero.  D and W are padded as usual.
+ *   deconv: x [B,Cin,D,H_in,W] whose LAST row may be a halo row, y [B,Cout,2D,2*H_compute,2W]. */
+int cmfb200_conv3d_k3_rows_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B, int Cin,
+                               int Cout, int D, int H_in, int W, int stride, int h_offset, int H_out, void* stream);
+int cmfb200_deconv3d_k3s2_rows_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B, int Cin,
+                                   int Cout, int D, int H_in, int H_compute, int W, void* stream);
 /* Transposed conv k3 s2 p1 op1: y: [B,Cout,2D,2H,2W].  Cout in {32,64}; same gn_sums contract. */
 int cmfb200_deconv3d_k3s2_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
                               int B, int Cin, int Cout, int D, int H, int W, void* stream);
@@ -124,6 +136,10 @@ int cmfb200_f32_to_c8_bf16(const float* x, void* y_c8, int B, int C, long long s
 int cmfb200_pack_conv2d_weight(const float* weight, float* packed, int Cout, int Cin, int ksize, void* stream);
 int cmfb200_conv2d_fwd(const float* x, const float* packed_w, float* y, double* gn_sums,
                        int B, int Cin, int Cout, int H, int W, int ksize, int stride, int dilation, void* stream);
+/* Row-window variant for row-band sharding (see cmfb200_conv3d_k3_rows_fwd): x [B,Cin,H_in,W] carries halo rows, y
+ * [B,Cout,H_out,Wo]; output row m reads input rows m*stride - pad + h_offset + kh*dilation. */
+int cmfb200_conv2d_rows_fwd(const float* x, const float* packed_w, float* y, double* gn_sums, int B, int Cin, int Cout,
+                            int H_in, int W, int ksize, int stride, int dilation, int h_offset, int H_out, void* stream);
 
 /* SPP tail of the feature extractor (cmfsm.py:152-170, 207-233).
  * pool: x [B,C,H,W] -> average pools with kernel = stride = 8/16/32/64 (floor mode): p8 [B,C,H/8,W/8] ... p64.
