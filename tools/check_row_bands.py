@@ -34,7 +34,8 @@ def main():
     g = torch.Generator().manual_seed(5)
     left = torch.rand(1, 3, args.height, args.width, generator=g).to(dev)
     right = torch.rand(1, 3, args.height, args.width, generator=g).to(dev)
-    outs = model.forward_row_bands(left, right)  # warm-up + result
+    model.forward_row_bands(left, right)  # warm-up (kernel loading, NCCL connections)
+    outs = model.forward_row_bands(left, right)  # second warm-up + result
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
@@ -45,7 +46,11 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    per_rank = [float(ms)]
     if world > 1:
+        gathered = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(gathered, ms)
+        per_rank = [float(t) for t in gathered]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         with torch.no_grad():
@@ -57,7 +62,7 @@ def main():
                 model(left, right)
             t1.record()
             torch.cuda.synchronize()
-        rep = {"world": world, "shape": [args.height, args.width], "maxdisp": args.maxdisp, "ms_sharded": float(ms),
+        rep = {"world": world, "shape": [args.height, args.width], "maxdisp": args.maxdisp, "ms_sharded": float(ms), "ms_per_rank": per_rank,
                "ms_single_gpu": t0.elapsed_time(t1) / args.steps}
         for i, (a, b) in enumerate(zip(outs, ref), 1):
             d = (a - b).abs()
