@@ -317,6 +317,9 @@ class cmfsm(nn.Module):
         cost0 = self._ig(self.dres0[2], cost0, relu=True)
         t = self._ig(self.dres1[0], cost0, relu=True)
         cost0, cost0_split = self._ig(self.dres1[2], t, residual=cost0, split=True)
+        if not hasattr(self, "dres3"):  # single-hourglass variants (cm_sub_*)
+            out1, _pre1, _post1 = self._hourglass_bf16(self.dres2, cost0, cost0_split, None, None, cost0, False)
+            return (self._classify_bf16(self.classif1, out1),)
         (out1, out1_split), pre1, post1 = self._hourglass_bf16(self.dres2, cost0, cost0_split, None, None, cost0, True)
         (out2, out2_split), _pre2, post2 = self._hourglass_bf16(self.dres3, out1, out1_split, pre1, post1, cost0, True)
         out3, _pre3, _post3 = self._hourglass_bf16(self.dres4, out2, out2_split, pre1, post2, cost0, False)
@@ -333,6 +336,8 @@ class cmfsm(nn.Module):
         cost0 = self._cg(self.dres1[2], t, residual=cost0)
         del t
         out1, pre1, post1 = self._hourglass(self.dres2, cost0, None, None, cost0)
+        if not hasattr(self, "dres3"):  # single-hourglass variants (cm_sub_*)
+            return (self._classify(self.classif1, out1),)
         out2, _pre2, post2 = self._hourglass(self.dres3, out1, pre1, post1, cost0)
         out3, _pre3, _post3 = self._hourglass(self.dres4, out2, pre1, post2, cost0)
         return (self._classify(self.classif1, out1), self._classify(self.classif2, out2),

@@ -267,3 +267,25 @@ def test_ragged_shape_and_other_maxdisp_vs_fp64_oracle():
         assert float(ours.max()) <= 2 * float(theirs.max()) + 2e-3
         assert float(ours.mean()) <= 2 * float(theirs.mean()) + 1e-4
         assert torch.isfinite(b16).all() and float((b16 - a).abs().mean()) < 1.0
+
+
+@pytest.mark.parametrize("variant", ["8", "16"])
+def test_cm_sub_variants_match_fp64_oracle(variant):
+    """cm_sub_8 / cm_sub_16 (single-hourglass ablations) on the CUDA kernels vs their fp64 CPU oracle."""
+    import cm_sub_oracle as orcs
+    from cmf.models import get_model
+
+    torch.manual_seed(gc.WEIGHT_SEED)
+    net = get_model("cm_sub_" + variant).to(DEV).eval()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    left, right = gc.seeded_pair(1, 256, 512, seed=5)
+    with torch.no_grad():
+        ours = net(left.to(DEV), right.to(DEV))
+    assert ours[0] is ours[1] and ours[1] is ours[2] and tuple(ours[0].shape) == (1, 256, 512)
+    r32 = orcs.forward(sd, left, right, variant, 192)[0]
+    r64 = orcs.forward({k: v.double() for k, v in sd.items()}, left.double(), right.double(), variant, 192)[0]
+    d_ours, d_ref = (ours[0].cpu().double() - r64).abs(), (r32.double() - r64).abs()
+    print("cm_sub_%s: ours-vs-fp64 max %.3e mean %.3e ; ref32-vs-fp64 max %.3e mean %.3e"
+          % (variant, d_ours.max(), d_ours.mean(), d_ref.max(), d_ref.mean()))
+    assert float(d_ours.mean()) <= 2 * float(d_ref.mean()) + 1e-3
+    assert float(d_ours.max()) <= 3 * float(d_ref.max()) + 5e-2

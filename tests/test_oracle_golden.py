@@ -4,6 +4,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 import torch
 
 import cmfsm_oracle as orc
@@ -132,6 +133,24 @@ def test_sub16_full_forward_against_reference(golden_dir):
         assert float(d.max()) < 0.5 and float(d.mean()) < 2e-2, (key, float(d.max()), float(d.mean()))
     torch.testing.assert_close(stages["w3"][0, :, ::8, ::8], g["w3_sub"], rtol=2e-3, atol=1e-3)
     torch.testing.assert_close(stages["c1"][0], g["c1_sub"], rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("variant", ["8", "16"])
+def test_cm_sub_forward_against_reference(golden_dir, variant):
+    """Single-hourglass ablations cm_sub_8 / cm_sub_16: oracle vs the outputs of the real reference modules."""
+    import cm_sub_oracle as orcs
+    from cmf.models import get_model
+
+    g = _npz(golden_dir, "cm_sub%s_c1.npz" % variant)
+    torch.manual_seed(gc.WEIGHT_SEED)
+    sd = get_model("cm_sub_" + variant).state_dict()
+    left, right = gc.seeded_pair(1, 256, 512)
+    stages = {}
+    p1, p2, p3 = orcs.forward(sd, left, right, variant, 192, stages)
+    assert p1 is p2 and p2 is p3 and tuple(p1.shape) == (1, 256, 512)
+    d = (p1[0, ::4, ::4] - g["pred1_sub"]).abs()
+    assert float(d.max()) < 0.5 and float(d.mean()) < 2e-2, (float(d.max()), float(d.mean()))
+    torch.testing.assert_close(stages["c1"][0, ::2, ::2, ::2], g["c1_sub"], rtol=1e-3, atol=1e-3)
 
 
 def test_shape_validation():
