@@ -2,18 +2,19 @@
 
 `get_model(name)` instantiates the class with NO arguments, exactly like the reference.  Scope of this
 build: `cmfsm` is the B200-native hot path; `cmfsm_sub_8` and `cmfsm_sub_16` (the 1/8- and
-1/16-resolution "downsample configs") and their single-hourglass ablations `cm_sub_8` / `cm_sub_16` run on the same
-kernels (inference).  The other five registered names of the reference (baselines / ablations) are listed so that a typo and an out-of-scope name produce different,
+1/16-resolution "downsample configs") and the single-hourglass ablations `cm_sub_4` / `cm_sub_8` / `cm_sub_16` run on the
+same kernels (inference).  The other four registered names of the reference (baselines / ablations) are listed so that a typo and an out-of-scope name produce different,
 explicit errors instead of the reference's bare `print`.
 """
 from cmf.models.cmfsm import cmfsm
 from cmf.models.cmfsm_sub_8 import cmfsm_sub_8
 from cmf.models.cmfsm_sub_16 import cmfsm_sub_16
+from cmf.models.cm_sub_4 import cm_sub_4
 from cmf.models.cm_sub_8 import cm_sub_8
 from cmf.models.cm_sub_16 import cm_sub_16
 
-_IMPLEMENTED = {"cmfsm": cmfsm, "cmfsm_sub_8": cmfsm_sub_8, "cmfsm_sub_16": cmfsm_sub_16, "cm_sub_8": cm_sub_8,
-                "cm_sub_16": cm_sub_16}
+_IMPLEMENTED = {"cmfsm": cmfsm, "cmfsm_sub_8": cmfsm_sub_8, "cmfsm_sub_16": cmfsm_sub_16, "cm_sub_4": cm_sub_4,
+                "cm_sub_8": cm_sub_8, "cm_sub_16": cm_sub_16}
 _REFERENCE_NAMES = ("cmf", "cmfsm", "bilinear_cmf", "cmfsm_sub_8", "cmfsm_sub_16", "bilinear_cmf_sub_8",
                     "bilinear_cmf_sub_16", "cm_sub_16", "cm_sub_8", "cm_sub_4")
 

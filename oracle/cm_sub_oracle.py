@@ -1,4 +1,4 @@
-"""CPU oracle of the single-hourglass ablations `cm_sub_8` / `cm_sub_16` -- TEST INFRASTRUCTURE ONLY.
+"""CPU oracle of the single-hourglass ablations `cm_sub_4` / `cm_sub_8` / `cm_sub_16` -- TEST INFRASTRUCTURE ONLY.
 
 Restates /root/reference/cmf/models/cm_sub_8.py and cm_sub_16.py: feature extractor + six_related_context_mapping of
 the corresponding cmfsm_sub_* variant, dres0 + dres1 + ONE hourglass + classif1, then the cost-volume mapping of
@@ -24,8 +24,13 @@ def aggregation_single(sd, cost):
 
 
 def forward(sd, left, right, variant, maxdisp=192, stages=None):
-    """variant: "8" or "16".  Returns (pred1, pred1, pred1), each [B,H,W]."""
-    fe = sub8.feature_extraction if variant == "8" else sub16.feature_extraction
+    """variant: "4", "8" or "16".  Returns (pred1, pred1, pred1), each [B,H,W].  cm_sub_4 keeps cmfsm's 1/4-resolution
+    extractor (with dilations 2 / 4 in layer3 / layer4, cm_sub_4.py:148-149) and the pre-GroupNorm stem output as hr."""
+    if variant == "4":
+        def fe(sd_, x):
+            return base.feature_extraction(sd_, x, dilations=(2, 4))
+    else:
+        fe = sub8.feature_extraction if variant == "8" else sub16.feature_extraction
     with torch.no_grad():
         sd = base.strip_module_prefix(sd)
         L, all_l = fe(sd, left)

@@ -69,7 +69,7 @@ def _layer(sd, key, x, blocks, stride, dilation):
 # ----------------------------------------------------------------------------------------------
 # a2: 2D feature extraction  (cmfsm.py:126-236)
 # ----------------------------------------------------------------------------------------------
-def feature_extraction(sd, x, prefix="feature_extraction", stages=None):
+def feature_extraction(sd, x, prefix="feature_extraction", stages=None, dilations=(1, 2)):
     """Returns (feature [B,32,H/4,W/4], all_feature [B,32,H,W]).  cmfsm.py:199-236.
 
     `all_feature` is the output of firstconv (pre-GN, pre-ReLU) -- cmfsm.py:138,200.
@@ -86,8 +86,8 @@ def feature_extraction(sd, x, prefix="feature_extraction", stages=None):
     second = o
     l1 = _layer(sd, p + ".layer1", o, 3, 1, 1)
     raw = _layer(sd, p + ".layer2", l1, 16, 2, 1)
-    l3 = _layer(sd, p + ".layer3", raw, 3, 1, 1)
-    skip = _layer(sd, p + ".layer4", l3, 3, 1, 2)
+    l3 = _layer(sd, p + ".layer3", raw, 3, 1, dilations[0])  # cm_sub_4 uses dilations (2, 4), cm_sub_4.py:148-149
+    skip = _layer(sd, p + ".layer4", l3, 3, 1, dilations[1])
     size = skip.shape[2:]
     branches = []
     for name, k in (("branch1", 64), ("branch2", 32), ("branch3", 16), ("branch4", 8)):

@@ -1,5 +1,5 @@
-"""Pins oracle/cm_sub_oracle.py against the UNMODIFIED reference `cm_sub_8` / `cm_sub_16` (run here) and writes
-tests/golden/cm_sub{8,16}_c1.npz + cm_sub{8,16}_state_dict.json.  TEST INFRASTRUCTURE.
+"""Pins oracle/cm_sub_oracle.py against the UNMODIFIED reference `cm_sub_4` / `cm_sub_8` / `cm_sub_16` (run here) and
+writes tests/golden/cm_sub{4,8,16}_c1.npz + cm_sub{4,8,16}_state_dict.json.  TEST INFRASTRUCTURE.
 Usage:  PYTHONPATH=oracle python oracle/gen_golden_cm_sub.py
 """
 import json
@@ -22,7 +22,7 @@ def main():
     get_model, _ = import_reference()
     import cm_sub_oracle as orc
 
-    for variant in ("8", "16"):
+    for variant in ("4", "8", "16"):
         name = "cm_sub_" + variant
         torch.manual_seed(gc.WEIGHT_SEED)
         ref = get_model(name).eval()

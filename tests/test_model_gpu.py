@@ -269,7 +269,7 @@ def test_ragged_shape_and_other_maxdisp_vs_fp64_oracle():
         assert torch.isfinite(b16).all() and float((b16 - a).abs().mean()) < 1.0
 
 
-@pytest.mark.parametrize("variant", ["8", "16"])
+@pytest.mark.parametrize("variant", ["4", "8", "16"])
 def test_cm_sub_variants_match_fp64_oracle(variant):
     """cm_sub_8 / cm_sub_16 (single-hourglass ablations) on the CUDA kernels vs their fp64 CPU oracle."""
     import cm_sub_oracle as orcs

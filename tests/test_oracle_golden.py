@@ -135,7 +135,7 @@ def test_sub16_full_forward_against_reference(golden_dir):
     torch.testing.assert_close(stages["c1"][0], g["c1_sub"], rtol=1e-3, atol=1e-3)
 
 
-@pytest.mark.parametrize("variant", ["8", "16"])
+@pytest.mark.parametrize("variant", ["4", "8", "16"])
 def test_cm_sub_forward_against_reference(golden_dir, variant):
     """Single-hourglass ablations cm_sub_8 / cm_sub_16: oracle vs the outputs of the real reference modules."""
     import cm_sub_oracle as orcs
