@@ -2,8 +2,9 @@
 
 `get_model(name)` instantiates the class with NO arguments, exactly like the reference.  Scope of this
 build: `cmfsm` is the B200-native hot path; `cmfsm_sub_8` and `cmfsm_sub_16` (the 1/8- and
-1/16-resolution "downsample configs") and the single-hourglass ablations `cm_sub_4` / `cm_sub_8` / `cm_sub_16` run on the
-same kernels (inference).  The other four registered names of the reference (baselines / ablations) are listed so that a typo and an out-of-scope name produce different,
+1/16-resolution "downsample configs") and the single-hourglass ablations `cm_sub_4` / `cm_sub_8` / `cm_sub_16` and the no-mapping baselines
+`bilinear_cmf` / `bilinear_cmf_sub_8` / `bilinear_cmf_sub_16` run on the same kernels (inference).  The one remaining
+registered name of the reference (`cmf`, with its super-resolution refinement head) is listed so that a typo and an out-of-scope name produce different,
 explicit errors instead of the reference's bare `print`.
 """
 from cmf.models.cmfsm import cmfsm
@@ -12,9 +13,13 @@ from cmf.models.cmfsm_sub_16 import cmfsm_sub_16
 from cmf.models.cm_sub_4 import cm_sub_4
 from cmf.models.cm_sub_8 import cm_sub_8
 from cmf.models.cm_sub_16 import cm_sub_16
+from cmf.models.bilinear_cmf import bilinear_cmf
+from cmf.models.bilinear_cmf_sub_8 import bilinear_cmf_sub_8
+from cmf.models.bilinear_cmf_sub_16 import bilinear_cmf_sub_16
 
 _IMPLEMENTED = {"cmfsm": cmfsm, "cmfsm_sub_8": cmfsm_sub_8, "cmfsm_sub_16": cmfsm_sub_16, "cm_sub_4": cm_sub_4,
-                "cm_sub_8": cm_sub_8, "cm_sub_16": cm_sub_16}
+                "cm_sub_8": cm_sub_8, "cm_sub_16": cm_sub_16, "bilinear_cmf": bilinear_cmf,
+                "bilinear_cmf_sub_8": bilinear_cmf_sub_8, "bilinear_cmf_sub_16": bilinear_cmf_sub_16}
 _REFERENCE_NAMES = ("cmf", "cmfsm", "bilinear_cmf", "cmfsm_sub_8", "cmfsm_sub_16", "bilinear_cmf_sub_8",
                     "bilinear_cmf_sub_16", "cm_sub_16", "cm_sub_8", "cm_sub_4")
 

@@ -55,6 +55,7 @@ SIGNATURES = {
     "cmfb200_softargmin_ctxmap5_fwd": [_P] * 8 + [_I] * 5 + [_P],
     "cmfb200_spp_upsample_concat_sized_fwd": [_P] * 7 + [_I] * 12 + [_P],
     "cmfb200_ctxmap_weights3_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "cmfb200_trilinear_softargmin_fwd": [_P] * 6 + [_I] * 7 + [_P],
     "cmfb200_volume_mapping_fwd": [_P] * 8 + [_I] * 5 + [_P],
     "cmfb200_ctxmap_weights_bwd": [_P] * 11 + [_I, _I, _I, _I, _P],
     "cmfb200_softargmin_ctxmap_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

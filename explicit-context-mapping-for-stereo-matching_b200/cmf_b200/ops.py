@@ -659,3 +659,17 @@ def volume_mapping(c1, c2, c3, weights5, weights3, scale):
                                                           _p(outs[1]), _p(outs[2]), B, Dl, h, w, scale, _stream()),
                    "volume_mapping_fwd")
     return tuple(outs)
+
+
+# ---- bilinear_cmf* baselines -----------------------------------------------------------------------
+def trilinear_softargmin(c1, c2, c3, maxdisp, H, W):
+    """cmf/models/bilinear_cmf.py:418-452: raw classifier volumes [B,D',h,w] -> cumulative sums -> trilinear upsampling
+    to [B,maxdisp,H,W] -> softmax over maxdisp -> regression.  Returns 3 x [B,H,W]."""
+    _req(c1, c2, c3)
+    B, Dl, h, w = c1.shape
+    outs = [torch.empty((B, H, W), device=c1.device, dtype=torch.float32) for _ in range(3)]
+    with torch.cuda.device(c1.device), _timed("trilinear_softargmin_fwd"):
+        _lib.check(_lib.load().cmfb200_trilinear_softargmin_fwd(_p(c1), _p(c2), _p(c3), _p(outs[0]), _p(outs[1]), _p(outs[2]),
+                                                                B, Dl, h, w, maxdisp, H, W, _stream()),
+                   "trilinear_softargmin_fwd")
+    return tuple(outs)

@@ -215,6 +215,11 @@ int cmfb200_ctxmap_weights3_fwd(const float* lr, const float* hr, const float* w
 int cmfb200_volume_mapping_fwd(const float* c1, const float* c2, const float* c3, const float* weights5,
                                const float* weights3, float* out1, float* out2, float* out3, int B, int Dl, int h,
                                int w, int scale, void* stream);
+/* Epilogue of the bilinear_cmf / bilinear_cmf_sub_8 / bilinear_cmf_sub_16 baselines (bilinear_cmf.py:418-452): the
+ * classifier volumes c_n [B,D',h,w] are accumulated (c2 += c1, c3 += c2), trilinearly upsampled (align_corners=False)
+ * to [B,maxdisp,H,W], soft-maxed over maxdisp and regressed; out_n [B,H,W].  Nothing is materialised. */
+int cmfb200_trilinear_softargmin_fwd(const float* c1, const float* c2, const float* c3, float* out1, float* out2,
+                                     float* out3, int B, int Dl, int h, int w, int maxdisp, int H, int W, void* stream);
 
 /* ---- K4: soft-argmin + x scale upsample + 9-neighbour context mapping ---------------------------
  * Replaces cmfsm.py:703-769 (3x softmax, disparityregression :111-123, ~60 slice kernels).

@@ -20,10 +20,11 @@ def test_registry_names():
     assert type(m).__name__ == "cmfsm" and m.maxdisp == 192
     m8 = get_model("cmfsm_sub_8")
     assert type(m8).__name__ == "cmfsm_sub_8" and m8.maxdisp == 192
-    for name in ("cmfsm_sub_16", "cm_sub_4", "cm_sub_8", "cm_sub_16"):
+    for name in ("cmfsm_sub_16", "cm_sub_4", "cm_sub_8", "cm_sub_16", "bilinear_cmf", "bilinear_cmf_sub_8",
+                 "bilinear_cmf_sub_16"):
         assert type(get_model(name)).__name__ == name
     with pytest.raises(NotImplementedError):
-        get_model("bilinear_cmf")
+        get_model("cmf")
     with pytest.raises(KeyError):
         get_model("no_such_model")
 
@@ -46,7 +47,10 @@ def test_state_dict_contract_and_seeded_init(golden_dir):
 @pytest.mark.parametrize("name,fixture", [("cmfsm_sub_8", "cmfsm_sub8_state_dict.json"),
                                           ("cmfsm_sub_16", "cmfsm_sub16_state_dict.json"),
                                           ("cm_sub_4", "cm_sub4_state_dict.json"), ("cm_sub_8", "cm_sub8_state_dict.json"),
-                                          ("cm_sub_16", "cm_sub16_state_dict.json")])
+                                          ("cm_sub_16", "cm_sub16_state_dict.json"),
+                                          ("bilinear_cmf", "bilinear4_state_dict.json"),
+                                          ("bilinear_cmf_sub_8", "bilinear8_state_dict.json"),
+                                          ("bilinear_cmf_sub_16", "bilinear16_state_dict.json")])
 def test_variant_state_dict_contract_and_seeded_init(golden_dir, name, fixture):
     """The 1/8- and 1/16-resolution variants: keys, order, shapes and seed-0 values equal the reference's."""
     from cmf.models import get_model

@@ -596,3 +596,17 @@ def test_k4_backward_vs_autograd(B, D, h, w, scale):
         err = _rel_l2(a.cpu().double(), b)
         print("K4 bwd %s rel-L2 %.2e" % (name, err))
         assert a.shape == b.shape and err < 2e-5, (name, err)
+
+
+@pytest.mark.parametrize("B,Dl,h,w,maxdisp,H,W", [(1, 6, 5, 7, 24, 20, 28), (2, 12, 9, 18, 192, 144, 288), (1, 5, 4, 9, 40, 32, 72)])
+def test_trilinear_softargmin_vs_oracle(B, Dl, h, w, maxdisp, H, W):
+    """cmfb200_trilinear_softargmin_fwd vs F.interpolate(trilinear) + softmax + regression in fp64."""
+    import bilinear_oracle as orcb
+    from cmf_b200 import ops
+
+    cs = [_rand(B, Dl, h, w, seed=210 + i) * 2 for i in range(3)]
+    want = orcb.trilinear_softargmin(*[c.double() for c in cs], maxdisp, H, W)
+    got = ops.trilinear_softargmin(*[c.to(DEV) for c in cs], maxdisp, H, W)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        torch.testing.assert_close(a.cpu().double(), b, rtol=1e-4, atol=1e-3)

@@ -289,3 +289,26 @@ def test_cm_sub_variants_match_fp64_oracle(variant):
           % (variant, d_ours.max(), d_ours.mean(), d_ref.max(), d_ref.mean()))
     assert float(d_ours.mean()) <= 2 * float(d_ref.mean()) + 1e-3
     assert float(d_ours.max()) <= 3 * float(d_ref.max()) + 5e-2
+
+
+@pytest.mark.parametrize("variant,name", [("4", "bilinear_cmf"), ("8", "bilinear_cmf_sub_8"), ("16", "bilinear_cmf_sub_16")])
+def test_bilinear_baselines_match_fp64_oracle(variant, name):
+    """The no-mapping baselines on the CUDA kernels vs their fp64 CPU oracle (pinned to the reference modules)."""
+    import bilinear_oracle as orcb
+    from cmf.models import get_model
+
+    torch.manual_seed(gc.WEIGHT_SEED)
+    net = get_model(name).to(DEV).eval()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    left, right = gc.seeded_pair(1, 256, 512, seed=5)
+    with torch.no_grad():
+        ours = net(left.to(DEV), right.to(DEV))
+    r32 = orcb.forward(sd, left, right, variant, 192)
+    r64 = orcb.forward({k: v.double() for k, v in sd.items()}, left.double(), right.double(), variant, 192)
+    for i, (a, b32, b64) in enumerate(zip(ours, r32, r64), 1):
+        assert tuple(a.shape) == (1, 256, 512)
+        d_ours, d_ref = (a.cpu().double() - b64).abs(), (b32.double() - b64).abs()
+        print("%s pred%d: ours-vs-fp64 max %.3e mean %.3e ; ref32-vs-fp64 max %.3e mean %.3e"
+              % (name, i, d_ours.max(), d_ours.mean(), d_ref.max(), d_ref.mean()))
+        assert float(d_ours.mean()) <= 2 * float(d_ref.mean()) + 1e-3
+        assert float(d_ours.max()) <= 3 * float(d_ref.max()) + 5e-2

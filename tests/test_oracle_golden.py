@@ -153,6 +153,22 @@ def test_cm_sub_forward_against_reference(golden_dir, variant):
     torch.testing.assert_close(stages["c1"][0, ::2, ::2, ::2], g["c1_sub"], rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("variant,name", [("4", "bilinear_cmf"), ("8", "bilinear_cmf_sub_8"), ("16", "bilinear_cmf_sub_16")])
+def test_bilinear_forward_against_reference(golden_dir, variant, name):
+    """No-mapping baselines: oracle vs the outputs of the real reference modules."""
+    import bilinear_oracle as orcb
+    from cmf.models import get_model
+
+    g = _npz(golden_dir, "bilinear%s_c1.npz" % variant)
+    torch.manual_seed(gc.WEIGHT_SEED)
+    sd = get_model(name).state_dict()
+    left, right = gc.seeded_pair(1, 256, 512)
+    for i, p in enumerate(orcb.forward(sd, left, right, variant, 192), 1):
+        assert tuple(p.shape) == (1, 256, 512)
+        d = (p[0, ::4, ::4] - g["pred%d_sub" % i]).abs()
+        assert float(d.max()) < 0.5 and float(d.mean()) < 2e-2, (i, float(d.max()), float(d.mean()))
+
+
 def test_shape_validation():
     import pytest
 
