@@ -165,7 +165,7 @@ class cmfsm(nn.Module):
     def _finish_init(self):
         # packed-weight cache: stable per-layer name (survives DataParallel's shallow replicas) + device
         for name, m in self.named_modules():
-            if isinstance(m, (nn.Conv2d, nn.Conv3d, nn.ConvTranspose3d)):
+            if isinstance(m, (nn.Conv2d, nn.Conv3d, nn.ConvTranspose3d, nn.ConvTranspose2d)):
                 m._cmf_name = name
         self._packed = {}  # (layer name, device index[, "ig"]) -> (version, data_ptr, packed weight)
         # 3-D aggregation arithmetic: "fp32" (CUDA-core FMA, the parity mode BASELINE config 2 is quoted in) or

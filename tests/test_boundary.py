@@ -23,8 +23,7 @@ def test_registry_names():
     for name in ("cmfsm_sub_16", "cm_sub_4", "cm_sub_8", "cm_sub_16", "bilinear_cmf", "bilinear_cmf_sub_8",
                  "bilinear_cmf_sub_16"):
         assert type(get_model(name)).__name__ == name
-    with pytest.raises(NotImplementedError):
-        get_model("cmf")
+    assert type(get_model("cmf")).__name__ == "cmf"
     with pytest.raises(KeyError):
         get_model("no_such_model")
 
@@ -50,7 +49,7 @@ def test_state_dict_contract_and_seeded_init(golden_dir):
                                           ("cm_sub_16", "cm_sub16_state_dict.json"),
                                           ("bilinear_cmf", "bilinear4_state_dict.json"),
                                           ("bilinear_cmf_sub_8", "bilinear8_state_dict.json"),
-                                          ("bilinear_cmf_sub_16", "bilinear16_state_dict.json")])
+                                          ("bilinear_cmf_sub_16", "bilinear16_state_dict.json"), ("cmf", "cmf_state_dict.json")])
 def test_variant_state_dict_contract_and_seeded_init(golden_dir, name, fixture):
     """The 1/8- and 1/16-resolution variants: keys, order, shapes and seed-0 values equal the reference's."""
     from cmf.models import get_model

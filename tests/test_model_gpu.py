@@ -312,3 +312,27 @@ def test_bilinear_baselines_match_fp64_oracle(variant, name):
               % (name, i, d_ours.max(), d_ours.mean(), d_ref.max(), d_ref.mean()))
         assert float(d_ours.mean()) <= 2 * float(d_ref.mean()) + 1e-3
         assert float(d_ours.max()) <= 3 * float(d_ref.max()) + 5e-2
+
+
+def test_cmf_model_matches_fp64_oracle():
+    """Registry model `cmf` on the CUDA kernels (zero-padded channel counts, 2-D transposed conv through the 3-D kernel)
+    vs its fp64 CPU oracle, which oracle/gen_golden_cmf.py pinned to the real reference module."""
+    import cmf_oracle as orcc
+    from cmf.models import get_model
+
+    torch.manual_seed(gc.WEIGHT_SEED)
+    net = get_model("cmf").to(DEV).eval()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    left, right = gc.seeded_pair(1, 256, 512, seed=5)
+    with torch.no_grad():
+        ours = net(left.to(DEV), right.to(DEV))
+    r32 = orcc.forward(sd, left, right, 192)
+    r64 = orcc.forward({k: v.double() for k, v in sd.items()}, left.double(), right.double(), 192)
+    for i, (a, b32, b64) in enumerate(zip(ours, r32, r64), 1):
+        assert tuple(a.shape) == (1, 1, 256, 512)
+        scale = float(b64.abs().mean()) + 1e-6
+        d_ours, d_ref = (a.cpu().double() - b64).abs(), (b32.double() - b64).abs()
+        print("cmf pred%d: |mean| %.3f ours-vs-fp64 max %.3e mean %.3e ; ref32-vs-fp64 max %.3e mean %.3e"
+              % (i, scale, d_ours.max(), d_ours.mean(), d_ref.max(), d_ref.mean()))
+        assert float(d_ours.mean()) <= 2 * float(d_ref.mean()) + 1e-5 * scale + 1e-6
+        assert float(d_ours.max()) <= 3 * float(d_ref.max()) + 1e-4 * scale + 1e-5

@@ -169,6 +169,22 @@ def test_bilinear_forward_against_reference(golden_dir, variant, name):
         assert float(d.max()) < 0.5 and float(d.mean()) < 2e-2, (i, float(d.max()), float(d.mean()))
 
 
+def test_cmf_forward_against_reference(golden_dir):
+    """Registry model `cmf` (stride-2 stem + super-resolution refinement head): oracle vs the real reference outputs."""
+    import cmf_oracle as orcc
+    from cmf.models import get_model
+
+    g = _npz(golden_dir, "cmf_c1.npz")
+    torch.manual_seed(gc.WEIGHT_SEED)
+    sd = get_model("cmf").state_dict()
+    left, right = gc.seeded_pair(1, 256, 512)
+    for i, p in enumerate(orcc.forward(sd, left, right, 192), 1):
+        assert tuple(p.shape) == (1, 1, 256, 512)
+        want = g["pred%d_sub" % i]
+        rel = float((p[0, 0, ::4, ::4] - want).norm() / want.norm().clamp_min(1e-6))
+        assert rel < 1e-3, (i, rel)
+
+
 def test_shape_validation():
     import pytest
 
