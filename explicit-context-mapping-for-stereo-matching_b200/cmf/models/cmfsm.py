@@ -307,8 +307,21 @@ class cmfsm(nn.Module):
         self._packed[key] = (w._version, w.data_ptr(), packed)
         return packed
 
+    def _pack_cout1_taps(self, conv):
+        w = conv.weight
+        key = (conv._cmf_name, w.device.index, "taps")
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+            return hit[2]
+        packed = ops.pack_cout1_taps(w)
+        self._packed[key] = (w._version, w.data_ptr(), packed)
+        return packed
+
     def _classify_bf16(self, head, x):
-        return ops.conv3d_igemm_cout1(self._ig(head[0], x, relu=True), self._pack_ig_cout1(head[2]))
+        t = self._ig(head[0], x, relu=True)
+        if os.environ.get("CMF_B200_COUT1_GATHER"):  # A/B switch: N=27 GEMM per plane + 27-point gather (same speed today)
+            return ops.conv3d_igemm_cout1_gather(t, self._pack_cout1_taps(head[2]))
+        return ops.conv3d_igemm_cout1(t, self._pack_ig_cout1(head[2]))
 
     def _aggregate_bf16(self, lfeat, rfeat, D):
         cost = ops.cost_volume_concat_c8(lfeat, rfeat, D)

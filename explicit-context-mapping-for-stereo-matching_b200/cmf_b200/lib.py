@@ -31,6 +31,7 @@ SIGNATURES = {
     "cmfb200_conv3d_igemm_bf16_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_conv3d_c8_cout1_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_conv3d_igemm_cout1_bf16_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "cmfb200_conv3d_igemm_cout1_gather_bf16_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_deconv3d_igemm_bf16_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_conv3d_s2_igemm_bf16_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_c8_parity_split": [_P, _P, _I, _I, _I, _I, _I, _P],

@@ -509,6 +509,31 @@ def conv3d_igemm_cout1(x, packed32):
     return y
 
 
+def pack_cout1_taps(weight):
+    """nn.Conv3d weight [1,32,3,3,3] (fp32) -> bf16 [4,32,8]: row n < 27 of the 32 = tap n, K-major in 8-channel chunks
+    (the B operand of `conv3d_igemm_cout1_gather`)."""
+    w = weight.detach()
+    _req(w)
+    if tuple(w.shape) != (1, 32, 3, 3, 3):
+        raise ValueError("expected a [1,32,3,3,3] weight, got %s" % (tuple(w.shape),))
+    taps = torch.zeros((32, 32), device=w.device, dtype=torch.float32)
+    taps[:27] = w[0].reshape(32, 27).t()
+    return taps.view(32, 4, 8).permute(1, 0, 2).contiguous().to(BF16)
+
+
+def conv3d_igemm_cout1_gather(x, taps):
+    """classifN.2 as one N=27 GEMM per plane + a 27-point gather: C8/bf16 [B,4,D,H,W,8] x pack_cout1_taps -> fp32 [B,D,H,W]."""
+    _req(x, taps, dtype=BF16)
+    B, NC, D, H, W, _ = x.shape
+    if NC != 4 or tuple(taps.shape) != (4, 32, 8):
+        raise ValueError("expected a 32-channel C8 input and [4,32,8] tap weights")
+    y = torch.empty((B, D, H, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _timed("conv3d_igemm_cout1_bf16_fwd"):
+        _lib.check(_lib.load().cmfb200_conv3d_igemm_cout1_gather_bf16_fwd(_p(x), _p(taps), _p(y), B, 32, D, H, W, _stream()),
+                   "conv3d_igemm_cout1_gather_bf16_fwd")
+    return y
+
+
 def deconv3d_igemm(x, packed, want_stats=True):
     """tcgen05 transposed conv (k3 s2 p1 op1) on C8/bf16: [B,Cin/8,D,H,W,8] -> [B,Cout/8,2D,2H,2W,8]."""
     _req(x, packed, dtype=BF16)

@@ -42,36 +42,6 @@ __device__ __forceinline__ void kd_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-struct KdUnit {
-    int b, ty, tx, d0, d1, pl0, pl1;
-};
-
-// Work partition: the (tile column, depth) space of one output-channel group is linearised (column-major, depth
-// fastest) and cut into equal contiguous ranges, one per CTA of the group; a range is walked as segments that stay
-// inside one column.  A segment [d0,d1) needs the input planes d0-1 .. d1 (clipped to the volume).
-struct KdWalk {
-    long long pos, end;
-    int D, tiles_w, per_sample;
-    __device__ __forceinline__ KdWalk(int rank, int nranks, long long total, int D_, int tiles_w_, int tiles_h_)
-        : pos(total * rank / nranks), end(total * (rank + 1) / nranks), D(D_), tiles_w(tiles_w_),
-          per_sample(tiles_w_ * tiles_h_) {}
-    __device__ __forceinline__ bool next(KdUnit& u) {
-        if (pos >= end) return false;
-        const int col = (int)(pos / D);
-        u.d0 = (int)(pos - (long long)col * D);
-        const long long left = end - pos;
-        u.d1 = (left < (long long)(D - u.d0)) ? u.d0 + (int)left : D;
-        pos += u.d1 - u.d0;
-        u.b = col / per_sample;
-        const int r = col - u.b * per_sample;
-        u.ty = r / tiles_w;
-        u.tx = r - u.ty * tiles_w;
-        u.pl0 = u.d0 > 0 ? u.d0 - 1 : 0;
-        u.pl1 = u.d1 < D ? u.d1 : D - 1;
-        return true;
-    }
-};
-
 // COUT1: classifier tail (Cin -> 1): the weights arrive zero-padded to 32 output channels, only column 0 of every
 // accumulator block is read back and written as fp32 [B][D][H][W] (no GroupNorm follows).
 template <int CIN, int NS, bool COUT1>

@@ -98,6 +98,37 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
     return v[0];
 }
 
+// ---- work partition of the depth-walking kernels (conv3d_igemm_kdstack.cu, conv3d_igemm_cout1_gather.cu) ----
+struct KdUnit {
+    int b, ty, tx, d0, d1, pl0, pl1;
+};
+
+// Work partition: the (tile column, depth) space of one output-channel group is linearised (column-major, depth
+// fastest) and cut into equal contiguous ranges, one per CTA of the group; a range is walked as segments that stay
+// inside one column.  A segment [d0,d1) needs the input planes d0-1 .. d1 (clipped to the volume).
+struct KdWalk {
+    long long pos, end;
+    int D, tiles_w, per_sample;
+    __device__ __forceinline__ KdWalk(int rank, int nranks, long long total, int D_, int tiles_w_, int tiles_h_)
+        : pos(total * rank / nranks), end(total * (rank + 1) / nranks), D(D_), tiles_w(tiles_w_),
+          per_sample(tiles_w_ * tiles_h_) {}
+    __device__ __forceinline__ bool next(KdUnit& u) {
+        if (pos >= end) return false;
+        const int col = (int)(pos / D);
+        u.d0 = (int)(pos - (long long)col * D);
+        const long long left = end - pos;
+        u.d1 = (left < (long long)(D - u.d0)) ? u.d0 + (int)left : D;
+        pos += u.d1 - u.d0;
+        u.b = col / per_sample;
+        const int r = col - u.b * per_sample;
+        u.ty = r / tiles_w;
+        u.tx = r - u.ty * tiles_w;
+        u.pl0 = u.d0 > 0 ? u.d0 - 1 : 0;
+        u.pl1 = u.d1 < D ? u.d1 : D - 1;
+        return true;
+    }
+};
+
 // ---- host: cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda.so) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

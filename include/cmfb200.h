@@ -104,6 +104,11 @@ int cmfb200_conv3d_c8_cout1_fwd(const void* x_c8, const float* weight, float* y,
  * rounded to bf16 like every other layer of the bf16 aggregation); y fp32 [B][D][H][W].  Cin = 32. */
 int cmfb200_conv3d_igemm_cout1_bf16_fwd(const void* x_c8, const void* packed_w32, float* y, int B, int Cin, int D,
                                         int H, int W, void* stream);
+/* The same layer as ONE N=27 GEMM per input plane (P[pos,tap] on the unshifted tile) + a 27-point gather in shared
+ * memory: tap_weights = bf16 [Cin/8][32][8] with row n < 27 = tap n = (kd*3+kh)*3+kw of the [1,Cin,3,3,3] weight, rows
+ * 27..31 zero.  y fp32 [B][D][H][W].  Cin = 32.  Bound by reading the input once. */
+int cmfb200_conv3d_igemm_cout1_gather_bf16_fwd(const void* x_c8, const void* tap_weights, float* y, int B, int Cin,
+                                               int D, int H, int W, void* stream);
 /* Transposed conv k3 s2 p1 op1 on tensor cores: x_c8 [B][Cin/8][D][H][W][8] -> y_c8 [B][Cout/8][2D][2H][2W][8];
  * packed_w from cmfb200_pack_igemm_weight_bf16(transposed=1).  (Cin,Cout) in {(64,64),(64,32)}. */
 int cmfb200_deconv3d_igemm_bf16_fwd(const void* x_c8, const void* packed_w, void* y_c8, double* gn_sums,
