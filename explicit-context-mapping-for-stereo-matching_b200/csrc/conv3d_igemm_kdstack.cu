@@ -192,9 +192,12 @@ __global__ void __launch_bounds__(kIgThreads, 1)
                 }
                 tc_fence_after();
                 if constexpr (COUT1) {
-                    float o0 = __uint_as_float(tmem_ld_32x32b_x1(tlane + ((g_base + d - u.pl0) & 3) * kBufCols + 32));
-                    if (d - 1 >= 0) o0 += __uint_as_float(tmem_ld_32x32b_x1(tlane + ((g_base + d - 1 - u.pl0) & 3) * kBufCols + 0));
-                    if (d + 1 < D) o0 += __uint_as_float(tmem_ld_32x32b_x1(tlane + ((g_base + d + 1 - u.pl0) & 3) * kBufCols + 64));
+                    uint32_t r1, r0 = 0, r2 = 0;  // 0 = +0.0f
+                    tmem_ld_32x32b_x1_issue(tlane + ((g_base + d - u.pl0) & 3) * kBufCols + 32, r1);
+                    if (d - 1 >= 0) tmem_ld_32x32b_x1_issue(tlane + ((g_base + d - 1 - u.pl0) & 3) * kBufCols + 0, r0);
+                    if (d + 1 < D) tmem_ld_32x32b_x1_issue(tlane + ((g_base + d + 1 - u.pl0) & 3) * kBufCols + 64, r2);
+                    tmem_ld_wait();
+                    const float o0 = (__uint_as_float(r1) + __uint_as_float(r0)) + __uint_as_float(r2);
                     if (d - 1 >= u.pl0) {
                         tc_fence_before();
                         kd_mbar_arrive(tmemEmpty + ((g_base + d - 1 - u.pl0) & 3));
@@ -205,22 +208,21 @@ __global__ void __launch_bounds__(kIgThreads, 1)
                 __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_out);
                 float o[32];
                 {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tlane + ((g_base + d - u.pl0) & 3) * kBufCols + 32, v);  // kd = 1, always present
+                    // the three plane blocks are requested back to back and awaited once (one TMEM round trip per output
+                    // plane instead of three: the epilogue chain, not the MMAs, bounded this kernel)
+                    uint32_t v1[32], v0[32], v2[32];
+                    const bool has0 = d - 1 >= 0, has2 = d + 1 < D;  // warp-uniform
+                    tmem_ld_32x32b_x32_issue(tlane + ((g_base + d - u.pl0) & 3) * kBufCols + 32, v1);  // kd = 1
+                    if (has0) tmem_ld_32x32b_x32_issue(tlane + ((g_base + d - 1 - u.pl0) & 3) * kBufCols + 0, v0);
+                    if (has2) tmem_ld_32x32b_x32_issue(tlane + ((g_base + d + 1 - u.pl0) & 3) * kBufCols + 64, v2);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) o[c] = __uint_as_float(v[c]);
-                }
-                if (d - 1 >= 0) {  // warp-uniform
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tlane + ((g_base + d - 1 - u.pl0) & 3) * kBufCols + 0, v);
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) o[c] += __uint_as_float(v[c]);
-                }
-                if (d + 1 < D) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tlane + ((g_base + d + 1 - u.pl0) & 3) * kBufCols + 64, v);
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) o[c] += __uint_as_float(v[c]);
+                    for (int c = 0; c < 32; ++c) {
+                        float a = __uint_as_float(v1[c]);
+                        if (has0) a += __uint_as_float(v0[c]);
+                        if (has2) a += __uint_as_float(v2[c]);
+                        o[c] = a;
+                    }
                 }
                 if (d - 1 >= u.pl0) {  // plane d-1 has no reader left
                     tc_fence_before();
