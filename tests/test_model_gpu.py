@@ -207,6 +207,11 @@ def test_sub8_variant_matches_fp64_oracle():
               % (i, scale, d_ours.max(), d_ours.mean(), d_ref.max(), d_ref.mean()))
         assert float(d_ours.mean()) <= 2 * float(d_ref.mean()) + 1e-5 * scale
         assert float(d_ours.max()) <= 3 * float(d_ref.max()) + 1e-4 * scale
+    net.enable_cuda_graph(True)  # graph capture / replay works for the variants too
+    with torch.no_grad():
+        replay = net(left.to(DEV), right.to(DEV))
+    net.enable_cuda_graph(False)
+    assert all(torch.equal(a, r) for a, r in zip(ours, replay))
     net.aggregation = "bf16"
     with torch.no_grad():
         b = net(left.to(DEV), right.to(DEV))
