@@ -36,6 +36,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     constexpr int NI4 = (NI + 3) / 4;
     constexpr int NSLOT = (PD * PH * PW + kConvThreads - 1) / kConvThreads;
     constexpr int STAGE = CC * (PATCH + WSL);  // floats per pipeline stage
+    // stride 2: a patch row is stored de-interleaved, [even columns | odd columns] (odd half at HALF): output v reads
+    // columns 2v, 2v+1, 2v+2 = E[v], O[v], E[v+1], so a thread's inputs are one aligned float4 + one scalar of E and one
+    // aligned float4 of O at a 16-byte lane pitch (conflict-free) instead of three float4 at a 32-byte pitch (2-way).
+    constexpr int HALF = (((PW + 1) / 2) + 3) & ~3;
+    static_assert(S == 1 || HALF + PW / 2 <= PWP, "de-interleaved row does not fit the row pitch");
     static_assert((TW / kVPT - 1) * kVPT * S + NI4 * 4 <= PWP, "vector over-read leaves the patch row");
     static_assert((CC * WSL) % 4 == 0 && (CC * PATCH) % 4 == 0, "stage slices must stay 16-byte aligned");
 
@@ -78,7 +83,8 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         const bool in_patch = e < PD * PH * PW;
         ok[j] = in_patch && (unsigned)di < (unsigned)D && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
         goff[j] = ok[j] ? (di * H + hi) * W + wi : 0;
-        soff[j] = in_patch ? (pd * PH + ph) * PWP + pw : -1;
+        const int pcol = (S == 2) ? ((pw & 1) ? HALF + (pw >> 1) : (pw >> 1)) : pw;
+        soff[j] = in_patch ? (pd * PH + ph) * PWP + pcol : -1;
     }
 
     auto stage = [&](int c0, int buf) {
@@ -96,8 +102,9 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         cp_async_commit();
     };
 
-    // zero the alignment tail of every patch row once (never written by cp.async, read by the vector loads)
-    if constexpr (PWP > PW) {
+    // zero the alignment tail of every patch row once (never written by cp.async, read by the vector loads);
+    // the de-interleaved stride-2 rows have no slot that is read but not written
+    if constexpr (PWP > PW && S == 1) {
         for (int i = tid; i < 2 * CC * PD * PH * (PWP - PW); i += kConvThreads) {
             const int t = i % (PWP - PW);
             const int r = i / (PWP - PW);  // (buf, ci, pd*PH+ph) flattened
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         const float* sW = sIn + CC * PATCH;
 #pragma unroll 1
         for (int ci = 0; ci < CC; ++ci) {
-            const float* pin = sIn + ci * PATCH + (td * S * PH + th * S) * PWP + qx * kVPT * S;
+            const float* pin = sIn + ci * PATCH + (td * S * PH + th * S) * PWP + qx * kVPT * (S == 2 ? 1 : S);
             const float* pw_ = sW + ci * WSL + cg * CPT;
 #pragma unroll
             for (int kd = 0; kd < 3; ++kd) {
@@ -129,10 +136,19 @@ __global__ void __launch_bounds__(kConvThreads, 2)
                 for (int kh = 0; kh < 3; ++kh) {
                     const float* prow = pin + (kd * PH + kh) * PWP;
                     float in[NI4 * 4];
+                    if constexpr (S == 2) {
+                        const float4 e = *reinterpret_cast<const float4*>(prow);
+                        const float e4 = prow[4];
+                        const float4 o = *reinterpret_cast<const float4*>(prow + HALF);
+                        // in[2v + kw]: even positions from E, odd from O
+                        in[0] = e.x; in[1] = o.x; in[2] = e.y; in[3] = o.y; in[4] = e.z; in[5] = o.z; in[6] = e.w;
+                        in[7] = o.w; in[8] = e4;
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < NI4; ++j) {
-                        const float4 a = *reinterpret_cast<const float4*>(prow + 4 * j);
-                        in[4 * j + 0] = a.x; in[4 * j + 1] = a.y; in[4 * j + 2] = a.z; in[4 * j + 3] = a.w;
+                        for (int j = 0; j < NI4; ++j) {
+                            const float4 a = *reinterpret_cast<const float4*>(prow + 4 * j);
+                            in[4 * j + 0] = a.x; in[4 * j + 1] = a.y; in[4 * j + 2] = a.z; in[4 * j + 3] = a.w;
+                        }
                     }
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
