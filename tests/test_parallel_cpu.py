@@ -148,3 +148,55 @@ def test_band_rows_partition():
 @pytest.mark.timeout(300)
 def test_world_size_2_gloo():
     mp.spawn(_worker, args=(2, _free_port(), 24), nprocs=2, join=True)
+
+
+def _rows_conv_reference(ext, w, stride, dilation, h_offset, out_rows):
+    """CPU statement of the row-window contract of cmfb200_conv*_rows_fwd (include/cmfb200.h): output row m reads input
+    rows m*stride - pad + h_offset + kh*dilation of `ext`, rows outside `ext` read zero; W is padded as usual."""
+    import torch.nn.functional as F
+
+    pad = dilation
+    grow = out_rows * stride + h_offset + 2 * pad  # enough zero rows below so that every window exists
+    z = F.conv2d(F.pad(ext, (0, 0, 0, grow)), w, None, 1, pad, dilation)  # stride-1 responses, centre row r <-> z[r]
+    rows = [m * stride + h_offset for m in range(out_rows)]
+    return z[:, :, rows][:, :, :, ::stride]
+
+
+@pytest.mark.parametrize("stride,dilation", [(1, 1), (1, 2), (2, 1)])
+def test_row_window_contract_reproduces_the_unsharded_conv(stride, dilation):
+    """The halo sizes / h_offset values used by cmfsm._cg_band and _conv2_band: a band extended by its neighbours' rows
+    (zeros at the image border) and convolved under the row-window contract equals the band's rows of the whole-image
+    convolution, for every band."""
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(40)
+    x = torch.randn(1, 3, 32, 11, generator=g)
+    w = torch.randn(4, 3, 3, 3, generator=g)
+    full = F.conv2d(x, w, None, stride, dilation, dilation)
+    n, band = 4, 8
+    top, bottom = (2, 0) if stride == 2 else (dilation, dilation)
+    for r in range(n):
+        lo, hi = r * band, (r + 1) * band
+        t = x[:, :, lo - top:lo] if r > 0 else x.new_zeros(1, 3, top, 11)
+        b = x[:, :, hi:hi + bottom] if r < n - 1 else x.new_zeros(1, 3, bottom, 11)
+        ext = torch.cat([t, x[:, :, lo:hi], b], 2)
+        got = _rows_conv_reference(ext, w, stride, dilation, top, band // stride)
+        torch.testing.assert_close(got, full[:, :, lo // stride:hi // stride], rtol=1e-5, atol=1e-5)
+
+
+def test_row_window_contract_transposed_conv():
+    """Transposed conv (k3 s2 p1 op1) on a band + ONE bottom halo row, producing output rows only for the band's own
+    input rows (H_compute = band): equals the band's 2x rows of the whole-volume result."""
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(1, 3, 16, 7, generator=g)
+    w = torch.randn(3, 2, 3, 3, generator=g)
+    full = F.conv_transpose2d(x, w, None, 2, 1, 1)
+    n, band = 4, 4
+    for r in range(n):
+        lo, hi = r * band, (r + 1) * band
+        halo = x[:, :, hi:hi + 1] if r < n - 1 else x.new_zeros(1, 3, 1, 7)
+        ext = torch.cat([x[:, :, lo:hi], halo], 2)
+        got = F.conv_transpose2d(ext, w, None, 2, 1, 1)[:, :, :2 * band]  # rows of the band's own inputs only
+        torch.testing.assert_close(got, full[:, :, 2 * lo:2 * hi], rtol=1e-5, atol=1e-5)
