@@ -7,10 +7,11 @@ checkpoints and the reference drivers (train.py, test.py, eval_kitti.py) work un
 
 What differs underneath: cost volume, 3-D aggregation (conv/deconv + GroupNorm + residual + ReLU),
 context-mapping weights and the soft-argmin/upsample/mapping epilogue run as hand-written sm_100a kernels
-from libcmfb200.so (`cmf_b200.ops`), and so do the 2-D feature extractor's convolutions + GroupNorms at
-inference, including the SPP pools / bilinear upsamples / concat (under autograd the 2-D extractor runs
-through cuDNN in strict fp32).  Output semantics are per-sample `[B,1,H,W]` (the reference
-broadcasts to `[B,B,H,W]` for B>1).  There is no CPU path: CPU inputs raise.
+from libcmfb200.so (`cmf_b200.ops`), and so do the 2-D feature extractor's convolutions + GroupNorms,
+including the SPP pools / bilinear upsamples / concat -- at inference and under autograd alike (the
+backward kernels are listed in `cmf_b200.autograd_ops`).  Output semantics are per-sample `[B,1,H,W]`
+(the reference broadcasts to `[B,B,H,W]` for B>1).  There is no CPU path: CPU
+inputs raise.
 """
 import math
 import os
@@ -62,7 +63,8 @@ class ResidualUnit(nn.Module):
 
 
 class feature_extraction(nn.Module):
-    """2-D SPP feature extractor (reference cmfsm.py:126-236); cuDNN fp32 for now."""
+    """Parameter container of the 2-D SPP feature extractor (reference cmfsm.py:126-236); run by
+    `cmfsm._features` (inference) / `cmfsm._features_train` (autograd) on the libcmfb200 kernels."""
 
     def __init__(self):
         super().__init__()
@@ -90,17 +92,6 @@ class feature_extraction(nn.Module):
         self._width = width
         units += [ResidualUnit(width, width, 1, None, pad, dilation) for _ in range(1, n)]
         return nn.Sequential(*units)
-
-    def forward(self, x):
-        full = self.firstconv(x)  # [B,32,H,W], pre-GN / pre-ReLU: the context-mapping "hr" feature
-        half = self.layer1(self.secondconv(full))
-        raw = self.layer2(half)
-        skip = self.layer4(self.layer3(raw))
-        size = skip.shape[2:]
-        pyramid = [F.interpolate(getattr(self, "branch%d" % i)(skip), size, mode="bilinear", align_corners=False)
-                   for i in (4, 3, 2, 1)]
-        feat = self.lastconv(torch.cat([raw, skip] + pyramid, 1))
-        return feat, half, full
 
 
 class hourglass(nn.Module):
@@ -174,18 +165,26 @@ class cmfsm(nn.Module):
         self._graphs = None  # enable_cuda_graph(): {(shape, device, aggregation): captured forward}
 
     # -------------------------------------------------------------------------------- helpers
-    def _pack(self, conv):
+    def _cached(self, conv, tag, make):
+        """Packed form `make(weight)` of a conv weight, cached per (layer, device, tag) and revalidated against
+        the weight's (`_version`, `data_ptr`).  DataParallel replicas (re-created on every forward with freshly
+        broadcast weight tensors whose version/address can repeat while the values changed) never use the cache."""
         w = conv.weight
-        key = (conv._cmf_name, w.device.index)
+        if getattr(self, "_is_replica", False) or not isinstance(w, nn.Parameter):
+            return make(w)
+        key = (conv._cmf_name, w.device.index, tag)
         hit = self._packed.get(key)
         if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
             return hit[2]
-        if isinstance(conv, nn.Conv2d):
-            packed = ops.pack_conv2d_weight(w)
-        else:
-            packed = ops.pack_conv3d_weight(w, transposed=isinstance(conv, nn.ConvTranspose3d))
+        packed = make(w)
         self._packed[key] = (w._version, w.data_ptr(), packed)
         return packed
+
+    def _pack(self, conv):
+        if isinstance(conv, nn.Conv2d):
+            return self._cached(conv, "f32", ops.pack_conv2d_weight)
+        transposed = isinstance(conv, nn.ConvTranspose3d)
+        return self._cached(conv, "f32", lambda w: ops.pack_conv3d_weight(w, transposed=transposed))
 
     def _cg(self, block, x, stride=1, residual=None, relu=False):
         """conv/deconv + GroupNorm (+residual) (+ReLU) with the parameters of a [conv, GroupNorm] pair."""
@@ -265,14 +264,8 @@ class cmfsm(nn.Module):
     # implicit GEMM on the C8 layout, including the three 32->1 classifier convs (weights zero-padded to 32
     # output channels, depth-stacked schedule, fp32 output).
     def _pack_ig(self, conv):
-        w = conv.weight
-        key = (conv._cmf_name, w.device.index, "ig")
-        hit = self._packed.get(key)
-        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
-            return hit[2]
-        packed = ops.pack_igemm_weight(w, transposed=isinstance(conv, nn.ConvTranspose3d))
-        self._packed[key] = (w._version, w.data_ptr(), packed)
-        return packed
+        transposed = isinstance(conv, nn.ConvTranspose3d)
+        return self._cached(conv, "ig", lambda w: ops.pack_igemm_weight(w, transposed=transposed))
 
     def _ig(self, block, x, residual=None, relu=False, split=False, x_split=None):
         """conv + GroupNorm (+residual) (+ReLU) on C8.  `x_split`: parity-split copy of x (stride-2 convs);
@@ -296,26 +289,15 @@ class cmfsm(nn.Module):
         return out, pre, post
 
     def _pack_ig_cout1(self, conv):
-        w = conv.weight
-        key = (conv._cmf_name, w.device.index, "ig1")
-        hit = self._packed.get(key)
-        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
-            return hit[2]
-        padded = torch.zeros((32,) + tuple(w.shape[1:]), device=w.device, dtype=w.dtype)
-        padded[:1] = w.detach()
-        packed = ops.pack_igemm_weight(padded)
-        self._packed[key] = (w._version, w.data_ptr(), packed)
-        return packed
+        def make(w):
+            padded = torch.zeros((32,) + tuple(w.shape[1:]), device=w.device, dtype=w.dtype)
+            padded[:1] = w.detach()
+            return ops.pack_igemm_weight(padded)
+
+        return self._cached(conv, "ig1", make)
 
     def _pack_cout1_taps(self, conv):
-        w = conv.weight
-        key = (conv._cmf_name, w.device.index, "taps")
-        hit = self._packed.get(key)
-        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
-            return hit[2]
-        packed = ops.pack_cout1_taps(w)
-        self._packed[key] = (w._version, w.data_ptr(), packed)
-        return packed
+        return self._cached(conv, "taps", ops.pack_cout1_taps)
 
     def _classify_bf16(self, head, x):
         t = self._ig(head[0], x, relu=True)
@@ -532,7 +514,17 @@ class cmfsm(nn.Module):
         self._graphs = {} if on else None
         return self
 
+    def _weights_fingerprint(self):
+        # a captured graph bakes in the packed conv-weight buffers made during its warm-up: any in-place update
+        # (optimizer.step, load_state_dict: `_version` moves) or re-allocation (.to(), .half(): `data_ptr` moves)
+        # of a parameter must invalidate it
+        return hash(tuple((p.data_ptr(), p._version) for p in self.parameters()))
+
     def _forward_graphed(self, left, right):
+        fp = self._weights_fingerprint()
+        if self._graphs.get("weights") != fp:
+            self._graphs.clear()  # stale graphs replay stale packed weights: drop them all
+            self._graphs["weights"] = fp
         key = (tuple(left.shape), left.device.index, self.aggregation)
         entry = self._graphs.get(key)
         if entry is None:

@@ -17,12 +17,19 @@ import torch
 import torch.distributed as dist
 
 
-def world():
-    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+def world(group=None):
+    """Number of ranks of `group` (default: the whole job); 1 when torch.distributed is not initialised."""
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
 
-def rank():
-    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+def rank(group=None):
+    """This process's rank INSIDE `group` (default group: the global rank)."""
+    return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
+def _peer(group, r):
+    """Global rank of rank `r` of `group` (point-to-point ops address peers by global rank)."""
+    return r if group is None else dist.get_global_rank(group, r)
 
 
 # ------------------------------------------------------------------------------------------ data parallel
@@ -32,10 +39,16 @@ def allreduce_gradients(params, bucket_bytes=32 << 20, average=False, group=None
     5,255,368 fp32 gradients = 21 MB -> a single 32 MB bucket by default: on NVSwitch the all-reduce cost is
     latency- not link-bound, so fewer, larger collectives win.  Returns the number of collectives.
     """
-    n = world()
-    grads = [p.grad for p in params if p.grad is not None]
-    if n == 1 or not grads:
+    n = world(group)
+    params = list(params)
+    if n == 1 or not params:
         return 0
+    # bucket over ALL parameters (a missing gradient is a zero contribution), so that every rank issues the same
+    # collectives even when a parameter received no gradient on some ranks only
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    grads = [p.grad for p in params]
     buckets, cur, cur_bytes = [], [], 0
     for g in grads:
         nbytes = g.numel() * g.element_size()
@@ -60,8 +73,9 @@ def allreduce_gradients(params, bucket_bytes=32 << 20, average=False, group=None
 
 def broadcast_parameters(module, src=0, group=None):
     """Make every rank start from rank `src`'s weights (DataParallel replicates from device 0 every step)."""
-    if world() == 1:
+    if world(group) == 1:
         return
+    src = _peer(group, src)
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
 
@@ -71,7 +85,7 @@ def masked_smooth_l1_dp(outputs, target, mask, weights=(0.5, 0.7, 1.0), group=No
     over the valid pixels of the GLOBAL batch.  Each rank contributes sum/global_count, so that summing gradients
     over ranks (allreduce_gradients(average=False)) reproduces the single-process DataParallel gradient exactly."""
     count = mask.sum().to(torch.float64)
-    if world() > 1:
+    if world(group) > 1:
         dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
     count = count.clamp_min(1.0).to(target.dtype)
     loss = target.new_zeros(())
@@ -117,7 +131,7 @@ def exchange_row_halo(x, top=1, bottom=1, dim=-2, group=None):
 
     Grouped point-to-point send/recv: each rank posts at most 2 sends + 2 recvs (`batch_isend_irecv`), which
     NCCL fuses into one launch."""
-    n, r = world(), rank()
+    n, r = world(group), rank(group)
     dim = dim % x.dim()
     shape_t = list(x.shape)
     shape_t[dim] = top
@@ -129,14 +143,14 @@ def exchange_row_halo(x, top=1, bottom=1, dim=-2, group=None):
         rows = x.shape[dim]
         if r > 0:
             if bottom:
-                ops.append(dist.P2POp(dist.isend, x.narrow(dim, 0, bottom).contiguous(), r - 1, group))
+                ops.append(dist.P2POp(dist.isend, x.narrow(dim, 0, bottom).contiguous(), _peer(group, r - 1), group))
             if top:
-                ops.append(dist.P2POp(dist.irecv, halo_t, r - 1, group))
+                ops.append(dist.P2POp(dist.irecv, halo_t, _peer(group, r - 1), group))
         if r < n - 1:
             if top:
-                ops.append(dist.P2POp(dist.isend, x.narrow(dim, rows - top, top).contiguous(), r + 1, group))
+                ops.append(dist.P2POp(dist.isend, x.narrow(dim, rows - top, top).contiguous(), _peer(group, r + 1), group))
             if bottom:
-                ops.append(dist.P2POp(dist.irecv, halo_b, r + 1, group))
+                ops.append(dist.P2POp(dist.irecv, halo_b, _peer(group, r + 1), group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
@@ -146,14 +160,14 @@ def exchange_row_halo(x, top=1, bottom=1, dim=-2, group=None):
 
 def allreduce_gn_sums(sums, group=None):
     """Sum per-band GroupNorm statistics ([B,C,2] double: sum, sum of squares) over all bands, in place."""
-    if world() > 1:
+    if world(group) > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     return sums
 
 
 def gather_bands(x, dim=-2, group=None):
     """All-gather equally sized bands along `dim` (every rank gets the full tensor)."""
-    n = world()
+    n = world(group)
     if n == 1:
         return x
     parts = [torch.empty_like(x) for _ in range(n)]

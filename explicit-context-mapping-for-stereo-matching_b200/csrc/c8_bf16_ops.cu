@@ -1,22 +1,11 @@
-// K2 (throughput path) -- 3x3x3 stride-1 convolution of the aggregation network as an implicit GEMM on the
-// 5th-generation tensor cores: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulate in TMEM), operands
-// staged by TMA, one elected thread issuing the MMAs.  Replaces nn.Conv3d(k3,s1,p1) of convbn_3d /
-// hourglass.conv2,conv4 / classif.0 (cmf/models/cmfsm.py:49-58, 248-259, 604-634) in bf16 mode.
+// Auxiliary kernels and entry points of the bf16 / C8 pipeline of the 3-D aggregation (BASELINE config 4):
+// weight packing, K1 in C8, GroupNorm apply on C8 (+ parity-split copy), layout converters, and the
+// `cmfb200_conv3d_igemm_bf16_fwd` entry (the tcgen05 kernel itself is conv3d_igemm_kdstack.cu).
 //
 // Activation layout "C8": bf16 [B][C/8][D][H][W][8] -- a voxel's 8-channel group is one 16-byte unit and the
 // voxels of a channel group are dense.  That makes every im2col row of every tap a 16-byte unit at a constant
-// pitch, which is exactly the no-swizzle K-major UMMA canonical layout ((8,m),(8,2)):((16B,SBO),(1,LBO)):
-//   * ONE rank-5 TMA box load {(8+2)*8 ch, 16+2, BD+2, C/8, 1} brings the halo'd activation block of a CTA
-//     into shared memory as [C/8][BD+2][18][10] x 16 B; out-of-volume coordinates (the conv padding) are
-//     zero-filled by the TMA unit;
-//   * the A operand of tap (kd,kh,kw), depth slice mt, k-step kc is just a descriptor on that block:
-//     start = base + 2kc*chunk + (((mt+kd)*18 + kh)*10 + kw)*16 B, SBO = 160 B (next h line), LBO = chunk:
-//     128 GEMM rows = 16 h-lines x 8 w-voxels.  No im2col buffer, every activation byte is fetched once per CTA.
-//   * weights are pre-packed per tap as [C/8][Cout][8] bf16 (same canonical layout, SBO = 128 B,
-//     LBO = Cout*16 B) and streamed through a small ring with 1-D bulk copies.
-// Work per CTA: BD depth slices x 16 x 8 voxels x all Cout; accumulators: BD tiles of 128 lanes x Cout
-// columns in TMEM.  Warp roles: w0 = TMA producer, w1 = TMEM allocator + MMA issuer, w2-5 = epilogue
-// (tcgen05.ld -> bf16 C8 store + GroupNorm sum/sum-of-squares, reduced per CTA, one double atomic per channel).
+// pitch, which is exactly the no-swizzle K-major UMMA canonical layout ((8,m),(8,2)):((16B,SBO),(1,LBO)); a
+// rank-5 TMA box load brings a halo'd activation block into shared memory with the conv padding zero-filled.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -25,174 +14,6 @@
 #include "igemm_common.cuh"
 
 namespace cmfb200 {
-
-constexpr int kIgTW = 8, kIgTH = 16;           // output tile in w, h (128 GEMM rows)
-constexpr int kIgPW = kIgTW + 2, kIgPH = kIgTH + 2;
-
-template <int CIN, int COUT, int BD, int NS>
-struct IgCfg {
-    static constexpr int NC = CIN / 8;
-    static constexpr int PD = BD + 2;
-    static constexpr int VOX = PD * kIgPH * kIgPW;
-    static constexpr int CHUNK_BYTES = VOX * 16;
-    static constexpr int A_BYTES = NC * CHUNK_BYTES;
-    static constexpr int TAP_BYTES = CIN * COUT * 2;
-    static constexpr int TMEM_COLS = (BD * COUT <= 32) ? 32 : (BD * COUT <= 64) ? 64 : (BD * COUT <= 128) ? 128
-                                     : (BD * COUT <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = A_BYTES + NS * TAP_BYTES + 1024 /*barriers, tmem ptr, reduction scratch*/
-                                      + 4 * COUT * 2 * 8 + 1024 /*alignment slack*/;
-    static_assert(BD * COUT <= 512, "accumulators exceed TMEM");
-    static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 256, "UMMA shape");
-};
-
-// ---- the kernel -------------------------------------------------------------------------------------
-template <int CIN, int COUT, int BD, int NS>
-__global__ void __launch_bounds__(kIgThreads, 2)
-    conv3d_igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ wpk,
-                             __nv_bfloat16* __restrict__ y, double* __restrict__ gn_sums, int D, int H, int W,
-                             int tiles_w) {
-    using G = IgCfg<CIN, COUT, BD, NS>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;
-    uint8_t* sW = smem + G::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + NS * G::TAP_BYTES);
-    uint64_t* barA = bars;            // activation block landed
-    uint64_t* barD = bars + 1;        // all MMAs retired, accumulators final
-    uint64_t* full = bars + 2;        // [NS] weight tap landed
-    uint64_t* empty = bars + 2 + NS;  // [NS] weight tap consumed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * NS);
-    double* sred = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [4][COUT][2]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_x = blockIdx.x % tiles_w, tile_y = blockIdx.x / tiles_w;
-    const int w0 = tile_x * kIgTW, h0 = tile_y * kIgTH, d0 = blockIdx.y * BD;
-    const int b = blockIdx.z;
-
-    if (threadIdx.x == 0) {
-        mbar_init(barA, 1);
-        mbar_init(barD, 1);
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
-        }
-        fence_mbar_init();
-    }
-    if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it at the end
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(G::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer: one box for the halo'd activation block, then the 27 weight taps
-            mbar_arrive_expect_tx(barA, G::A_BYTES);
-            tma_load_5d(sA, &tmap_x, barA, (w0 - 1) * 8, h0 - 1, d0 - 1, 0, b);
-            for (int tap = 0; tap < 27; ++tap) {
-                const int s = tap % NS;
-                if (tap >= NS) mbar_wait(empty + s, ((tap / NS) - 1) & 1);
-                mbar_arrive_expect_tx(full + s, G::TAP_BYTES);
-                bulk_g2s(sW + s * G::TAP_BYTES, wpk + (size_t)tap * CIN * COUT, G::TAP_BYTES, full + s);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer (single thread)
-            // InstrDescriptor: c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1, K-major A and B, N>>3 [17,23), M>>4 [24,29)
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
-                                       ((uint32_t)(128 >> 4) << 24);
-            const uint32_t a0 = smem_u32(sA), w_0 = smem_u32(sW);
-            mbar_wait(barA, 0);
-            tc_fence_after();
-            for (int tap = 0; tap < 27; ++tap) {
-                const int s = tap % NS;
-                const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-                mbar_wait(full + s, (tap / NS) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int mt = 0; mt < BD; ++mt) {
-                    const uint32_t arow = a0 + ((((mt + kd) * kIgPH + kh) * kIgPW) + kw) * 16;
-#pragma unroll
-                    for (int kc = 0; kc < CIN / 16; ++kc) {
-                        const uint64_t ad = umma_desc(arow + 2 * kc * G::CHUNK_BYTES, G::CHUNK_BYTES, kIgPW * 16);
-                        const uint64_t bd = umma_desc(w_0 + s * G::TAP_BYTES + 2 * kc * (COUT * 16), COUT * 16, 128);
-                        umma_bf16(tmem_base + mt * COUT, ad, bd, idesc, (tap | kc) != 0 ? 1u : 0u);
-                    }
-                }
-                umma_commit(empty + s);  // frees the weight slot once these MMAs have read it
-            }
-            umma_commit(barD);
-        }
-    } else {
-        // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;
-        const int h = h0 + (row >> 3), w = w0 + (row & 7);
-        const bool hw_ok = (h < H) && (w < W);
-        const size_t plane = (size_t)H * W;
-        mbar_wait(barD, 0);
-        tc_fence_after();
-#pragma unroll 1
-        for (int half = 0; half < COUT / 32; ++half) {
-            float s[32], ss[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                s[c] = 0.f;
-                ss[c] = 0.f;
-            }
-#pragma unroll 1
-            for (int mt = 0; mt < BD; ++mt) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + mt * COUT + half * 32, v);
-                const int d = d0 + mt;
-                if (hw_ok && d < D) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        __nv_bfloat162 p[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float f0 = __uint_as_float(v[j * 8 + 2 * e]), f1 = __uint_as_float(v[j * 8 + 2 * e + 1]);
-                            p[e] = __floats2bfloat162_rn(f0, f1);
-                            // statistics of the values actually stored (bf16-rounded), so GroupNorm is self-consistent
-                            const float r0 = __low2float(p[e]), r1 = __high2float(p[e]);
-                            s[j * 8 + 2 * e] += r0;
-                            ss[j * 8 + 2 * e] = fmaf(r0, r0, ss[j * 8 + 2 * e]);
-                            s[j * 8 + 2 * e + 1] += r1;
-                            ss[j * 8 + 2 * e + 1] = fmaf(r1, r1, ss[j * 8 + 2 * e + 1]);
-                        }
-                        const int chunk = half * 4 + j;
-                        __nv_bfloat16* dst = y + ((((size_t)b * (COUT / 8) + chunk) * D + d) * plane + (size_t)h * W + w) * 8;
-                        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(p);
-                    }
-                }
-            }
-            if (gn_sums != nullptr) {  // lane l ends up with the warp total of column half*32 + l
-                sred[(quad * COUT + half * 32 + lane) * 2 + 0] = (double)warp_transpose_sum32(s, lane);
-                sred[(quad * COUT + half * 32 + lane) * 2 + 1] = (double)warp_transpose_sum32(ss, lane);
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (gn_sums != nullptr && threadIdx.x < COUT * 2) {
-        const int c = threadIdx.x >> 1, which = threadIdx.x & 1;
-        double a = 0.0;
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) a += sred[(qd * COUT + c) * 2 + which];
-        atomicAdd(gn_sums + ((size_t)b * COUT + c) * 2 + which, a);
-    }
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(G::TMEM_COLS)
-                     : "memory");
-    }
-}
 
 // ---- auxiliary kernels of the bf16 / C8 pipeline -----------------------------------------------------
 // weights: conv [Cout][Cin][27] (or deconv [Cin][Cout][27]) fp32 -> bf16 [27][Cin/8][Cout][8]
@@ -399,37 +220,9 @@ __global__ void f32_to_c8_bf16_kernel(const float* __restrict__ x, __nv_bfloat16
     }
 }
 
-// ---- host side ----------------------------------------------------------------------------------------
-template <int CIN, int COUT, int BD, int NS>
-static int launch_igemm(const void* x, const void* wpk, void* y, double* gn, int B, int D, int H, int W,
-                        cudaStream_t st) {
-    using G = IgCfg<CIN, COUT, BD, NS>;
-    EncodeTiledFn encode = get_encode_fn();
-    CMF_REQUIRE(encode != nullptr, "conv3d_igemm: cuTensorMapEncodeTiled is not available from this driver");
-    CUtensorMap tmap;
-    const cuuint64_t gdim[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)G::NC, (cuuint64_t)B};
-    const cuuint64_t gstr[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
-                                (cuuint64_t)G::NC * D * H * W * 16};
-    const cuuint32_t box[5] = {kIgPW * 8, kIgPH, (cuuint32_t)G::PD, (cuuint32_t)G::NC, 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CMF_REQUIRE(r == CUDA_SUCCESS, "conv3d_igemm: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    auto kern = conv3d_igemm_bf16_kernel<CIN, COUT, BD, NS>;
-    CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-    const int tiles_w = (int)cdiv(W, kIgTW), tiles_h = (int)cdiv(H, kIgTH);
-    dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)cdiv(D, BD), (unsigned)B);
-    CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d_igemm: grid too large");
-    kern<<<grid, kIgThreads, G::SMEM_BYTES, st>>>(tmap, reinterpret_cast<const __nv_bfloat16*>(wpk),
-                                                  reinterpret_cast<__nv_bfloat16*>(y), gn, D, H, W, tiles_w);
-    CMF_LAUNCH_CHECK("conv3d_igemm_bf16_kernel");
-    return CMFB200_OK;
-}
-
-// persistent schedule (conv3d_igemm_persistent.cu); the kernel above is kept as the simple reference schedule
-int conv3d_igemm_persistent_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout,
-                                     int D, int H, int W, cudaStream_t st);
+// depth-stacked persistent schedule (conv3d_igemm_kdstack.cu): 32->32, 64->32, 64->64
+int conv3d_igemm_kdstack_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout, int D,
+                                  int H, int W, cudaStream_t st);
 
 }  // namespace cmfb200
 
@@ -452,13 +245,9 @@ extern "C" int cmfb200_conv3d_igemm_bf16_fwd(const void* x_c8, const void* packe
     CMF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_igemm_bf16_fwd: non-positive dimension");
     CMF_REQUIRE((reinterpret_cast<uintptr_t>(x_c8) & 15) == 0, "conv3d_igemm_bf16_fwd: input must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    static const bool simple_schedule = getenv("CMFB200_IGEMM_SIMPLE") != nullptr;  // A/B switch for profiling
-    if (!simple_schedule) return conv3d_igemm_persistent_dispatch(x_c8, packed_w, y_c8, gn_sums, B, Cin, Cout, D, H, W, st);
-    if (Cin == 32 && Cout == 32) return launch_igemm<32, 32, 4, 4>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
-    if (Cin == 64 && Cout == 32) return launch_igemm<64, 32, 2, 4>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
-    if (Cin == 64 && Cout == 64) return launch_igemm<64, 64, 2, 2>(x_c8, packed_w, y_c8, gn_sums, B, D, H, W, st);
-    CMF_REQUIRE(false, "conv3d_igemm_bf16_fwd: unsupported (Cin=%d, Cout=%d); supported: 32->32, 64->32, 64->64", Cin,
-                Cout);
+    CMF_REQUIRE(Cout == 32 || (Cin == 64 && Cout == 64),
+                "conv3d_igemm_bf16_fwd: unsupported (Cin=%d, Cout=%d); supported: 32->32, 64->32, 64->64", Cin, Cout);
+    return conv3d_igemm_kdstack_dispatch(x_c8, packed_w, y_c8, gn_sums, B, Cin, Cout, D, H, W, st);
 }
 
 extern "C" int cmfb200_cost_volume_concat_c8_bf16(const float* L, const float* R, void* cost_c8, int B, int C, int h,

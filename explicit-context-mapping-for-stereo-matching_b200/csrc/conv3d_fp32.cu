@@ -3,7 +3,7 @@
 // convbn_3d, hourglass and classif (cmf/models/cmfsm.py:49-58, 240-303, 604-634).  This is the mode the
 // fp32 parity gate runs in (the reference's fp32 result moves by 2e-3 px between thread counts, SURVEY.md
 // section 0.7, so tensor-core operand rounding is not an option here); the bf16 tcgen05 implicit GEMM in
-// conv3d_igemm.cu is the throughput mode.
+// conv3d_igemm_kdstack.cu is the throughput mode.
 //
 // Register-tiled direct convolution: a CTA owns a TD x TH x 32 block of output voxels and ALL output
 // channels; per chunk of CC input channels the halo'd input patch and the [CC][27][COUT] weight slice
@@ -695,15 +695,12 @@ extern "C" int cmfb200_pack_conv3d_weight(const float* weight, float* packed, in
 
 static int conv3d_k3_dispatch(const float* x, const float* packed_w, float* y, double* gn_sums, int B, int Cin, int Cout,
                              int D, int H, int W, int stride, RowWin rw, cudaStream_t st) {
-    static const bool one_row = getenv("CMFB200_CONV3D_ONE_ROW") != nullptr;  // A/B switch for profiling
-    if (Cout == 32 && stride == 1 && !one_row) return launch_conv_r2_best<32, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
-    if (Cout == 64 && stride == 1 && !one_row) return launch_conv_r2_best<64, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
-    if (Cout == 32 && stride == 1) return launch_conv_best<32, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
-    if (Cout == 64 && stride == 1) return launch_conv_best<64, 8, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
+    if (Cout == 32 && stride == 1) return launch_conv_r2_best<32, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
+    if (Cout == 64 && stride == 1) return launch_conv_r2_best<64, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
     if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
     if (Cout == 64 && stride == 2) return launch_conv<64, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
     if (Cout == 1 && stride == 1) {
-        if (gn_sums == nullptr && !one_row && rw.Ho < 0) {  // classifier tail: TMA-staged 4x4-outputs-per-thread kernel
+        if (gn_sums == nullptr && rw.Ho < 0) {  // classifier tail: TMA-staged 4x4-outputs-per-thread kernel
             const int rc = conv3d_cout1_fp32_dispatch(x, packed_w, y, B, Cin, D, H, W, st);
             if (rc >= 0) return rc;
         }

@@ -1,7 +1,7 @@
 // K2 (throughput path) -- "kd-stacked" persistent implicit GEMM for the stride-1 3x3x3 layers: 32->32, 64->32 and
 // 64->64 (as two independent groups of 32 output channels, each on half of the CTAs).
 //
-// conv3d_igemm_persistent.cu issues one M128 x N32 MMA per (tap, k-step): with both operands in shared memory such an
+// A per-tap schedule issues one M128 x N32 MMA per (tap, k-step): with both operands in shared memory such an
 // MMA reads 4 KB of A + 1 KB of B through the 128 B/clk port = 40 clk for 16 clk of tensor work (the 40 % ceiling
 // measured there).  Here the three depth taps share one A read:
 //
@@ -297,7 +297,7 @@ static int launch_kdstack(const void* x, const void* wpk, void* y, double* gn, i
     return CMFB200_OK;
 }
 
-// used by conv3d_igemm_persistent_dispatch: 32->32, 64->32 and (as two groups of 32 output channels) 64->64
+// used by cmfb200_conv3d_igemm_bf16_fwd (c8_bf16_ops.cu): 32->32, 64->32 and (as two groups of 32 output channels) 64->64
 int conv3d_igemm_kdstack_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout, int D,
                                   int H, int W, cudaStream_t st) {
     if (Cin == 32) return launch_kdstack<32, 6, false>(x, wpk, y, gn, B, Cout, D, H, W, st);

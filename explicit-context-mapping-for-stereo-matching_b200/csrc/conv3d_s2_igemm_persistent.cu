@@ -1,5 +1,5 @@
 // K2 (throughput path) -- PERSISTENT stride-2 3x3x3 conv (hourglass.conv1 / conv3, cmf/models/cmfsm.py:244-254) on
-// the parity-split C8/bf16 input.  Same decomposition as conv3d_s2_igemm_bf16_kernel (conv3d_igemm_s2.cu): input
+// the parity-split C8/bf16 input.  Decomposition (see c8_s2_entry.cu): input
 // index i = 2*o + k - 1, so tap k=1 reads parity-0 inputs at o and taps k=0 / k=2 read parity-1 inputs at o-1 / o;
 // the eight parity sub-volumes of a tile are eight TMA boxes feeding 1, 2, 4 or 8 taps each into one accumulator.
 // What changes is the schedule (the one-tile-per-CTA kernel re-streamed all 27 weight taps per tile and paid the CTA
@@ -281,7 +281,7 @@ static int launch_s2_persistent(const void* xs, const void* wpk, void* y, double
     return CMFB200_OK;
 }
 
-// used by cmfb200_conv3d_s2_igemm_bf16_fwd (conv3d_igemm_s2.cu)
+// used by cmfb200_conv3d_s2_igemm_bf16_fwd (c8_s2_entry.cu)
 int conv3d_s2_igemm_persistent_dispatch(const void* xs, const void* wpk, void* y, double* gn, int B, int Cin, int Cout,
                                         int Do, int Ho, int Wo, cudaStream_t st) {
     if (Cin == 32 && Cout == 64) return launch_s2_persistent<32, 64, 2, 3>(xs, wpk, y, gn, B, Cout, Do, Ho, Wo, st);

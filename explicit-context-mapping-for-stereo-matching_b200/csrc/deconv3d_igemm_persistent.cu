@@ -1,5 +1,5 @@
 // K2 (throughput path) -- PERSISTENT transposed conv (k3 s2 p1 op1, hourglass.conv5/conv6, cmf/models/cmfsm.py:261-281)
-// on the C8/bf16 layout.  Same decomposition as deconv3d_igemm_bf16_kernel (conv3d_igemm_s2.cu): an output voxel of
+// on the C8/bf16 layout.  Decomposition (see c8_s2_entry.cu): an output voxel of
 // parity 0 along an axis takes tap k=1 of input i, parity 1 takes tap k=2 of input i and tap k=0 of input i+1.  What
 // changes is the schedule (the one-tile-per-CTA kernel spent most of its time in CTA start-up and in re-streaming
 // up to 110 KB of weights per tile):
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
     }
 }
 
-// used by cmfb200_deconv3d_igemm_bf16_fwd (conv3d_igemm_s2.cu); Cin = 64, Cout = 32 or 64
+// used by cmfb200_deconv3d_igemm_bf16_fwd (c8_s2_entry.cu); Cin = 64, Cout = 32 or 64
 int deconv3d_igemm_persistent_dispatch(const void* x, const void* wpk, void* y, double* gn, int B, int Cin, int Cout,
                                        int D, int H, int W, cudaStream_t st) {
     CMF_REQUIRE(Cin == 64 && (Cout == 32 || Cout == 64), "deconv3d_igemm_persistent: unsupported (Cin=%d, Cout=%d)", Cin, Cout);

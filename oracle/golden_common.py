@@ -69,3 +69,26 @@ def head_input():
 def classif_input():
     g = torch.Generator().manual_seed(SEED_CLS_X)
     return torch.randn(2, 32, 6, 8, 12, generator=g)
+
+
+def flying_padded_pair(seed=INPUT_SEED, structured=False):
+    """BASELINE config 2 input: a 540x960 pair fed as 576x960 the way the reference test loader pads it
+    (cmf/loader/Flying3d.py:67-72: the last 36 rows are appended once more).  Same stream as bench.py."""
+    if structured:
+        left, right = structured_pair(540, 960, delta=20, seed=seed)
+    else:
+        g = torch.Generator().manual_seed(seed)
+        left, right = torch.rand(1, 3, 540, 960, generator=g), torch.rand(1, 3, 540, 960, generator=g)
+    return tuple(torch.cat([x, x[:, :, -36:]], 2).contiguous() for x in (left, right))
+
+
+def kitti_padded_pair(seed=INPUT_SEED, delta=20):
+    """BASELINE config 4 input: a 375x1242 structured pair (true disparity `delta`) padded to 384x1248 the way
+    the reference KITTI loader does (cmf/loader/KITTI.py:100-108: the first 9 rows are prepended, then the first
+    6 columns)."""
+    left, right = structured_pair(375, 1242, delta=delta, seed=seed)
+    out = []
+    for x in (left, right):
+        x = torch.cat([x[:, :, :384 - 375], x], 2)
+        out.append(torch.cat([x[:, :, :, :1248 - 1242], x], 3).contiguous())
+    return tuple(out)

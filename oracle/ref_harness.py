@@ -1,8 +1,10 @@
-"""Import the UNMODIFIED reference (`/root/reference/cmf`) on CPU.
+"""Import the UNMODIFIED reference package `cmf` (CPU, or the GPU under cuDNN with TF32 off).
 
 TEST INFRASTRUCTURE ONLY -- used in the build container to pin the oracle restatement
-(`oracle/cmfsm_oracle.py`) and to generate `tests/golden/*` (see `oracle/gen_golden.py`).
-`/root/reference` does not exist on the GPU box, so nothing at run time may import this.
+(`oracle/cmfsm_oracle.py`) and to generate `tests/golden/*` (see `oracle/gen_golden.py`), and by the
+`--impl reference` arm of bench.py / the driver drop-in test.  The reference tree is looked up at
+`$CMF_REFERENCE_ROOT`, then `oracle/_ref/reference` (an unmodified copy staged by
+`__graft_entry__.build()`, git-ignored, shipped to the GPU box with the snapshot), then `/root/reference`.
 
 Two shims are needed:
   1. `cmf.caffe_pb2` is stale protobuf codegen imported (and never used) at cmf/models/cmfsm.py:19.
@@ -13,7 +15,9 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CMF_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")
+REFERENCE_ROOT = os.environ.get("CMF_REFERENCE_ROOT") or (_STAGED if os.path.isdir(os.path.join(_STAGED, "cmf", "models"))
+                                                           else "/root/reference")
 
 
 def reference_available():

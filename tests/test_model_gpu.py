@@ -56,7 +56,10 @@ def test_forward_batch2_matches_per_sample(model):
         one = model(left[1:2].contiguous(), right[1:2].contiguous())
     for a, b in zip(both, one):
         assert a.shape == (2, 1, 256, 512)
-        torch.testing.assert_close(a[1:2], b, rtol=0, atol=5e-3)
+        # different grid partition -> different order of the GroupNorm double atomics; the reference's own B=2 vs B=1
+        # runs differ by 8e-4 px and its 8-thread vs 1-thread runs by 2.1e-3 px
+        print("batched vs per-sample: max|d| %.3e px" % float((a[1:2] - b).abs().max()))
+        torch.testing.assert_close(a[1:2], b, rtol=0, atol=2e-3)
 
 
 def test_forward_vs_cpu_oracle_structured_pair(model):
@@ -97,35 +100,162 @@ def test_cuda_graph_replay_matches_eager(model):
         finally:
             model.enable_cuda_graph(False)
     for a, b, c in zip(eager, first, again):
-        # GroupNorm statistics use double atomics whose order is not fixed: allow the last-bit noise floor
-        torch.testing.assert_close(a, b, rtol=0, atol=5e-3)
-        torch.testing.assert_close(b, c, rtol=0, atol=5e-3)
+        # Replay and eager run the same kernels on the same data; the only freedom is the order of the double
+        # atomics of the GroupNorm statistics (last-bit changes of mean/var), which this network amplifies.  The
+        # measured difference is printed; the gate is 1/10 of the fp32-vs-fp64 distance of the reference itself.
+        print("graph replay vs eager: max|d| %.3e ; replay vs replay: %.3e" % (float((a - b).abs().max()),
+                                                                             float((b - c).abs().max())))
+        torch.testing.assert_close(a, b, rtol=0, atol=1e-3)
+        torch.testing.assert_close(b, c, rtol=0, atol=1e-3)
+
+
+def test_cuda_graph_is_dropped_when_weights_change():
+    """A captured graph bakes in the packed conv weights: after an in-place weight update (optimizer.step /
+    load_state_dict) the next forward must re-capture, not replay stale weights."""
+    from cmf.models import get_model
+
+    torch.manual_seed(5)
+    net = get_model("cmfsm").to(DEV).eval()
+    left, right = gc.seeded_pair(1, 256, 512, seed=12)
+    left, right = left.to(DEV), right.to(DEV)
+    net.enable_cuda_graph(True)
+    with torch.no_grad():
+        before = net(left, right)
+        net.dres0[0][0].weight.mul_(1.5)  # in place: same data_ptr, `_version` moves
+        net.feature_extraction.lastconv[2].weight.add_(0.01)
+        after_graph = net(left, right)
+        net.enable_cuda_graph(False)
+        after_eager = net(left, right)
+    assert float((before[2] - after_eager[2]).abs().mean()) > 1e-2  # the update matters
+    for a, b in zip(after_graph, after_eager):
+        torch.testing.assert_close(a, b, rtol=0, atol=1e-3)
+
+
+def test_dataparallel_replicas_never_reuse_packed_weights():
+    """nn.DataParallel replicas get freshly broadcast weights every forward; they must not hit the packed-weight
+    cache of an earlier forward.  One device is enough to exercise the replica path."""
+    from cmf.models import get_model
+
+    torch.manual_seed(6)
+    net = get_model("cmfsm").to(DEV).eval()
+    left, right = gc.seeded_pair(1, 256, 512, seed=13)
+    left, right = left.to(DEV), right.to(DEV)
+    replica = torch.nn.parallel.replicate(net, [0])[0]
+    with torch.no_grad():
+        a = replica(left, right)
+        net.dres0[0][0].weight.mul_(1.5)
+        replica = torch.nn.parallel.replicate(net, [0])[0]
+        b = replica(left, right)
+        want = net(left, right)
+    assert float((a[2] - b[2]).abs().mean()) > 1e-2
+    for x, y in zip(b, want):
+        torch.testing.assert_close(x, y, rtol=0, atol=1e-3)
+
+
+def _epe_pairs(model, pairs, gt=20.0):
+    """Dataset EPE (mean |d - gt| over all pixels of all pairs) of both aggregation modes + per-pixel deviation."""
+    rows, dev = [], []
+    try:
+        for left, right in pairs:
+            left, right = left.to(DEV), right.to(DEV)
+            with torch.no_grad():
+                model.aggregation = "fp32"
+                ref = model(left, right)
+                model.aggregation = "bf16"
+                got = model(left, right)
+            assert all(torch.isfinite(a).all() for a in got)
+            rows.append([(float((a - gt).abs().mean()), float((b - gt).abs().mean())) for a, b in zip(got, ref)])
+            dev.append([float((a - b).abs().mean()) for a, b in zip(got, ref)])
+    finally:
+        model.aggregation = "fp32"
+    return rows, dev
 
 
 def test_bf16_aggregation_mode(model):
     """bf16-operand / fp32-accumulate 3-D aggregation (tcgen05 implicit GEMM) vs the fp32 CUDA path.
 
-    Gates (north star / SURVEY.md 8c): |EPE_bf16 - EPE_fp32| <= 0.02 px against the synthetic ground truth of the
-    structured pair (true disparity 20 px); the per-pixel deviation on RANDOM-INIT weights is reported next to the
-    survey's own measurement of bf16 operand rounding (mean 0.49-0.67 px, max 6.5-16 px) and bounded by 2x that.
-    """
-    left, right = gc.structured_pair(256, 512, delta=20)
-    left, right = left.to(DEV), right.to(DEV)
-    try:
-        with torch.no_grad():
-            model.aggregation = "fp32"
-            ref = model(left, right)
-            model.aggregation = "bf16"
-            got = model(left, right)
-    finally:
+    Gate (north star / SURVEY.md 8c): |EPE_bf16 - EPE_fp32| <= 0.02 px.  EPE is a DATASET statistic (mean end-point
+    error over all pixels of all pairs); on random-init weights the per-pair value of the delta scatters by about
+    +-0.03 px between input seeds for ANY bf16 rounding scheme (tools/emulate_bf16_schemes.py, CPU emulation), so it
+    is evaluated over four structured 256x512 pairs (true disparity 20 px) and the per-pair values are printed.
+    The per-pixel deviation is bounded by 2x the survey's measurement of pure bf16 operand rounding (0.49-0.67 px)."""
+    pairs = [gc.structured_pair(256, 512, delta=20, seed=s) for s in (1, 2, 3, 4)]
+    rows, dev = _epe_pairs(model, pairs)
+    for i in range(3):
+        epe16 = sum(r[i][0] for r in rows) / len(rows)
+        epe32 = sum(r[i][1] for r in rows) / len(rows)
+        print("pred%d bf16-vs-fp32 over %d pairs: EPE bf16 %.4f fp32 %.4f |delta| %.4f (per pair %s); mean|d| %s px"
+              % (i + 1, len(rows), epe16, epe32, abs(epe16 - epe32), ["%+.4f" % (r[i][0] - r[i][1]) for r in rows],
+                 ["%.3f" % d[i] for d in dev]))
+        assert abs(epe16 - epe32) <= 0.02
+        assert max(d[i] for d in dev) < 1.4
+
+
+def test_config4_shape_batch_fp32_golden_and_bf16_epe(model, golden_dir):
+    """BASELINE config 4 shape: 384x1248 (KITTI top/left pad, cmf/loader/KITTI.py:100-108), B=2, per-sample output
+    semantics.  fp32: against the outputs of the UNMODIFIED reference run per sample at B=1 and against the fp64
+    oracle (fixtures of oracle/gen_golden_configs.py), usual gate.  bf16 aggregation: dataset |EPE delta| <= 0.02 px
+    against the true disparity of the structured pairs."""
+    g = np.load(os.path.join(golden_dir, "cmfsm_configs.npz"))
+    meta = json.load(open(os.path.join(golden_dir, "cmfsm_configs_meta.json")))
+    sub = meta["sub"]
+    pairs = [gc.kitti_padded_pair(1), gc.kitti_padded_pair(2)]
+    left = torch.cat([p[0] for p in pairs]).to(DEV)
+    right = torch.cat([p[1] for p in pairs]).to(DEV)
+    with torch.no_grad():
         model.aggregation = "fp32"
-    for i, (a, b) in enumerate(zip(got, ref), 1):
-        d = (a - b).abs()
-        epe_a, epe_b = float((a - 20.0).abs().mean()), float((b - 20.0).abs().mean())
-        print("pred%d bf16-vs-fp32: mean|d| %.3f max|d| %.2f px ; EPE vs GT: bf16 %.4f fp32 %.4f delta %.4f"
-              % (i, d.mean(), d.max(), epe_a, epe_b, abs(epe_a - epe_b)))
-        assert torch.isfinite(a).all()
-        assert float(d.mean()) < 1.4 and abs(epe_a - epe_b) < 0.05
+        outs32 = model(left, right)
+        model.aggregation = "bf16"
+        try:
+            outs16 = model(left, right)
+        finally:
+            model.aggregation = "fp32"
+    for b, case in enumerate(("c4_s1", "c4_s2")):
+        ref_dist = meta["cases"][case]["ref32_vs_fp64_max_mean"]
+        for i in range(3):
+            got = outs32[i][b, 0, ::sub, ::sub].cpu().double()
+            d64 = (got - torch.from_numpy(g["%s_pred%d_fp64" % (case, i + 1)])).abs()
+            d32 = (got - torch.from_numpy(g["%s_pred%d_ref32" % (case, i + 1)]).double()).abs()
+            print("%s pred%d fp32: |ours-fp64| max %.2e mean %.2e ; |ref32-fp64| max %.2e mean %.2e ; |ours-ref32| max %.2e"
+                  % (case, i + 1, d64.max(), d64.mean(), ref_dist[i][0], ref_dist[i][1], d32.max()))
+            assert float(d64.max()) <= 2 * ref_dist[i][0] + 2e-3
+            assert float(d64.mean()) <= 2 * ref_dist[i][1] + 1e-4
+    for i in range(3):
+        assert tuple(outs16[i].shape) == (2, 1, 384, 1248) and torch.isfinite(outs16[i]).all()
+        epe16, epe32 = float((outs16[i] - 20.0).abs().mean()), float((outs32[i] - 20.0).abs().mean())
+        print("config-4 shape pred%d: EPE bf16 %.4f fp32 %.4f |delta| %.4f ; mean|d| %.3f px"
+              % (i + 1, epe16, epe32, abs(epe16 - epe32), float((outs16[i] - outs32[i]).abs().mean())))
+        assert abs(epe16 - epe32) <= 0.02
+
+
+def test_config2_forward_vs_reference_golden(model, golden_dir):
+    """BASELINE config 2 (the shape the headline number is quoted on): 540x960 fed as 576x960, fp32, against the
+    outputs of the UNMODIFIED reference and the fp64 oracle at that shape (oracle/gen_golden_configs.py); then the
+    bf16 aggregation mode at the same shape against our fp32 result."""
+    g = np.load(os.path.join(golden_dir, "cmfsm_configs.npz"))
+    meta = json.load(open(os.path.join(golden_dir, "cmfsm_configs_meta.json")))
+    sub, ref_dist = meta["sub"], meta["cases"]["c2"]["ref32_vs_fp64_max_mean"]
+    left, right = gc.flying_padded_pair(1)
+    left, right = left.to(DEV), right.to(DEV)
+    with torch.no_grad():
+        outs = model(left, right)
+        model.aggregation = "bf16"
+        try:
+            outs16 = model(left, right)
+        finally:
+            model.aggregation = "fp32"
+    for i in range(3):
+        assert tuple(outs[i].shape) == (1, 1, 576, 960)
+        got = outs[i][0, 0, ::sub, ::sub].cpu().double()
+        d64 = (got - torch.from_numpy(g["c2_pred%d_fp64" % (i + 1)])).abs()
+        d32 = (got - torch.from_numpy(g["c2_pred%d_ref32" % (i + 1)]).double()).abs()
+        dev = (outs16[i] - outs[i]).abs()
+        print("config 2 pred%d fp32: |ours-fp64| max %.2e mean %.2e ; |ref32-fp64| max %.2e mean %.2e ; |ours-ref32| max "
+              "%.2e mean %.2e ; bf16-vs-fp32 mean %.3f max %.2f px"
+              % (i + 1, d64.max(), d64.mean(), ref_dist[i][0], ref_dist[i][1], d32.max(), d32.mean(), dev.mean(), dev.max()))
+        assert float(d64.max()) <= 2 * ref_dist[i][0] + 2e-3
+        assert float(d64.mean()) <= 2 * ref_dist[i][1] + 1e-4
+        assert torch.isfinite(outs16[i]).all() and float(dev.mean()) < 1.4
 
 
 def test_training_step_gradients_flow(model):

@@ -195,3 +195,22 @@ def test_shape_validation():
     with pytest.raises(ValueError):
         orc.check_shapes(256, 256, 192)
     orc.check_shapes(576, 960, 192)
+
+
+def test_oracle_at_config4_shape_vs_reference_golden(golden_dir):
+    """The oracle at the KITTI-padded 384x1248 shape (BASELINE config 4) against the UNMODIFIED reference's outputs
+    (oracle/gen_golden_configs.py).  Thread count differs from the generating run, so the gate is the reference's
+    own thread-count reproducibility (2.1e-3 px), not bit equality."""
+    from cmf.models.cmfsm import cmfsm  # parameter container (seeded init == the reference's, test_boundary.py)
+
+    g = _npz(golden_dir, "cmfsm_configs.npz")
+    meta = json.load(open(os.path.join(golden_dir, "cmfsm_configs_meta.json")))
+    assert all(c["oracle_equals_reference"] for c in meta["cases"].values())
+    torch.manual_seed(gc.WEIGHT_SEED)
+    sd = {k: v.detach() for k, v in cmfsm().state_dict().items()}
+    left, right = gc.kitti_padded_pair(1)
+    assert tuple(left.shape) == (1, 3, 384, 1248)
+    outs = orc.forward(sd, left, right, 192)
+    for i, o in enumerate(outs, 1):
+        d = (o[0, 0, ::meta["sub"], ::meta["sub"]] - g["c4_s1_pred%d_ref32" % i]).abs()
+        assert float(d.max()) < 5e-3, (i, float(d.max()))
