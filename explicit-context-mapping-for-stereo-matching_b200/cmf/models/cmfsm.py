@@ -162,6 +162,9 @@ class cmfsm(nn.Module):
         # 3-D aggregation arithmetic: "fp32" (CUDA-core FMA, the parity mode BASELINE config 2 is quoted in) or
         # "bf16" (tcgen05 implicit GEMM, bf16 operands / fp32 accumulate, BASELINE config 4)
         self.aggregation = os.environ.get("CMF_B200_AGGREGATION", "fp32")
+        # fp32 convolutions at inference: "tc3" = fp32-accurate three-term bf16 split on the tensor cores
+        # (csrc/conv_tc3.cu; stride-1 layers, the rest stays on the FFMA kernels), "ffma" = CUDA-core FMA everywhere
+        self.conv_engine = os.environ.get("CMF_B200_CONV", "tc3")
         self._graphs = None  # enable_cuda_graph(): {(shape, device, aggregation): captured forward}
 
     # -------------------------------------------------------------------------------- helpers
@@ -228,6 +231,58 @@ class cmfsm(nn.Module):
         feat, _ = self._c2(fe.lastconv[2], o, False)
         return feat, full
 
+    # ---- 2-D extractor with the stride-1 convolutions on the tensor cores (fp32-accurate split-bf16, conv_tc3.cu).
+    # Activations travel as C8S3 (three bf16 terms = the fp32 value); the stride-2 convs, the 3-channel stem and the
+    # tiny SPP branch convs stay on the FFMA kernels (NCHW fp32), the GroupNorm apply converts between the two.
+    def _pack_tc3(self, conv):
+        return self._cached(conv, "tc3", ops.pack_tc3_weight)
+
+    def _cg_tc(self, block, x_s3, res_s3=None, relu=False, want_s3=True, want_nchw=False):
+        conv, gn = block[0], block[1]
+        y, sums = ops.conv_tc3(x_s3, self._pack_tc3(conv), conv.dilation[0], True)
+        return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, True, res_s3=res_s3, relu=relu, want_s3=want_s3,
+                                want_nchw=want_nchw)
+
+    def _cg_ffma_to_s3(self, block, x_nchw, relu=False):
+        """FFMA conv on NCHW fp32 + GroupNorm, result as C8S3."""
+        y, sums = self._c2(block[0], x_nchw, True)
+        return ops.gn_apply_tc3(y, sums, block[1].weight, block[1].bias, False, relu=relu)[0]
+
+    def _features_tc3(self, x):
+        fe = self.feature_extraction
+        o = self._cg_ffma_to_s3(fe.firstconv[0], x, relu=True)  # 3 -> 32: K = 27, stays on CUDA cores
+        o, _ = self._cg_tc(fe.firstconv[2], o, relu=True)
+        o, _ = self._cg_tc(fe.firstconv[4], o, relu=True)
+        full, fsums = ops.conv_tc3(o, self._pack_tc3(fe.firstconv[6]), 1, True, out_nchw=True)  # kept: K5's "hr" input
+        gn0 = fe.secondconv[0]
+        o = ops.gn_apply(full, fsums, gn0.weight, gn0.bias, None, True)  # statistics came from the conv epilogue
+        o = self._cg_ffma_to_s3(fe.secondconv[2], o, relu=True)  # stride 2
+        o, o_nchw = self._cg_tc(fe.secondconv[4], o, relu=True)
+        raw = raw_nchw = None
+        for name in ("layer1", "layer2", "layer3", "layer4"):
+            units = getattr(fe, name)
+            for i, unit in enumerate(units):
+                last = i == len(units) - 1
+                # NCHW copies: layer1 -> the stride-2 FFMA convs of layer2; layer2 / layer4 -> the SPP kernels
+                want_nchw = last and name in ("layer1", "layer2", "layer4")
+                want_s3 = not (last and name == "layer4")
+                if unit.conv1[0][0].stride[0] == 2:
+                    t = self._cg_ffma_to_s3(unit.conv1[0], o_nchw, relu=True)
+                    skip = self._cg_ffma_to_s3(unit.downsample, o_nchw)
+                else:
+                    t, _ = self._cg_tc(unit.conv1[0], o, relu=True)
+                    skip = o if unit.downsample is None else self._cg_tc(unit.downsample, o)[0]
+                o, o_nchw = self._cg_tc(unit.conv2, t, res_s3=skip, want_s3=want_s3, want_nchw=want_nchw)
+            if name == "layer2":
+                raw_nchw = o_nchw
+        skip_nchw = o_nchw
+        pooled = ops.spp_pool(skip_nchw)
+        b1, b2, b3, b4 = [self._cg2(getattr(fe, "branch%d" % (i + 1))[1], p, relu=True) for i, p in enumerate(pooled)]
+        cat = ops.f32_to_c8s3(ops.spp_upsample_concat(raw_nchw, skip_nchw, b4, b3, b2, b1))
+        o, _ = self._cg_tc(fe.lastconv[0], cat, relu=True)
+        feat, _ = ops.conv_tc3(o, self._pack_tc3(fe.lastconv[2]), 1, False, out_nchw=True)
+        return feat, full
+
     # ---- the same extractor under autograd (training): forward = the same kernels, backward per cmf_b200.autograd_ops
     def _features_train(self, x):
         fe = self.feature_extraction
@@ -288,22 +343,16 @@ class cmfsm(nn.Module):
         out = self._ig(hg.conv6, post, residual=resid, relu=False, split=split_out)
         return out, pre, post
 
-    def _pack_ig_cout1(self, conv):
-        def make(w):
-            padded = torch.zeros((32,) + tuple(w.shape[1:]), device=w.device, dtype=w.dtype)
-            padded[:1] = w.detach()
-            return ops.pack_igemm_weight(padded)
-
-        return self._cached(conv, "ig1", make)
-
-    def _pack_cout1_taps(self, conv):
-        return self._cached(conv, "taps", ops.pack_cout1_taps)
-
     def _classify_bf16(self, head, x):
-        t = self._ig(head[0], x, relu=True)
-        if os.environ.get("CMF_B200_COUT1_GATHER"):  # A/B switch: N=27 GEMM per plane + 27-point gather (same speed today)
-            return ops.conv3d_igemm_cout1_gather(t, self._pack_cout1_taps(head[2]))
-        return ops.conv3d_igemm_cout1(t, self._pack_ig_cout1(head[2]))
+        """classifN: 32->32 conv on tcgen05 (bf16), GroupNorm + ReLU kept in fp32, then the 32->1 tail on the fp32 FFMA
+        kernel with fp32 weights.  The tail's logits feed the soft-argmin directly and are the rounding-sensitive spot
+        of the bf16 mode: with bf16 operands there the dataset |EPE delta| sits at 0.02-0.03 px, with this tail at
+        0.01-0.017 px (tools/emulate_bf16_schemes.py, 12 pairs) for +0.04 ms per launch."""
+        conv, gn = head[0][0], head[0][1]
+        y, sums = ops.conv3d_igemm(x, self._pack_ig(conv))
+        t = ops.gn_apply_c8(y, sums, gn.weight, gn.bias, None, True, f32_out=True)
+        out, _ = ops.conv3d_k3(t, self._pack(head[2]), 1)
+        return out.squeeze(1)
 
     def _aggregate_bf16(self, lfeat, rfeat, D):
         cost = ops.cost_volume_concat_c8(lfeat, rfeat, D)
@@ -320,6 +369,58 @@ class cmfsm(nn.Module):
         out3, _pre3, _post3 = self._hourglass_bf16(self.dres4, out2, out2_split, pre1, post2, cost0, False)
         return (self._classify_bf16(self.classif1, out1), self._classify_bf16(self.classif2, out2),
                 self._classify_bf16(self.classif3, out3))
+
+    # ---- fp32 aggregation with the stride-1 3x3x3 convs on the tensor cores (fp32-accurate split-bf16, conv_tc3.cu);
+    # stride-2 / transposed / 32->1 layers stay on the FFMA kernels (NCDHW fp32), GroupNorm apply converts.
+    def _cg3_tc(self, block, x_s3, res_nchw=None, relu=False, want_s3=True, want_nchw=False):
+        conv, gn = block[0], block[1]
+        y, sums = ops.conv_tc3(x_s3, self._pack_tc3(conv), 1, True)
+        return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, True, res_nchw=res_nchw, relu=relu, want_s3=want_s3,
+                                want_nchw=want_nchw)
+
+    def _cg3_ffma(self, block, x, stride=1, res_nchw=None, relu=False, want_s3=False, want_nchw=True):
+        """FFMA conv / transposed conv on NCDHW fp32 + GroupNorm; result as (C8S3 or None, NCDHW or None)."""
+        conv, gn = block[0], block[1]
+        y, sums = ops.conv3d_k3(x, self._pack(conv), stride, isinstance(conv, nn.ConvTranspose3d), want_stats=True)
+        if not want_s3:
+            return None, ops.gn_apply(y, sums, gn.weight, gn.bias, res_nchw, relu, out=y)
+        return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, False, res_nchw=res_nchw, relu=relu, want_s3=True,
+                                want_nchw=want_nchw)
+
+    def _hourglass_tc3(self, hg, x, presqu, postsqu, resid, out_s3, out_nchw):
+        t, _ = self._cg3_ffma(hg.conv1[0], x, 2, relu=True, want_s3=True, want_nchw=False)
+        _, pre = self._cg3_tc(hg.conv2, t, res_nchw=postsqu, relu=True, want_s3=False, want_nchw=True)
+        t, _ = self._cg3_ffma(hg.conv3[0], pre, 2, relu=True, want_s3=True, want_nchw=False)
+        _, t = self._cg3_tc(hg.conv4[0], t, relu=True, want_s3=False, want_nchw=True)
+        _, post = self._cg3_ffma(hg.conv5, t, res_nchw=presqu if presqu is not None else pre, relu=True)
+        o_s3, o = self._cg3_ffma(hg.conv6, post, res_nchw=resid, relu=False, want_s3=out_s3, want_nchw=out_nchw)
+        return o_s3, o, pre, post
+
+    def _classify_tc3(self, head, x_s3):
+        _, t = self._cg3_tc(head[0], x_s3, relu=True, want_s3=False, want_nchw=True)
+        y, _ = ops.conv3d_k3(t, self._pack(head[2]), 1)
+        return y.squeeze(1)
+
+    def _aggregate_tc3(self, lfeat, rfeat, D):
+        cost = ops.cost_volume_concat_c8s3(lfeat, rfeat, D)
+        t, _ = self._cg3_tc(self.dres0[0], cost, relu=True)
+        del cost
+        c0_s3, c0 = self._cg3_tc(self.dres0[2], t, relu=True, want_nchw=True)
+        t, _ = self._cg3_tc(self.dres1[0], c0_s3, relu=True)
+        del c0_s3
+        _, cost0 = self._cg3_tc(self.dres1[2], t, res_nchw=c0, want_s3=False, want_nchw=True)
+        del t, c0
+        single = not hasattr(self, "dres3")  # single-hourglass variants (cm_sub_*)
+        o1_s3, out1, pre1, post1 = self._hourglass_tc3(self.dres2, cost0, None, None, cost0, True, not single)
+        c1 = self._classify_tc3(self.classif1, o1_s3)
+        del o1_s3
+        if single:
+            return (c1,)
+        o2_s3, out2, _pre2, post2 = self._hourglass_tc3(self.dres3, out1, pre1, post1, cost0, True, True)
+        c2 = self._classify_tc3(self.classif2, o2_s3)
+        del o2_s3, out1
+        o3_s3, _o3, _pre3, _post3 = self._hourglass_tc3(self.dres4, out2, pre1, post2, cost0, True, False)
+        return c1, c2, self._classify_tc3(self.classif3, o3_s3)
 
     def _aggregate_fp32(self, lfeat, rfeat, D):
         """Inference-only fp32 aggregation: cost volume -> dres0/1 -> three hourglasses -> raw classifier volumes."""
@@ -564,6 +665,8 @@ class cmfsm(nn.Module):
         both = torch.cat([left, right], 0)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.feature_extraction.parameters()):
             feat, full = self._features_train(both.contiguous())
+        elif self.conv_engine == "tc3":
+            feat, full = self._features_tc3(both.contiguous())
         else:
             feat, full = self._features(both.contiguous())
         lfeat, rfeat = feat[:B], feat[B:]
@@ -585,6 +688,9 @@ class cmfsm(nn.Module):
                 return ops.softargmin_ctxmap(c1, c2, c3, weights9, scale)
             if self.aggregation != "fp32":
                 raise ValueError("aggregation must be 'fp32' or 'bf16', got %r" % (self.aggregation,))
+            if self.conv_engine == "tc3":
+                c1, c2, c3 = self._aggregate_tc3(lfeat, rfeat, D)
+                return ops.softargmin_ctxmap(c1, c2, c3, weights9, scale)
             cost = ops.cost_volume_concat(lfeat, rfeat, D)
 
         cost0 = self._cg(self.dres0[0], cost, relu=True)

@@ -9,7 +9,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcmfb200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _c = ctypes
 _P = _c.c_void_p
@@ -29,14 +29,12 @@ SIGNATURES = {
     "cmfb200_deconv3d_k3s2_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_pack_igemm_weight_bf16": [_P, _P, _I, _I, _I, _P],
     "cmfb200_conv3d_igemm_bf16_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "cmfb200_conv3d_c8_cout1_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_conv3d_igemm_cout1_bf16_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "cmfb200_conv3d_igemm_cout1_gather_bf16_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_deconv3d_igemm_bf16_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_conv3d_s2_igemm_bf16_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_c8_parity_split": [_P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_cost_volume_concat_c8_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "cmfb200_gn_apply_c8_bf16": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "cmfb200_gn_apply_c8_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "cmfb200_c8_bf16_to_f32": [_P, _P, _I, _I, _LL, _P],
     "cmfb200_f32_to_c8_bf16": [_P, _P, _I, _I, _LL, _P],
     "cmfb200_pack_conv2d_weight": [_P, _P, _I, _I, _I, _P],
@@ -60,6 +58,10 @@ SIGNATURES = {
     "cmfb200_volume_mapping_fwd": [_P] * 8 + [_I] * 5 + [_P],
     "cmfb200_ctxmap_weights_bwd": [_P] * 11 + [_I, _I, _I, _I, _P],
     "cmfb200_softargmin_ctxmap_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "cmfb200_cost_volume_concat_c8s3": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "cmfb200_pack_tc3_weight": [_P, _P, _I, _I, _I, _I, _P],
+    "cmfb200_conv_tc3_fwd": [_P, _P, _P, _P] + [_I] * 10 + [_P],
+    "cmfb200_gn_apply_tc3": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _F, _I, _P],
 }
 _RESTYPES = {"cmfb200_last_error": _c.c_char_p, "cmfb200_launch_count": _c.c_ulonglong}
 

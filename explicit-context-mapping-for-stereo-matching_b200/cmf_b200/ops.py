@@ -479,21 +479,6 @@ def conv3d_igemm(x, packed, want_stats=True):
     return y, sums
 
 
-def conv3d_c8_cout1(x, weight):
-    """classifN.2: C8/bf16 [B,Cin/8,D,H,W,8] x nn.Conv3d weight [1,Cin,3,3,3] (fp32) -> fp32 [B,D,H,W]."""
-    weight = weight.detach()
-    _req(x, dtype=BF16)
-    _req(weight)
-    B, NC, D, H, W, _ = x.shape
-    if tuple(weight.shape) != (1, NC * 8, 3, 3, 3):
-        raise ValueError("expected a [1,%d,3,3,3] weight, got %s" % (NC * 8, tuple(weight.shape)))
-    y = torch.empty((B, D, H, W), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device), _timed("conv3d_c8_cout1_fwd"):
-        _lib.check(_lib.load().cmfb200_conv3d_c8_cout1_fwd(_p(x), _p(weight), _p(y), B, NC * 8, D, H, W, _stream()),
-                   "conv3d_c8_cout1_fwd")
-    return y
-
-
 def conv3d_igemm_cout1(x, packed32):
     """classifN.2 on tensor cores: C8/bf16 [B,4,D,H,W,8] x pack_igemm_weight(weight zero-padded to 32 couts)
     -> fp32 [B,D,H,W]."""
@@ -506,31 +491,6 @@ def conv3d_igemm_cout1(x, packed32):
     with torch.cuda.device(x.device), _timed("conv3d_igemm_cout1_bf16_fwd"):
         _lib.check(_lib.load().cmfb200_conv3d_igemm_cout1_bf16_fwd(_p(x), _p(packed32), _p(y), B, NC * 8, D, H, W, _stream()),
                    "conv3d_igemm_cout1_bf16_fwd")
-    return y
-
-
-def pack_cout1_taps(weight):
-    """nn.Conv3d weight [1,32,3,3,3] (fp32) -> bf16 [4,32,8]: row n < 27 of the 32 = tap n, K-major in 8-channel chunks
-    (the B operand of `conv3d_igemm_cout1_gather`)."""
-    w = weight.detach()
-    _req(w)
-    if tuple(w.shape) != (1, 32, 3, 3, 3):
-        raise ValueError("expected a [1,32,3,3,3] weight, got %s" % (tuple(w.shape),))
-    taps = torch.zeros((32, 32), device=w.device, dtype=torch.float32)
-    taps[:27] = w[0].reshape(32, 27).t()
-    return taps.view(32, 4, 8).permute(1, 0, 2).contiguous().to(BF16)
-
-
-def conv3d_igemm_cout1_gather(x, taps):
-    """classifN.2 as one N=27 GEMM per plane + a 27-point gather: C8/bf16 [B,4,D,H,W,8] x pack_cout1_taps -> fp32 [B,D,H,W]."""
-    _req(x, taps, dtype=BF16)
-    B, NC, D, H, W, _ = x.shape
-    if NC != 4 or tuple(taps.shape) != (4, 32, 8):
-        raise ValueError("expected a 32-channel C8 input and [4,32,8] tap weights")
-    y = torch.empty((B, D, H, W), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device), _timed("conv3d_igemm_cout1_bf16_fwd"):
-        _lib.check(_lib.load().cmfb200_conv3d_igemm_cout1_gather_bf16_fwd(_p(x), _p(taps), _p(y), B, 32, D, H, W, _stream()),
-                   "conv3d_igemm_cout1_gather_bf16_fwd")
     return y
 
 
@@ -570,21 +530,123 @@ def conv3d_s2_igemm(x_split, packed, want_stats=True):
     return y, sums
 
 
-def gn_apply_c8(x, sums, gamma, beta, residual=None, relu=False, out=None, want_split=False, groups=GN_GROUPS,
-                eps=GN_EPS):
+def gn_apply_c8(x, sums, gamma, beta, residual=None, relu=False, out=None, want_split=False, f32_out=False,
+                groups=GN_GROUPS, eps=GN_EPS):
     """GroupNorm(+residual)(+ReLU) on C8/bf16.  With `want_split` also returns the parity-split copy that the
-    stride-2 implicit GEMM consumes: (y, y_split)."""
+    stride-2 implicit GEMM consumes: (y, y_split).  With `f32_out` the result is returned ONLY as un-rounded fp32
+    [B,C,D,H,W] (the input of the fp32 classifier tail)."""
     gamma, beta = gamma.detach(), beta.detach()
     _req(gamma, beta)
     _req(x, residual, dtype=BF16)
     B, NC, D, H, W, _ = x.shape
-    y = torch.empty_like(x) if out is None else out
+    y32 = torch.empty((B, NC * 8, D, H, W), device=x.device, dtype=torch.float32) if f32_out else None
+    y = None if f32_out else (torch.empty_like(x) if out is None else out)
     split = torch.empty((B, 8, NC, D // 2, H // 2, W // 2, 8), device=x.device, dtype=BF16) if want_split else None
     with torch.cuda.device(x.device), _timed("gn_apply_c8_bf16"):
         _lib.check(_lib.load().cmfb200_gn_apply_c8_bf16(_p(x), _p(sums), _p(gamma), _p(beta), _p(residual), _p(y),
-                                                        _p(split), B, NC * 8, groups, D, H, W, eps, int(relu),
+                                                        _p(split), _p(y32), B, NC * 8, groups, D, H, W, eps, int(relu),
                                                         _stream()), "gn_apply_c8_bf16")
+    if f32_out:
+        return y32
     return (y, split) if want_split else y
+
+
+# ------------------------------------------------------------------------------------------ tc3 (fp32-accurate tcgen05)
+# C8S3: bf16 [B, C/8, 3, (D,) H, W, 8] -- three bf16 terms whose sum is the fp32 value; C8F: fp32 [B, C/8, (D,) H, W, 8].
+def pack_tc3_weight(weight):
+    """nn.Conv2d [Cout,Cin,k,k] / nn.Conv3d [Cout,Cin,3,3,3] weight (fp32) -> split-bf16 packing of conv_tc3."""
+    weight = weight.detach()
+    _req(weight)
+    Cout, Cin = weight.shape[:2]
+    KD = 3 if weight.dim() == 5 else 1
+    k = weight.shape[-1]
+    packed = torch.empty((KD * (Cin // 16), k, k, 2, 3, Cout, 8), device=weight.device, dtype=BF16)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.load().cmfb200_pack_tc3_weight(_p(weight), _p(packed), Cout, Cin, KD, k, _stream()),
+                   "pack_tc3_weight")
+    return packed
+
+
+def conv_tc3(x_s3, packed, dilation=1, want_stats=True, out_nchw=False):
+    """Stride-1 'same' conv (2-D or 3-D by the rank of x_s3) on the split-bf16 tensor-core path.
+    Returns (raw fp32 y in C8F -- or NCHW/NCDHW when out_nchw --, gn_sums or None)."""
+    _req(x_s3, packed, dtype=BF16)
+    three_d = x_s3.dim() == 7
+    B, NC = x_s3.shape[:2]
+    sp = tuple(x_s3.shape[3:-1])
+    D, H, W = sp if three_d else (1,) + sp
+    KS, k, _, _, _, Cout, _ = packed.shape
+    Cin = NC * 8
+    KD = KS // (Cin // 16)
+    if x_s3.shape[2] != 3 or KS != KD * (Cin // 16) or KD != (3 if three_d else 1):
+        raise ValueError("conv_tc3: input %s does not match packed weight %s" % (tuple(x_s3.shape), tuple(packed.shape)))
+    y = torch.empty(((B, Cout) + sp) if out_nchw else ((B, Cout // 8) + sp + (8,)), device=x_s3.device, dtype=torch.float32)
+    sums = _new_sums(B, Cout, x_s3.device) if want_stats else None
+    with torch.cuda.device(x_s3.device), _timed("conv_tc3_fwd"):
+        _lib.check(_lib.load().cmfb200_conv_tc3_fwd(_p(x_s3), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W, KD, k,
+                                                    dilation, int(out_nchw), _stream()), "conv_tc3_fwd")
+    return y, sums
+
+
+def gn_apply_tc3(raw, sums, gamma, beta, raw_c8f, res_s3=None, res_nchw=None, relu=False, want_s3=True, want_nchw=False,
+                 groups=GN_GROUPS, eps=GN_EPS):
+    """GroupNorm (+residual) (+ReLU) of the tc3 pipeline.  raw: C8F (raw_c8f) or NCHW/NCDHW fp32; the result is returned
+    as (C8S3 or None, NCHW fp32 or None).  sums=None: layout conversion / three-term split only."""
+    _req(raw, res_nchw)
+    _req(res_s3, dtype=BF16)
+    if sums is not None:
+        gamma, beta = gamma.detach(), beta.detach()
+        _req(gamma, beta)
+    if raw_c8f:
+        B, NC = raw.shape[:2]
+        C, sp = NC * 8, tuple(raw.shape[2:-1])
+    else:
+        B, C = raw.shape[:2]
+        sp = tuple(raw.shape[2:])
+    spatial = 1
+    for v in sp:
+        spatial *= v
+    y_s3 = torch.empty((B, C // 8, 3) + sp + (8,), device=raw.device, dtype=BF16) if want_s3 else None
+    y_nchw = torch.empty((B, C) + sp, device=raw.device, dtype=torch.float32) if want_nchw else None
+    with torch.cuda.device(raw.device), _timed("gn_apply_tc3"):
+        _lib.check(_lib.load().cmfb200_gn_apply_tc3(_p(raw), int(raw_c8f), _p(sums), _p(gamma) if sums is not None else None,
+                                                    _p(beta) if sums is not None else None, _p(res_s3), _p(res_nchw),
+                                                    _p(y_s3), _p(y_nchw), B, C, groups, spatial, eps, int(relu), _stream()),
+                   "gn_apply_tc3")
+    return y_s3, y_nchw
+
+
+def cost_volume_concat_c8s3(L, R, D):
+    """K1 in C8S3: [B,C,h,w] fp32 x2 -> [B, 2C/8, 3, D, h, w, 8] bf16 (terms sum to the fp32 volume exactly)."""
+    _req(L, R)
+    B, C, h, w = L.shape
+    cost = torch.empty((B, 2 * C // 8, 3, D, h, w, 8), device=L.device, dtype=BF16)
+    with torch.cuda.device(L.device), _timed("cost_volume_concat_c8s3"):
+        _lib.check(_lib.load().cmfb200_cost_volume_concat_c8s3(_p(L), _p(R), _p(cost), B, C, h, w, D, _stream()),
+                   "cost_volume_concat_c8s3")
+    return cost
+
+
+def f32_to_c8s3(x):
+    """[B,C,...] fp32 -> C8S3 (exact three-term bf16 split)."""
+    return gn_apply_tc3(x, None, None, None, raw_c8f=False)[0]
+
+
+def c8s3_to_f32(x_s3):
+    """C8S3 -> [B,C,...] fp32 (sum of the three terms; exact)."""
+    t = x_s3.float().sum(2)  # [B, C/8, ..., 8]
+    nd = t.dim()
+    perm = (0, 1, nd - 1) + tuple(range(2, nd - 1))
+    t = t.permute(*perm).contiguous()
+    return t.view((t.shape[0], t.shape[1] * 8) + tuple(t.shape[3:]))
+
+
+def c8f_to_f32(y):
+    """C8F fp32 [B,C/8,...,8] -> [B,C,...] fp32 (tests / tools)."""
+    nd = y.dim()
+    perm = (0, 1, nd - 1) + tuple(range(2, nd - 1))
+    t = y.permute(*perm).contiguous()
+    return t.view((t.shape[0], t.shape[1] * 8) + tuple(t.shape[3:]))
 
 
 def softargmin_ctxmap_bwd(c1, c2, c3, weights9, g1, g2, g3, scale):

@@ -79,8 +79,9 @@ __global__ void __launch_bounds__(256) gn_apply_c8_bf16_kernel(const __nv_bfloat
                                                                const float* __restrict__ beta,
                                                                const __nv_bfloat16* __restrict__ residual,
                                                                __nv_bfloat16* __restrict__ y,
-                                                               __nv_bfloat16* __restrict__ y_split, int C, int G,
-                                                               int D, int H, int W, float eps, int relu) {
+                                                               __nv_bfloat16* __restrict__ y_split,
+                                                               float* __restrict__ y_f32, int C, int G, int D, int H,
+                                                               int W, float eps, int relu) {
     const long long spatial = (long long)D * H * W;
     __shared__ float sscale[8], sshift[8];
     const int nc = C / 8;
@@ -131,68 +132,18 @@ __global__ void __launch_bounds__(256) gn_apply_c8_bf16_kernel(const __nv_bfloat
                 f1 = fmaxf(f1, 0.f);
             }
             out[e] = __floats2bfloat162_rn(f0, f1);
+            if (y_f32 != nullptr) {  // un-rounded fp32 [B][C][D][H][W] copy (input of the fp32 classifier tail)
+                y_f32[((size_t)b * C + chunk * 8 + 2 * e) * spatial + i] = f0;
+                y_f32[((size_t)b * C + chunk * 8 + 2 * e + 1) * spatial + i] = f1;
+            }
         }
-        *reinterpret_cast<uint4*>(y + (base + i) * 8) = *reinterpret_cast<const uint4*>(out);
+        if (y != nullptr) *reinterpret_cast<uint4*>(y + (base + i) * 8) = *reinterpret_cast<const uint4*>(out);
         if (y_split != nullptr) {  // parity-split copy for a stride-2 consumer: [B][8][C/8][D/2][H/2][W/2][8]
             const int w = (int)(i % W), h = (int)((i / W) % H), d = (int)(i / ((long long)W * H));
             const int par = ((d & 1) << 2) | ((h & 1) << 1) | (w & 1);
             const size_t dst = (((((size_t)b * 8 + par) * nc + chunk) * (D >> 1) + (d >> 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
             *reinterpret_cast<uint4*>(y_split + dst * 8) = *reinterpret_cast<const uint4*>(out);
         }
-    }
-}
-
-// classifier tail conv (Cin -> 1, 3x3x3, pad 1) straight from C8/bf16 to the fp32 volume K4 consumes
-// (classifN.2, cmf/models/cmfsm.py:624,629,634).  N=1 has no tensor-core shape; the op is bound by reading the
-// input once (106 MB at config 2): one thread per output voxel, 128-bit loads that hit L1 for the 27-fold reuse,
-// fp32 accumulation; weights [Cin][27] fp32 staged in shared memory as [Cin/8][27][8].
-__global__ void __launch_bounds__(256) conv3d_c8_cout1_kernel(const __nv_bfloat16* __restrict__ x,
-                                                              const float* __restrict__ wgt, float* __restrict__ y,
-                                                              int NC, int D, int H, int W) {
-    extern __shared__ __align__(16) float sw[];  // [NC][27][8]
-    for (int i = threadIdx.x; i < NC * 27 * 8; i += 256) {
-        const int j = i & 7, tap = (i >> 3) % 27, chunk = i / (27 * 8);
-        sw[i] = wgt[(chunk * 8 + j) * 27 + tap];
-    }
-    __syncthreads();
-    const size_t plane = (size_t)H * W, vol = (size_t)D * plane;
-    const int b = blockIdx.y;
-    const uint4* xb = reinterpret_cast<const uint4*>(x) + (size_t)b * NC * vol;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < vol; i += (size_t)gridDim.x * 256) {
-        const int w = (int)(i % W), h = (int)((i / W) % H), d = (int)(i / plane);
-        float acc = 0.f;
-        for (int chunk = 0; chunk < NC; ++chunk) {
-            const uint4* xc = xb + (size_t)chunk * vol;
-            const float* wc = sw + chunk * 27 * 8;
-#pragma unroll
-            for (int kd = 0; kd < 3; ++kd) {
-                const int dd = d + kd - 1;
-                if ((unsigned)dd >= (unsigned)D) continue;
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                    const int hh = h + kh - 1;
-                    if ((unsigned)hh >= (unsigned)H) continue;
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        const int ww = w + kw - 1;
-                        if ((unsigned)ww >= (unsigned)W) continue;
-                        const uint4 raw = __ldg(xc + (size_t)dd * plane + (size_t)hh * W + ww);
-                        const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
-                        const float4 w0 = *reinterpret_cast<const float4*>(wc + ((kd * 3 + kh) * 3 + kw) * 8);
-                        const float4 w1 = *reinterpret_cast<const float4*>(wc + ((kd * 3 + kh) * 3 + kw) * 8 + 4);
-                        acc = fmaf(__low2float(v[0]), w0.x, acc);
-                        acc = fmaf(__high2float(v[0]), w0.y, acc);
-                        acc = fmaf(__low2float(v[1]), w0.z, acc);
-                        acc = fmaf(__high2float(v[1]), w0.w, acc);
-                        acc = fmaf(__low2float(v[2]), w1.x, acc);
-                        acc = fmaf(__high2float(v[2]), w1.y, acc);
-                        acc = fmaf(__low2float(v[3]), w1.z, acc);
-                        acc = fmaf(__high2float(v[3]), w1.w, acc);
-                    }
-                }
-            }
-        }
-        y[(size_t)b * vol + i] = acc;
     }
 }
 
@@ -268,9 +219,9 @@ extern "C" int cmfb200_cost_volume_concat_c8_bf16(const float* L, const float* R
 }
 
 extern "C" int cmfb200_gn_apply_c8_bf16(const void* x_c8, const double* gn_sums, const float* gamma, const float* beta,
-                                        const void* residual_c8, void* y_c8, void* y_split_c8, int B, int C, int G,
-                                        int D, int H, int W, float eps, int relu, void* stream) {
-    CMF_REQUIRE(x_c8 && gn_sums && gamma && beta && y_c8, "gn_apply_c8_bf16: null pointer");
+                                        const void* residual_c8, void* y_c8, void* y_split_c8, float* y_f32, int B, int C,
+                                        int G, int D, int H, int W, float eps, int relu, void* stream) {
+    CMF_REQUIRE(x_c8 && gn_sums && gamma && beta && (y_c8 || y_f32), "gn_apply_c8_bf16: null pointer");
     CMF_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && G > 0 && C % G == 0 && D > 0 && H > 0 && W > 0, "gn_apply_c8_bf16: bad shape");
     CMF_REQUIRE(y_split_c8 == nullptr || ((D % 2 == 0) && (H % 2 == 0) && (W % 2 == 0)),
                 "gn_apply_c8_bf16: the parity-split copy needs even D,H,W (got %d,%d,%d)", D, H, W);
@@ -280,7 +231,7 @@ extern "C" int cmfb200_gn_apply_c8_bf16(const void* x_c8, const double* gn_sums,
     gn_apply_c8_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x_c8), gn_sums, gamma, beta,
         reinterpret_cast<const __nv_bfloat16*>(residual_c8), reinterpret_cast<__nv_bfloat16*>(y_c8),
-        reinterpret_cast<__nv_bfloat16*>(y_split_c8), C, G, D, H, W, eps, relu);
+        reinterpret_cast<__nv_bfloat16*>(y_split_c8), y_f32, C, G, D, H, W, eps, relu);
     CMF_LAUNCH_CHECK("gn_apply_c8_bf16_kernel");
     return CMFB200_OK;
 }
@@ -304,15 +255,3 @@ extern "C" int cmfb200_f32_to_c8_bf16(const float* x, void* y_c8, int B, int C, 
     return CMFB200_OK;
 }
 
-extern "C" int cmfb200_conv3d_c8_cout1_fwd(const void* x_c8, const float* weight, float* y, int B, int Cin, int D, int H,
-                                           int W, void* stream) {
-    CMF_REQUIRE(x_c8 && weight && y, "conv3d_c8_cout1_fwd: null pointer");
-    CMF_REQUIRE(B > 0 && Cin > 0 && Cin % 8 == 0 && D > 0 && H > 0 && W > 0 && B <= 65535, "conv3d_c8_cout1_fwd: bad shape");
-    const long long vol = (long long)D * H * W;
-    const size_t smem = (size_t)Cin * 27 * sizeof(float);
-    dim3 grid((unsigned)min((long long)kNumSMs * 16, cdiv(vol, 256)), (unsigned)B);
-    conv3d_c8_cout1_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_c8), weight,
-                                                                       y, Cin / 8, D, H, W);
-    CMF_LAUNCH_CHECK("conv3d_c8_cout1_kernel");
-    return CMFB200_OK;
-}

@@ -27,7 +27,7 @@ extern "C" {
 #define CMFB200_ERR_INVALID (-1) /* bad shape / null pointer / unsupported configuration */
 #define CMFB200_ERR_CUDA (-2)    /* a CUDA runtime call failed (message has the cudaError string) */
 
-#define CMFB200_ABI_VERSION 2
+#define CMFB200_ABI_VERSION 3
 
 /* ABI version of the loaded library (== CMFB200_ABI_VERSION of the header it was built from). */
 int cmfb200_abi_version(void);
@@ -95,20 +95,12 @@ int cmfb200_pack_igemm_weight_bf16(const float* weight, void* packed, int Cout, 
  * double buffer receiving sum / sum of squares of the stored (rounded) values, or NULL. */
 int cmfb200_conv3d_igemm_bf16_fwd(const void* x_c8, const void* packed_w, void* y_c8, double* gn_sums,
                                   int B, int Cin, int Cout, int D, int H, int W, void* stream);
-/* Classifier tail conv Cin -> 1 (k3 p1) from C8/bf16 to fp32 [B,D,H,W]; weight = nn.Conv3d weight [1,Cin,3,3,3]
- * fp32 (unpacked).  CUDA cores (N=1 has no tensor-core shape), fp32 accumulation. */
-int cmfb200_conv3d_c8_cout1_fwd(const void* x_c8, const float* weight, float* y, int B, int Cin, int D, int H,
-                                int W, void* stream);
-/* The same layer on tensor cores (depth-stacked tcgen05 schedule of the 32->32 layers): packed_w32 is
+/* classifN.2 (32->1) on tensor cores (depth-stacked tcgen05 schedule of the 32->32 layers; kept as the fp32-output probe
+ * of the tensor-core accumulator, tools/probe_tc_rounding.py -- the model runs this layer in fp32): packed_w32 is
  * cmfb200_pack_igemm_weight_bf16 of the [1,Cin,3,3,3] weight zero-padded to 32 output channels (so the weight is
  * rounded to bf16 like every other layer of the bf16 aggregation); y fp32 [B][D][H][W].  Cin = 32. */
 int cmfb200_conv3d_igemm_cout1_bf16_fwd(const void* x_c8, const void* packed_w32, float* y, int B, int Cin, int D,
                                         int H, int W, void* stream);
-/* The same layer as ONE N=27 GEMM per input plane (P[pos,tap] on the unshifted tile) + a 27-point gather in shared
- * memory: tap_weights = bf16 [Cin/8][32][8] with row n < 27 = tap n = (kd*3+kh)*3+kw of the [1,Cin,3,3,3] weight, rows
- * 27..31 zero.  y fp32 [B][D][H][W].  Cin = 32.  Bound by reading the input once. */
-int cmfb200_conv3d_igemm_cout1_gather_bf16_fwd(const void* x_c8, const void* tap_weights, float* y, int B, int Cin,
-                                               int D, int H, int W, void* stream);
 /* Transposed conv k3 s2 p1 op1 on tensor cores: x_c8 [B][Cin/8][D][H][W][8] -> y_c8 [B][Cout/8][2D][2H][2W][8];
  * packed_w from cmfb200_pack_igemm_weight_bf16(transposed=1).  (Cin,Cout) in {(64,64),(64,32)}. */
 int cmfb200_deconv3d_igemm_bf16_fwd(const void* x_c8, const void* packed_w, void* y_c8, double* gn_sums,
@@ -124,9 +116,11 @@ int cmfb200_c8_parity_split(const void* x_c8, void* y_split_c8, int B, int C, in
 int cmfb200_cost_volume_concat_c8_bf16(const float* L, const float* R, void* cost_c8,
                                        int B, int C, int h, int w, int D, void* stream);
 /* K3 on C8/bf16: y = GroupNorm(x) (+residual) (ReLU), fp32 math, bf16 in/out; y may alias x.  If y_split_c8 != NULL
- * the result is ALSO written in the parity-split layout a stride-2 consumer reads (D,H,W even). */
+ * the result is ALSO written in the parity-split layout a stride-2 consumer reads (D,H,W even).  If y_f32 != NULL the
+ * UN-ROUNDED fp32 result is also written as [B][C][D][H][W] (input of the fp32 classifier tail classifN.2, whose
+ * logits are the rounding-sensitive spot of the bf16 mode); y_c8 may then be NULL. */
 int cmfb200_gn_apply_c8_bf16(const void* x_c8, const double* gn_sums, const float* gamma, const float* beta,
-                             const void* residual_c8, void* y_c8, void* y_split_c8, int B, int C, int G,
+                             const void* residual_c8, void* y_c8, void* y_split_c8, float* y_f32, int B, int C, int G,
                              int D, int H, int W, float eps, int relu, void* stream);
 /* layout/dtype converters between C8/bf16 and dense fp32 [B,C,spatial] (NCDHW). */
 int cmfb200_c8_bf16_to_f32(const void* x_c8, float* y, int B, int C, long long spatial, void* stream);
@@ -246,6 +240,32 @@ int cmfb200_softargmin_ctxmap_bwd(const float* c1, const float* c2, const float*
 int cmfb200_softargmin_ctxmap5_fwd(const float* c1, const float* c2, const float* c3, const float* weights5,
                                    float* out1, float* out2, float* out3, float* pred_lr, int B, int D, int h, int w,
                                    int scale, void* stream);
+
+/* ---- fp32-accurate tensor-core convolution ("tc3": three-term bf16 split on tcgen05) ------------------------------
+ * Replaces the stride-1 nn.Conv2d layers of feature_extraction (cmf/models/cmfsm.py:126-236: convbn / BasicBlock /
+ * firstconv / lastconv) and the stride-1 nn.Conv3d layers of the aggregation network (cmfsm.py:49-58, 240-303,
+ * 604-634) in the fp32 parity mode: every fp32 operand is the exact sum of three bf16 terms, six bf16 MMAs per
+ * product accumulate in fp32 (csrc/conv_tc3.cu).  2-D images are volumes with D = 1.
+ *   activations "C8S3": bf16 [B][C/8][3][D][H][W][8];  raw conv output "C8F": fp32 [B][C/8][D][H][W][8]. */
+/* weight: nn.Conv2d [Cout][Cin][k][k] (KD = 1) or nn.Conv3d [Cout][Cin][3][3][3] (KD = 3), fp32 ->
+ * packed bf16 [KD*Cin/16][k][k][2][3][Cout][8].  Cin % 16 == 0, Cout % 8 == 0, k in {1,3}. */
+int cmfb200_pack_tc3_weight(const float* weight, void* packed, int Cout, int Cin, int KD, int KHW, void* stream);
+/* Stride-1 "same" convolution (padding = dilation*(k/2), depth padding 1 when KD = 3).  y: C8F, or plain
+ * [B][Cout][D][H][W] fp32 when out_nchw != 0; gn_sums (optional): [B][Cout][2] doubles (sum, sum of squares of y),
+ * must be zero on entry.  Supported: 3x3 d1 Cout 32/64/128, 3x3 d2 Cout 128, 1x1 Cout 32/128. */
+int cmfb200_conv_tc3_fwd(const void* x_c8s3, const void* packed_w, float* y, double* gn_sums, int B, int Cin, int Cout,
+                         int D, int H, int W, int KD, int KHW, int dilation, int out_nchw, void* stream);
+/* y = GroupNorm(raw) (+residual) (ReLU) (nn.GroupNorm + the adds / ReLUs of convbn, BasicBlock, hourglass):
+ * raw is C8F (raw_is_c8f) or [B][C][spatial] fp32; residual as C8S3 and/or [B][C][spatial] fp32 (either may be NULL);
+ * the result is written split into three bf16 terms (y_c8s3) and/or as [B][C][spatial] fp32 (y_nchw).
+ * gn_sums == NULL: no normalisation (layout conversion / split only). */
+int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma, const float* beta,
+                         const void* residual_c8s3, const float* residual_nchw, void* y_c8s3, float* y_nchw, int B,
+                         int C, int groups, long long spatial, float eps, int relu, void* stream);
+/* K1 written directly as C8S3 (cmfsm.py:667-682): cost [B][2C/8][3][D][h][w][8] bf16; the three terms of an element
+ * sum to the fp32 feature value exactly (or to +0.0 in the masked triangle). */
+int cmfb200_cost_volume_concat_c8s3(const float* L, const float* R, void* cost_c8s3, int B, int C, int h, int w, int D,
+                                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -58,8 +58,9 @@ def test_forward_batch2_matches_per_sample(model):
         assert a.shape == (2, 1, 256, 512)
         # different grid partition -> different order of the GroupNorm double atomics; the reference's own B=2 vs B=1
         # runs differ by 8e-4 px and its 8-thread vs 1-thread runs by 2.1e-3 px
+        # (measured on the B200, round 2: 0.0)
         print("batched vs per-sample: max|d| %.3e px" % float((a[1:2] - b).abs().max()))
-        torch.testing.assert_close(a[1:2], b, rtol=0, atol=2e-3)
+        torch.testing.assert_close(a[1:2], b, rtol=0, atol=1e-4)
 
 
 def test_forward_vs_cpu_oracle_structured_pair(model):
@@ -101,12 +102,12 @@ def test_cuda_graph_replay_matches_eager(model):
             model.enable_cuda_graph(False)
     for a, b, c in zip(eager, first, again):
         # Replay and eager run the same kernels on the same data; the only freedom is the order of the double
-        # atomics of the GroupNorm statistics (last-bit changes of mean/var), which this network amplifies.  The
-        # measured difference is printed; the gate is 1/10 of the fp32-vs-fp64 distance of the reference itself.
+        # atomics of the GroupNorm statistics (a last-bit change of a sum of ~1e5 doubles).  Measured on the B200:
+        # 0.0 in every run (round 2); the gate leaves room for one such last-bit event, nothing more.
         print("graph replay vs eager: max|d| %.3e ; replay vs replay: %.3e" % (float((a - b).abs().max()),
                                                                              float((b - c).abs().max())))
-        torch.testing.assert_close(a, b, rtol=0, atol=1e-3)
-        torch.testing.assert_close(b, c, rtol=0, atol=1e-3)
+        torch.testing.assert_close(a, b, rtol=0, atol=1e-4)
+        torch.testing.assert_close(b, c, rtol=0, atol=1e-4)
 
 
 def test_cuda_graph_is_dropped_when_weights_change():
@@ -121,14 +122,15 @@ def test_cuda_graph_is_dropped_when_weights_change():
     net.enable_cuda_graph(True)
     with torch.no_grad():
         before = net(left, right)
-        net.dres0[0][0].weight.mul_(1.5)  # in place: same data_ptr, `_version` moves
+        w = net.dres0[0][0].weight  # in place: same data_ptr, `_version` moves
+        w.add_(0.05 * torch.randn(w.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(3)))
         net.feature_extraction.lastconv[2].weight.add_(0.01)
         after_graph = net(left, right)
         net.enable_cuda_graph(False)
         after_eager = net(left, right)
     assert float((before[2] - after_eager[2]).abs().mean()) > 1e-2  # the update matters
     for a, b in zip(after_graph, after_eager):
-        torch.testing.assert_close(a, b, rtol=0, atol=1e-3)
+        torch.testing.assert_close(a, b, rtol=0, atol=1e-4)
 
 
 def test_dataparallel_replicas_never_reuse_packed_weights():
@@ -143,13 +145,14 @@ def test_dataparallel_replicas_never_reuse_packed_weights():
     replica = torch.nn.parallel.replicate(net, [0])[0]
     with torch.no_grad():
         a = replica(left, right)
-        net.dres0[0][0].weight.mul_(1.5)
+        w = net.dres0[0][0].weight  # (a pure rescaling would be undone by the GroupNorm that follows)
+        w.add_(0.05 * torch.randn(w.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(3)))
         replica = torch.nn.parallel.replicate(net, [0])[0]
         b = replica(left, right)
         want = net(left, right)
     assert float((a[2] - b[2]).abs().mean()) > 1e-2
     for x, y in zip(b, want):
-        torch.testing.assert_close(x, y, rtol=0, atol=1e-3)
+        torch.testing.assert_close(x, y, rtol=0, atol=1e-4)
 
 
 def _epe_pairs(model, pairs, gt=20.0):

@@ -1,0 +1,130 @@
+"""GPU: the fp32-accurate tensor-core convolution (three-term bf16 split on tcgen05, csrc/conv_tc3.cu) and the
+GroupNorm apply of its pipeline, through the C ABI, against fp64 PyTorch convolutions of the SAME fp32 operands.
+
+Gate: the result must be as close to the fp64 answer as a round-to-nearest fp32 FMA chain is (the FFMA kernels and
+cuDNN strict fp32 sit at rel-L2 1e-7..3e-7 on these shapes): rel-L2 < 5e-7, 20x below the 1e-5 gate of the FFMA tests
+and 4 orders of magnitude below single-pass bf16 (2e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand(*shape, seed):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def _rel_l2(a, b):
+    return float((a.detach().cpu().double() - b.double()).norm() / b.double().norm())
+
+
+def _rel_l2_scaled(a, b):
+    """rel-L2 after removing the best common scale factor (a uniform shrink is invisible to the GroupNorm that follows
+    every one of these convolutions); returns (residual, 1 - scale)."""
+    a, b = a.detach().cpu().double(), b.double()
+    alpha = float((a * b).sum() / (b * b).sum())
+    return float((a - alpha * b).norm() / b.norm()), 1.0 - alpha
+
+
+def test_three_term_split_is_exact_and_roundtrips():
+    from cmf_b200 import ops
+
+    x = _rand(2, 16, 5, 9, seed=1) * torch.logspace(-6, 6, 9)
+    x[0, 0, 0, :4] = torch.tensor([0.0, -0.0, 1.0, -3.0])
+    s3 = ops.f32_to_c8s3(x.to(DEV))
+    assert s3.shape == (2, 2, 3, 5, 9, 8) and s3.dtype == torch.bfloat16
+    assert torch.equal(ops.c8s3_to_f32(s3).cpu(), x)  # 8 + 8 + 8 significand bits reconstruct fp32 exactly
+    x3 = _rand(1, 8, 3, 4, 6, seed=2)
+    assert torch.equal(ops.c8s3_to_f32(ops.f32_to_c8s3(x3.to(DEV))).cpu(), x3)
+
+
+CONV2D_TC3 = [  # B, Cin, Cout, H, W, k, dil
+    (1, 32, 32, 32, 32, 3, 1), (2, 32, 32, 37, 50, 3, 1), (1, 64, 64, 16, 16, 3, 1), (2, 64, 64, 36, 60, 3, 1),
+    (1, 64, 128, 19, 21, 3, 1), (1, 128, 128, 36, 60, 3, 1), (2, 128, 128, 17, 33, 3, 2), (1, 320, 128, 20, 24, 3, 1),
+    (1, 64, 128, 18, 30, 1, 1), (2, 128, 32, 21, 40, 1, 1), (1, 32, 64, 16, 8, 3, 1),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,dil", CONV2D_TC3)
+def test_conv2d_tc3_vs_fp64(B, Cin, Cout, H, W, k, dil):
+    from cmf_b200 import ops
+
+    x = _rand(B, Cin, H, W, seed=60) + 0.3
+    wgt = _rand(Cout, Cin, k, k, seed=61) * (2.0 / (k * k * Cin)) ** 0.5
+    want = F.conv2d(x.double(), wgt.double(), None, 1, (k // 2) * dil, dil)
+    xs, wp = ops.f32_to_c8s3(x.to(DEV)), ops.pack_tc3_weight(wgt.to(DEV))
+    y, sums = ops.conv_tc3(xs, wp, dil, want_stats=True)
+    got = ops.c8f_to_f32(y)
+    assert got.shape == want.shape
+    err = _rel_l2(got, want)
+    ref = _rel_l2(F.conv2d(x, wgt, None, 1, (k // 2) * dil, dil), want)  # fp32 CPU conv of the same operands
+    res, shrink = _rel_l2_scaled(got, want)
+    print("conv2d_tc3 %s rel-L2 %.2e (fp32 CPU conv: %.2e); after removing the common shrink %.2e: %.2e"
+          % ((B, Cin, Cout, H, W, k, dil), err, ref, shrink, res))
+    assert err < 2e-6
+    torch.testing.assert_close(sums.cpu()[..., 0], want.sum((2, 3)), rtol=2e-5, atol=1e-3)
+    torch.testing.assert_close(sums.cpu()[..., 1], (want * want).sum((2, 3)), rtol=2e-5, atol=1e-3)
+    y2, none = ops.conv_tc3(xs, wp, dil, want_stats=False, out_nchw=True)
+    assert none is None and torch.equal(y2, got)
+
+
+CONV3D_TC3 = [(1, 32, 32, 4, 16, 32), (1, 64, 32, 5, 18, 20), (2, 32, 32, 3, 33, 9), (1, 64, 64, 6, 16, 16),
+              (1, 32, 32, 1, 16, 8)]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,D,H,W", CONV3D_TC3)
+def test_conv3d_tc3_vs_fp64(B, Cin, Cout, D, H, W):
+    from cmf_b200 import ops
+
+    x = _rand(B, Cin, D, H, W, seed=62) + 0.3
+    wgt = _rand(Cout, Cin, 3, 3, 3, seed=63) * (2.0 / (27 * Cin)) ** 0.5
+    want = F.conv3d(x.double(), wgt.double(), None, 1, 1)
+    y, sums = ops.conv_tc3(ops.f32_to_c8s3(x.to(DEV)), ops.pack_tc3_weight(wgt.to(DEV)), 1, want_stats=True)
+    err = _rel_l2(ops.c8f_to_f32(y), want)
+    res, shrink = _rel_l2_scaled(ops.c8f_to_f32(y), want)
+    ref = _rel_l2(F.conv3d(x, wgt, None, 1, 1), want)
+    print("conv3d_tc3 %s rel-L2 %.2e (fp32 CPU conv: %.2e); after removing the common shrink %.2e: %.2e"
+          % ((B, Cin, Cout, D, H, W), err, ref, shrink, res))
+    assert err < 2e-6
+    torch.testing.assert_close(sums.cpu()[..., 0], want.sum((2, 3, 4)), rtol=2e-5, atol=1e-3)
+    torch.testing.assert_close(sums.cpu()[..., 1], (want * want).sum((2, 3, 4)), rtol=2e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("C,raw_c8f,res,relu", [(32, True, None, True), (64, True, "s3", False), (128, False, "nchw", True),
+                                                (64, False, "s3", True)])
+def test_gn_apply_tc3_vs_oracle(C, raw_c8f, res, relu):
+    from cmf_b200 import ops
+
+    x = _rand(2, C, 9, 14, seed=70) * 2 + 0.5
+    gamma, beta = _rand(C, seed=71), _rand(C, seed=72)
+    r = _rand(2, C, 9, 14, seed=73) if res else None
+    want = F.group_norm(x.double(), 32, gamma.double(), beta.double(), 1e-5)
+    if r is not None:
+        want = want + r.double()
+    if relu:
+        want = F.relu(want)
+    xd = x.to(DEV)
+    sums = torch.stack([xd.double().sum((2, 3)), (xd.double() ** 2).sum((2, 3))], -1).contiguous()
+    raw = xd.view(2, C // 8, 8, 9, 14).permute(0, 1, 3, 4, 2).contiguous() if raw_c8f else xd
+    y_s3, y_n = ops.gn_apply_tc3(raw, sums, gamma.to(DEV), beta.to(DEV), raw_c8f,
+                                 res_s3=ops.f32_to_c8s3(r.to(DEV)) if res == "s3" else None,
+                                 res_nchw=r.to(DEV) if res == "nchw" else None, relu=relu, want_s3=True, want_nchw=True)
+    assert torch.equal(ops.c8s3_to_f32(y_s3), y_n)  # both outputs carry the same fp32 values
+    assert _rel_l2(y_n, want) < 1e-6
+
+
+@pytest.mark.parametrize("B,C,h,w,D", [(1, 32, 16, 40, 12), (2, 32, 7, 20, 24), (1, 8, 5, 36, 48)])
+def test_k1_c8s3_reconstructs_the_bit_exact_volume(B, C, h, w, D):
+    """K1 written as three bf16 terms: their sum is the oracle's fp32 cost volume, bit for bit (+0.0 where masked)."""
+    import cmfsm_oracle as orc
+    from cmf_b200 import ops
+
+    L, R = _rand(B, C, h, w, seed=80), _rand(B, C, h, w, seed=81)
+    cost = ops.cost_volume_concat_c8s3(L.to(DEV), R.to(DEV), D)
+    assert cost.shape == (B, 2 * C // 8, 3, D, h, w, 8)
+    got = ops.c8s3_to_f32(cost).cpu()
+    want = orc.cost_volume_concat(L, R, D)
+    assert torch.equal(got, want)
+    assert not torch.signbit(got[want == 0]).any()

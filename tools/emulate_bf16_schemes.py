@@ -55,8 +55,8 @@ def make_patched(s):
     def classif(sd, key, x):
         x = F.relu(convgn3d(sd, key + ".0", x))
         hi = is_hi(key + ".2")
-        a = r2 if hi else s.act
-        w = r2 if hi else s.wt
+        a = (lambda t: t) if hi and os.environ.get("ONLY_C2") else r2 if hi else s.act
+        w = (lambda t: t) if hi and os.environ.get("ONLY_C2") else r2 if hi else s.wt
         return F.conv3d(a(x), w(sd[key + ".2.weight"]), None, 1, 1).squeeze(1)
 
     return convgn3d, deconvgn3d, classif
@@ -69,7 +69,9 @@ def main():
 
     torch.manual_seed(gc.WEIGHT_SEED)
     sd = {k: v.detach() for k, v in cmfsm().state_dict().items()}
-    for seed in (1, 2):
+    seeds = [int(v) for v in os.environ.get("SEEDS", "1,2").split(",")]
+    totals = {}
+    for seed in seeds:
         left, right = gc.structured_pair(H, W, delta=20, seed=seed)
         with torch.no_grad():
             L, all_l = orc.feature_extraction(sd, left)
@@ -78,7 +80,9 @@ def main():
             cost = orc.cost_volume_concat(L, R, 48)
             ref = orc.softargmin_ctxmap(*orc.aggregation3d(sd, cost), weights, 4)
             epe_ref = [float((o - 20.0).abs().mean()) for o in ref]
-            schemes = [
+            ident = lambda t: t  # noqa: E731
+            schemes = [Scheme("double + classif.2 fp32 (FFMA, GN out of classif.0 kept fp32)", True, ("classif1.2", "classif2.2", "classif3.2")),
+                       Scheme("double (raw conv out bf16, GN out bf16) = round 1", True)] if os.environ.get("ONLY_C2") else [
                 Scheme("double (raw conv out bf16, GN out bf16) = round 1", True),
                 Scheme("single (raw fp32, GN out bf16)", False),
                 Scheme("single + classif.2 hi", False, ("classif1.2", "classif2.2", "classif3.2")),
@@ -93,10 +97,13 @@ def main():
                 got = orc.softargmin_ctxmap(*orc.aggregation3d(sd, r(cost)), weights, 4)
                 orc._convgn3d, orc._deconvgn3d, orc.classif = saved
                 line = []
-                for a, b, e in zip(got, ref, epe_ref):
+                for i, (a, b, e) in enumerate(zip(got, ref, epe_ref)):
                     ea = float((a - 20.0).abs().mean())
                     line.append("mean|d| %.3f dEPE %+.4f" % (float((a - b).abs().mean()), ea - e))
+                    totals.setdefault(s.name, [0.0, 0.0, 0.0])[i] += (ea - e) / len(seeds)
                 print("seed %d %-52s %s" % (seed, s.name, " | ".join(line)), flush=True)
+    for name, t in totals.items():
+        print("DATASET dEPE over %d pairs  %-52s %+.4f %+.4f %+.4f" % (len(seeds), name, *t), flush=True)
 
 
 if __name__ == "__main__":
