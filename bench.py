@@ -5,39 +5,52 @@ HBM GB/s vs peak).
 
 A "step" is one forward of the network over one synthetic 540x960 stereo pair (BASELINE config 2: fed as
 576x960 exactly as the reference loader pads it, cmf/loader/Flying3d.py:67-72; fp32, maxdisp 192, B=1 per
-GPU).  N>1: one process per GPU (torchrun), every rank runs its own pair -- the path shards by independent
-pairs with no data-path collective ("weak" scaling); the timed region is bracketed by barrier + synchronize
-and the max over ranks is reported.  Prints ONE JSON line on rank 0.
+GPU).  N>1: one process per GPU (torchrun), every rank runs its own pair -- the headline path shards by
+independent pairs with no data-path collective ("weak" scaling); the timed region is bracketed by barrier +
+synchronize and the max over ranks is reported.  Prints ONE JSON line on rank 0.
 
-  value     whole-job pairs/s with the padded inputs already resident in HBM
-  e2e       same metric through the public API `model(left, right)` from pinned HOST tensors, including the
-            H2D copy of both images and the D2H read of the cropped disparity every step
-  roofline  K1 cost-volume kernel (the kernel BASELINE.json's metric names): algorithmic bytes / CUDA-event
-            launch duration vs the measured HBM peak of MEASURED_PEAKS.json
-  kernels   per-kernel share of the step: the same K steps are repeated kernel-by-kernel (no graph) with a CUDA
-            event pair around every launch on the launching stream; `roofline` uses those durations
-  cpu_baseline  the CPU oracle port of the reference forward timed on this box's host cores (rank 0, N=1)
+  value        whole-job pairs/s with the padded inputs already resident in HBM (fp32 parity mode: every conv
+               fp32-accurate -- the stride-1 convs as three-term bf16 splits on tcgen05, the rest FFMA)
+  e2e          same metric through the public API `model(left, right)` from pinned HOST tensors, including the
+               H2D copy of both images and the D2H read of the cropped disparity every step
+  roofline     the time-dominant kernel (conv_tc3, tensor bound): algorithmic fp32 conv FLOPs / CUDA-event time vs
+               the measured sustained bf16 peak, and the same with the bf16 MMA FLOPs actually executed (6 per product)
+  roofline_k1  the cost-volume kernel (the kernel BASELINE.json's metric names), HBM bound
+  bf16         a second timed leg in the bf16-aggregation mode (BASELINE config 4's arithmetic): value, e2e, roofline_k2
+  parity       the step's own output against the UNMODIFIED reference's output and the fp64 oracle's at this exact
+               input (committed fixtures tests/golden/cmfsm_configs.npz, made by oracle/gen_golden_configs.py)
+  kernels      per-kernel share of the step: the same K steps repeated kernel-by-kernel (no graph) with a CUDA
+               event pair around every launch on the launching stream
+  cpu_baseline the reference itself (oracle/_ref/reference, unmodified) on this box's host cores (rank 0, N=1)
+  gpu_eager_baseline  the reference itself on this GPU through PyTorch eager + cuDNN, strict fp32 and TF32 (N=1)
+  sharded      (N>1) the two sharded configs: data-parallel training step (config 3) and one 2048x3072 pair over
+               row bands (config 5)
 
-`--impl reference` times the reference's own CPU path (the oracle port: the reference is pure Python and
-cannot travel to the GPU box) on the same config/metric.
+`--impl reference` times the reference's own CPU path (the unmodified reference package staged by
+`__graft_entry__.build()` under oracle/_ref/reference; the oracle port if that tree is absent) on the same
+config / metric.
 """
 import argparse
 import json
 import os
 import statistics
+import subprocess
 import sys
 import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "explicit-context-mapping-for-stereo-matching_b200")
-for _p in (PKG, os.path.join(ROOT, "oracle")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
 
 H_IMG, W_IMG, H_PAD, MAXDISP = 540, 960, 576, 192
 METRIC = "pairs/s @540x960 D=192"
 WORKLOAD = "cmfsm inference, synthetic 540x960 pair fed as 576x960 (BASELINE config 2), maxdisp 192, B=1 per GPU"
+
+
+def _use_ours():
+    for p in (PKG,):
+        if p not in sys.path:
+            sys.path.insert(0, p)
 
 
 def synthetic_pair(seed):
@@ -56,8 +69,8 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(p["hbm_gbs"]), float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler(threading.Thread):
@@ -91,52 +104,295 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
-def time_cpu_oracle(n_timed, budget_s=None):
-    """Reference CPU path (oracle port) on the bench workload; returns (seconds per pair list, cores)."""
+# =====================================================================================================
+# reference arm: the reference's own CPU implementation
+# =====================================================================================================
+def time_cpu_reference(n_total, budget_s=None):
+    """The reference forward on the host cores.  Returns (seconds per pair list, cores, kind)."""
     import torch
 
-    import cmfsm_oracle as orc
-    from cmf.models import get_model
-
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    sd = {k: v.detach() for k, v in get_model("cmfsm").state_dict().items()}
     left, right = synthetic_pair(1)
+    import ref_harness
+
+    if ref_harness.reference_available():
+        get_model, _ = ref_harness.import_reference(force_cpu=True)
+        torch.manual_seed(0)
+        model = get_model("cmfsm").eval()
+        kind = "reference"
+
+        def forward():
+            with torch.no_grad():
+                return model(left, right)[2].reshape(1, 1, H_PAD, W_IMG)[:, :, :H_IMG]
+    else:  # no staged reference tree on this box: the oracle port of the same forward
+        _use_ours()
+        import cmfsm_oracle as orc
+        from cmf.models import get_model
+
+        torch.manual_seed(0)
+        sd = {k: v.detach() for k, v in get_model("cmfsm").state_dict().items()}
+        kind = "port"
+
+        def forward():
+            return orc.forward(sd, left, right, MAXDISP)[2][:, :, :H_IMG]
     times, t_begin = [], time.perf_counter()
-    for i in range(n_timed):
+    for _ in range(n_total):
         t0 = time.perf_counter()
-        out = orc.forward(sd, left, right, MAXDISP)[2][:, :, :H_IMG]
+        out = forward()
         times.append(time.perf_counter() - t0)
         if budget_s is not None and time.perf_counter() - t_begin > budget_s:
             break
     assert out.shape[-2:] == (H_IMG, W_IMG)
-    return times, cores
+    return times, cores, kind
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return  # rank 0 alone runs the CPU reference arm
-    times, cores = time_cpu_oracle(args.warmup + args.steps, budget_s=240.0)
+    times, cores, kind = time_cpu_reference(args.warmup + args.steps, budget_s=240.0)
     warm = min(args.warmup, max(0, len(times) - 1))
     timed = times[warm:]
     sec = sum(timed) / len(timed)
     value = 1.0 / sec
-    sample = "%d full 576x960 pairs (after %d warm-up) through the CPU oracle port of cmfsm.forward" % (len(timed), warm)
+    what = ("the UNMODIFIED reference cmfsm.forward (oracle/_ref/reference)" if kind == "reference"
+            else "the CPU oracle port of cmfsm.forward")
+    sample = "%d full 576x960 pairs (after %d warm-up) through %s" % (len(timed), warm, what)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": len(timed), "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "device": "host CPU, %d threads" % cores},
-            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample,
+                             "s_per_pair": {"min": min(timed), "median": statistics.median(timed), "max": max(timed),
+                                            "n": len(timed)}},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def _json_from_subprocess(cmd, timeout):
+    """Run a helper in its own process (it imports the REFERENCE's `cmf` package, which clashes with ours) and
+    return the last JSON line it printed."""
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": "no JSON line (rc=%d): %s" % (out.returncode, out.stderr.strip()[-300:])}
+    except Exception as e:
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
+# =====================================================================================================
+# our arm
+# =====================================================================================================
+def conv_macs(h, w, D):
+    """MACs of one forward by layer family, both images for the 2-D part."""
+    vox = D * h * w
+    s1_3d = 27 * (vox * (64 * 32 + 6 * 32 * 32) + 3 * (vox // 8) * 64 * 64 + 3 * (vox // 64) * 64 * 64)
+    s2_3d = 27 * 3 * ((vox // 8) * 32 * 64 + (vox // 64) * 64 * 64)
+    dc_3d = 27 * 3 * ((vox // 64) * 64 * 64 + (vox // 8) * 64 * 32)
+    cls = 27 * 3 * vox * 32
+    px = 2 * 16 * h * w  # both images, full resolution
+    q = 2 * h * w
+    tc_2d = 9 * (3 * px * 32 * 32 + (px // 4) * 32 * 32 * 7 + q * (64 * 64 * 31 + 64 * 128 + 128 * 128 * 11 + 320 * 128)) \
+        + q * (64 * 128 + 128 * 32)
+    ffma_2d = 9 * (px * 3 * 32 + (px // 4) * 32 * 32 + q * 32 * 64) + q * 32 * 64
+    return {"tc3_2d": tc_2d, "tc3_3d": s1_3d, "ffma_2d": ffma_2d, "s2_3d": s2_3d, "deconv_3d": dc_3d, "cout1": cls}
+
+
+def timed_leg(model, step_device, step_e2e, steps, warmup, barrier, local_rank, lib):
+    import torch
+
+    for _ in range(max(warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        out = step_device()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert res.shape[-2:] == (H_IMG, W_IMG)
+    return out, ms_total, e2e_s * 1e3, sampler.summary()
+
+
+def per_kernel_pass(model, step_device, steps, barrier, ops, lib, use_graph):
+    """The same K steps launched kernel by kernel with a CUDA event pair around every launch."""
+    import torch
+
+    model.enable_cuda_graph(False)
+    for _ in range(3):  # the eager path uses the regular allocator pool: populate it before timing
+        step_device()
+    ops.enable_event_timing(True)
+    n0 = lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        step_device()
+    ev1.record()
+    barrier()
+    launches = (lib.launch_count() - n0) // steps
+    ms_eager = ev0.elapsed_time(ev1)
+    kernels = ops.drain_event_timing()
+    ops.enable_event_timing(False)
+    model.enable_cuda_graph(use_graph)
+    return kernels, launches, ms_eager
+
+
+def parity_report(out_fp32, out_bf16):
+    """This step's output vs the reference's / the fp64 oracle's at the same input (committed fixtures)."""
+    import numpy as np
+    import torch
+
+    gpath = os.path.join(ROOT, "tests", "golden", "cmfsm_configs.npz")
+    mpath = os.path.join(ROOT, "tests", "golden", "cmfsm_configs_meta.json")
+    if not (os.path.exists(gpath) and os.path.exists(mpath)):
+        return {"unavailable": "tests/golden/cmfsm_configs.npz missing"}
+    g, meta = np.load(gpath), json.load(open(mpath))
+    sub = meta["sub"]
+    got = out_fp32[0, 0, ::sub, ::sub].cpu().double()  # rows < 540 of the padded 576: same sub-sampling grid
+    ref64 = torch.from_numpy(g["c2_pred3_fp64"])[:got.shape[0]]
+    ref32 = torch.from_numpy(g["c2_pred3_ref32"]).double()[:got.shape[0]]
+    d64, d32, r = (got - ref64).abs(), (got - ref32).abs(), (ref32 - ref64).abs()
+    rep = {"what": "pred3 of this run (rank 0, fp32 mode) vs the unmodified reference's fp32 CPU output and the fp64 "
+                   "oracle on the same weights / input, sub-sampled ::%d (tests/golden/cmfsm_configs.npz)" % sub,
+           "ours_vs_fp64_px": {"max": float(d64.max()), "mean": float(d64.mean())},
+           "reference_fp32_vs_fp64_px": {"max": float(r.max()), "mean": float(r.mean())},
+           "ours_vs_reference_fp32_px": {"max": float(d32.max()), "mean": float(d32.mean())},
+           "gate": "ours_vs_fp64 <= 2 x reference_fp32_vs_fp64 (+2e-3 max / +1e-4 mean floor); the north-star 1e-3 px "
+                   "max-abs is below the reference's own 8-thread vs 1-thread reproducibility (2.1e-3 px, SURVEY 0.7)"}
+    rep["pass"] = bool(float(d64.max()) <= 2 * float(r.max()) + 2e-3 and float(d64.mean()) <= 2 * float(r.mean()) + 1e-4)
+    if out_bf16 is not None:
+        d = (out_bf16 - out_fp32).abs()
+        rep["bf16_vs_fp32_px"] = {"mean": float(d.mean()), "max": float(d.max()),
+                                  "note": "random-init weights; the |EPE delta| <= 0.02 px gate needs a ground truth "
+                                          "and lives in tests/test_model_gpu.py (structured pairs)"}
+    return rep
+
+
+def sharded_legs(args, rank, world, dev, barrier):
+    """BASELINE configs 3 and 5 on all ranks: data-parallel training step, one 2048x3072 pair over row bands."""
+    import torch
+    import torch.distributed as dist
+
+    from cmf.models import get_model
+    from cmf.models.cmfsm import cmfsm
+    from cmf_b200 import parallel as par
+
+    out = {}
+    # ---- config 3: training step, batch 8 per GPU of 256x512 crops, NCCL gradient all-reduce
+    torch.manual_seed(0)
+    net = get_model("cmfsm").to(dev).train()
+    par.broadcast_parameters(net)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    g = torch.Generator().manual_seed(100 + rank)
+    pb = 8
+    left, right = torch.rand(pb, 3, 256, 512, generator=g).to(dev), torch.rand(pb, 3, 256, 512, generator=g).to(dev)
+    disp = (torch.rand(pb, 256, 512, generator=g) * 191 + 0.5).to(dev)
+    loss = None
+    for _ in range(2):
+        loss = par.dp_train_step(net, opt, left, right, disp)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_steps = 3
+    for _ in range(n_steps):
+        loss = par.dp_train_step(net, opt, left, right, disp)
+    e1.record()
+    barrier()
+    # the gradient all-reduce alone (same buffers)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(5):
+        par.allreduce_gradients(list(net.parameters()))
+    a1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / n_steps, a0.elapsed_time(a1) / 5], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["c3_train"] = {"workload": "training step (fwd + bwd + gradient all-reduce + Adam), 256x512 crops, batch %d per GPU "
+                                   "x %d GPUs" % (pb, world), "ms_per_step": float(t[0]),
+                       "pairs_per_s": world * pb / (float(t[0]) * 1e-3), "allreduce_ms": float(t[1]),
+                       "global_loss": float(loss)}
+    del net, opt, left, right, disp
+    torch.cuda.empty_cache()
+
+    # ---- config 5: one 2048x3072 pair, maxdisp 384, sharded by row bands with halo exchange
+    torch.manual_seed(0)
+    big = cmfsm(maxdisp=384).to(dev).eval()
+    par.broadcast_parameters(big)
+    g = torch.Generator().manual_seed(7)
+    left, right = torch.rand(1, 3, 2048, 3072, generator=g).to(dev), torch.rand(1, 3, 2048, 3072, generator=g).to(dev)
+    with torch.no_grad():
+        for _ in range(2):
+            bands = big.forward_row_bands(left, right, gather=True)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(3):
+            bands = big.forward_row_bands(left, right, gather=True)
+        b1.record()
+        barrier()
+        ms_bands = b0.elapsed_time(b1) / 3
+        ms_one, max_abs = 0.0, 0.0
+        if rank == 0:  # the un-sharded forward of the same pair on ONE GPU, same arithmetic (FFMA fp32)
+            big.conv_engine = "ffma"
+            for _ in range(1):
+                whole = big(left, right)
+            torch.cuda.synchronize()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record()
+            for _ in range(2):
+                whole = big(left, right)
+            u1.record()
+            torch.cuda.synchronize()
+            ms_one = u0.elapsed_time(u1) / 2
+            max_abs = max(float((a - b).abs().max()) for a, b in zip(bands, whole))
+            big.conv_engine = "tc3"  # and the fastest one-GPU path (tensor-core fp32-accurate convs)
+            whole = big(left, right)
+            torch.cuda.synchronize()
+            u0.record()
+            for _ in range(2):
+                whole = big(left, right)
+            u1.record()
+            torch.cuda.synchronize()
+            ms_one_tc3 = u0.elapsed_time(u1) / 2
+        else:
+            ms_one_tc3 = 0.0
+        barrier()
+    t = torch.tensor([ms_bands, ms_one, max_abs, ms_one_tc3], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["c5_row_bands"] = {"workload": "ONE 2048x3072 pair, maxdisp 384, fp32, sharded by row bands over %d GPUs "
+                                       "(halo exchange per conv layer, GroupNorm sums all-reduced)" % world,
+                           "ms": float(t[0]), "ms_one_gpu_unsharded": float(t[1]),
+                           "speedup_vs_1": float(t[1]) / float(t[0]), "max_abs_vs_unsharded": float(t[2]),
+                           "arithmetic": "bands and the un-sharded comparison run the fp32 FFMA kernels (bit-identical "
+                                         "results expected); ms_one_gpu_unsharded_tc3 is the fastest one-GPU path",
+                           "ms_one_gpu_unsharded_tc3": float(t[3])}
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
+    _use_ours()
     from cmf.models import get_model
     from cmf_b200 import lib, ops
 
@@ -156,7 +412,7 @@ def run_ours(args, rank, world, local_rank):
 
     torch.manual_seed(0)
     model = get_model("cmfsm").to(dev).eval()
-    model.aggregation = args.aggregation
+    model.conv_engine = args.conv_engine
     use_graph = not args.no_cuda_graph
     model.enable_cuda_graph(use_graph)
     left_h, right_h = (t.pin_memory() for t in synthetic_pair(1 + rank))
@@ -172,132 +428,130 @@ def run_ours(args, rank, world, local_rank):
             r = right_h.to(dev, non_blocking=True)
             return model(l, r)[2][:, :, :H_IMG].contiguous().cpu()
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
+    legs = {}
+    for mode in ("fp32", "bf16"):
+        model.aggregation = mode
+        n0 = lib.launch_count()
+        out, ms_total, e2e_ms, clocks = timed_leg(model, step_device, step_e2e, args.steps, args.warmup, barrier,
+                                                  local_rank, lib)
+        assert tuple(out.shape) == (1, 1, H_IMG, W_IMG) and bool(torch.isfinite(out).all())
+        kernels, launches, ms_eager = per_kernel_pass(model, step_device, args.steps, barrier, ops, lib, use_graph)
+        t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        legs[mode] = {"out": out, "ms_total": float(t[0]), "e2e_ms": float(t[1]), "clocks": clocks, "kernels": kernels,
+                      "launches": launches, "ms_eager": ms_eager}
+        if args.skip_bf16_leg:
+            break
+    model.aggregation = "fp32"
 
-    # ---------------- timed region: K steps, device-resident inputs (one CUDA-graph replay per step by default)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    n0 = lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = step_device()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    assert tuple(out.shape) == (1, 1, H_IMG, W_IMG) and bool(torch.isfinite(out).all())
-
-    # ---------------- same K steps launched kernel by kernel with a CUDA event pair around every launch (on the
-    # launching stream): per-kernel durations for the roofline / share report and the launch count
-    model.enable_cuda_graph(False)
-    for _ in range(3):  # the eager path uses the regular allocator pool: populate it before timing
-        step_device()
-    ops.enable_event_timing(True)
-    n0 = lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step_device()
-    ev1.record()
-    barrier()
-    launches = (lib.launch_count() - n0) // args.steps
-    ms_eager = ev0.elapsed_time(ev1)
-    kernels = ops.drain_event_timing()
-    ops.enable_event_timing(False)
-    model.enable_cuda_graph(use_graph)
-
-    # ---------------- end-to-end: pinned host inputs -> H2D -> forward -> D2H, every step
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    assert res.shape[-2:] == (H_IMG, W_IMG)
-
-    t = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        model.enable_cuda_graph(False)
+        del model
+        torch.cuda.empty_cache()
+        sharded = sharded_legs(args, rank, world, dev, barrier)
 
     if rank == 0:
-        hbm_peak, peak_src = peaks()
+        hbm_peak, tpeak, peak_src = peaks()
         h, w, D = H_PAD // 4, W_IMG // 4, MAXDISP // 4
-        # read both fp32 feature maps once + write every voxel (4 B fp32 NCDHW, or 2 B in the C8/bf16 mode)
-        s_out = 4 if args.aggregation == "fp32" else 2
-        k1_name = "cost_volume_concat_fwd" if args.aggregation == "fp32" else "cost_volume_concat_c8_bf16"
-        k1_bytes = 2 * 32 * h * w * 4 + 64 * D * h * w * s_out
-        k1_n, k1_ms = kernels.get(k1_name, (0, 0.0))
-        k1_traffic = None  # dram read+write bytes per launch of the fp32 kernel, from the committed ncu capture
-        tpath = os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")
-        if args.aggregation == "fp32" and os.path.exists(tpath):
-            k1_traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
-        k1_gbs = (k1_bytes * k1_n / (k1_ms * 1e-3) / 1e9) if k1_ms > 0 else None
-        share = {k: {"launches": n // args.steps, "ms_per_step": ms / args.steps,
-                     "share": ms / ms_eager} for k, (n, ms) in sorted(kernels.items())}
-        precision = ("fp32 FMA 3-D aggregation (parity mode)" if args.aggregation == "fp32" else
-                     "bf16-operand/fp32-accumulate tcgen05 implicit-GEMM 3-D aggregation (all 28 layers; 2-D features fp32 FMA)")
-        ig_n, ig_ms = 0, 0.0
-        for name in ("conv3d_igemm_bf16_fwd", "conv3d_s2_igemm_bf16_fwd", "deconv3d_igemm_bf16_fwd"):
-            n_, ms_ = kernels.get(name, (0, 0.0))
-            ig_n, ig_ms = ig_n + n_, ig_ms + ms_
-        vox = D * h * w
-        # stride-1 convs (dres0/1, conv2, conv4, classif.0) + per hourglass conv1/conv3 (stride 2) and
-        # conv5/conv6 (transposed) = every 3-D layer except the three 32->1 classifier convs
-        ig_macs = 27 * (vox * (64 * 32 + 6 * 32 * 32) + 3 * (vox // 8) * 64 * 64 + 3 * (vox // 64) * 64 * 64
-                        + 3 * ((vox // 8) * 32 * 64 + (vox // 64) * 64 * 64)      # conv1, conv3
-                        + 3 * ((vox // 64) * 64 * 64 + (vox // 8) * 64 * 32))     # conv5, conv6
-        line = {"metric": METRIC, "value": world * args.steps / (ms_total * 1e-3), "unit": "pairs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if args.aggregation == "fp32" else "bf16",
-                "data": "synthetic",
+        macs = conv_macs(h, w, D)
+        f, K = legs["fp32"], args.steps
+
+        def kern(leg, name):
+            n, ms = leg["kernels"].get(name, (0, 0.0))
+            return n // K, ms / K  # launches per step, ms per step
+
+        def shares(leg):
+            return {k: {"launches": n // K, "ms_per_step": ms / K, "share": ms / leg["ms_eager"]}
+                    for k, (n, ms) in sorted(leg["kernels"].items())}
+
+        # ---- dominant kernel of the fp32 step: conv_tc3 (every stride-1 conv, 2-D and 3-D)
+        tc_n, tc_ms = kern(f, "conv_tc3_fwd")
+        tc_macs = macs["tc3_2d"] + macs["tc3_3d"]
+        roof = None
+        if tc_n:
+            alg = 2.0 * tc_macs / (tc_ms * 1e-3) / 1e12
+            roof = {"kernel": "conv_tc3_kernel (fp32-accurate stride-1 convs on tcgen05, %d launches/step = %.1f%% of the "
+                              "step)" % (tc_n, 100.0 * tc_ms * K / f["ms_eager"]),
+                    "bound": "tensor", "achieved": alg, "peak": tpeak, "unit": "TFLOP/s", "frac": alg / tpeak,
+                    "traffic": None, "peak_source": "bf16_tflops_sustained, " + peak_src,
+                    "algorithmic_flops_per_step": 2.0 * tc_macs,
+                    "executed_bf16_mma": {"tflops": 6.0 * alg, "frac": 6.0 * alg / tpeak,
+                                          "note": "every fp32 product = 6 exact bf16 MMAs (three-term split), so the "
+                                                  "ceiling of `frac` on this pipe is 1/6 = 0.167; `executed` is the "
+                                                  "tensor-pipe work actually issued"}}
+        else:  # FFMA engine: the 3-D direct conv dominates
+            c_n, c_ms = kern(f, "conv3d_k3_fwd")
+            alg = 2.0 * (macs["tc3_3d"] + macs["s2_3d"] + macs["cout1"]) / (c_ms * 1e-3) / 1e12 if c_ms else None
+            roof = {"kernel": "conv3d_k3_fwd (fp32 FFMA2 direct conv, %d launches/step)" % c_n, "bound": "tensor",
+                    "achieved": alg, "peak": tpeak, "unit": "TFLOP/s", "frac": alg / tpeak if alg else None,
+                    "traffic": None, "peak_source": "bf16_tflops_sustained, " + peak_src}
+        # ---- K1
+        def k1(leg, mode):
+            for name, s_out in (("cost_volume_concat_c8s3", 6), ("cost_volume_concat_fwd", 4),
+                                ("cost_volume_concat_c8_bf16", 2)):
+                n, ms = kern(leg, name)
+                if n:
+                    nbytes = 2 * 32 * h * w * 4 + 64 * D * h * w * s_out
+                    gbs = nbytes * n / (ms * 1e-3) / 1e9
+                    tr = None
+                    tpath = os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")
+                    if os.path.exists(tpath):
+                        tr = json.load(open(tpath)).get(name)
+                    return {"kernel": name + " (K1)", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": gbs / hbm_peak, "traffic": tr, "peak_source": "hbm_gbs, " + peak_src,
+                            "algorithmic_bytes_per_launch": nbytes, "us_per_launch": ms / n * 1e3,
+                            "bytes_per_voxel_written": s_out}
+            return None
+
+        precision = ("fp32 parity mode: stride-1 convs (2-D and 3-D) as three-term bf16 splits on tcgen05 with fp32 TMEM "
+                     "accumulation (fp32-accurate, csrc/conv_tc3.cu); stride-2 / transposed / 32->1 / 3->32 convs, K4, K5 "
+                     "fp32 FMA" if args.conv_engine == "tc3" else "fp32 FMA everywhere (CUDA cores)")
+        line = {"metric": METRIC, "value": world * K / (f["ms_total"] * 1e-3), "unit": "pairs/s", "n_gpus": world,
+                "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": f["ms_total"] / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "parallelism": "independent pairs, %d rank(s), no collective" % world,
-                           "l2": "working set per step (425 MB cost volume, 212 MB activations) exceeds the 126 MB L2",
-                           "precision": precision + "; fp32 FMA 2-D features, K1/K4/K5 fp32"},
-                "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "pairs/s",
+                           "l2": "working set per step (637 MB cost volume, 200-530 MB per layer) exceeds the 126 MB L2",
+                           "precision": precision},
+                "e2e": {"value": world * K / (f["e2e_ms"] * 1e-3), "unit": "pairs/s",
                         "h2d_bytes_per_step": 2 * 3 * H_PAD * W_IMG * 4, "d2h_bytes_per_step": H_IMG * W_IMG * 4},
-                "gpu_launches": int(launches) * args.steps,
+                "gpu_launches": int(f["launches"]) * K,
                 "launch_mode": {"timed_region": "one CUDA-graph replay per step (%d kernel nodes of libcmfb200 + ATen "
-                                                "cat / zero-fill / copy nodes)" % launches if use_graph else "eager launches",
-                                "ms_per_step_eager_with_events": ms_eager / args.steps},
-                "roofline": {"kernel": k1_name + " (K1)", "bound": "hbm", "achieved": k1_gbs,
-                             "peak": hbm_peak, "unit": "GB/s", "frac": (k1_gbs / hbm_peak) if k1_gbs else None,
-                             "traffic": k1_traffic, "traffic_source": "profiles/k1_ncu_traffic.json (ncu --set full)",
-                             "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
-                             "us_per_launch": (k1_ms / k1_n * 1e3) if k1_n else None},
-                "kernels": share, "clocks": sampler.summary()}
-        if ig_n:
-            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
-                os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-            tpeak = float(pk.get("bf16_tflops_sustained", 1400.0))
-            tf = 2.0 * ig_macs * args.steps / (ig_ms * 1e-3) / 1e12
-            line["roofline_k2"] = {"kernel": "tcgen05 implicit-GEMM kernels conv3d/conv3d_s2/deconv3d_igemm_bf16 (K2, %d launches/step)" % (ig_n // args.steps),
-                                   "bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
-                                   "frac": tf / tpeak, "traffic": None,
-                                   "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json" if pk else "fallback",
-                                   "algorithmic_flops_per_step": 2.0 * ig_macs}
-            c1_n, c1_ms = kernels.get("conv3d_igemm_cout1_bf16_fwd", (0, 0.0))
-            if c1_n:  # the three 32->1 classifier convs run the 32->32 schedule on zero-padded weights (1/32 useful)
-                all_macs = ig_macs + 3 * 27 * vox * 32
-                tf28 = 2.0 * all_macs * args.steps / ((ig_ms + c1_ms) * 1e-3) / 1e12
-                line["roofline_k2"]["all_28_layers"] = {"achieved": tf28, "frac": tf28 / tpeak,
-                                                        "algorithmic_flops_per_step": 2.0 * all_macs,
-                                                        "launches": (ig_n + c1_n) // args.steps}
-        if world == 1 and not args.no_cpu_baseline:
-            times, cores = time_cpu_oracle(3)
-            sec = statistics.median(times[1:]) if len(times) > 1 else times[0]
-            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                    "sample": "median of %d full 576x960 pairs after 1 warm-up (CPU oracle port)"
-                                              % (len(times) - 1)}
+                                                "cat / zero-fill / copy nodes)" % f["launches"] if use_graph else "eager launches",
+                                "ms_per_step_eager_with_events": f["ms_eager"] / K},
+                "roofline": roof, "roofline_k1": k1(f, "fp32"),
+                "kernels": shares(f), "clocks": f["clocks"]}
+        if "bf16" in legs:
+            b = legs["bf16"]
+            ig_n, ig_ms = 0, 0.0
+            for name in ("conv3d_igemm_bf16_fwd", "conv3d_s2_igemm_bf16_fwd", "deconv3d_igemm_bf16_fwd"):
+                n_, ms_ = kern(b, name)
+                ig_n, ig_ms = ig_n + n_, ig_ms + ms_
+            ig_macs = macs["tc3_3d"] + macs["s2_3d"] + macs["deconv_3d"]
+            tf = 2.0 * ig_macs / (ig_ms * 1e-3) / 1e12 if ig_ms else None
+            line["bf16"] = {"what": "same workload, model.aggregation='bf16' (BASELINE config 4's arithmetic): all 25 "
+                                    "GroupNorm-ed 3-D convs as bf16-operand / fp32-accumulate tcgen05 implicit GEMMs, "
+                                    "the 32->1 classifier tails and the 2-D extractor fp32-accurate",
+                            "value": world * K / (b["ms_total"] * 1e-3), "unit": "pairs/s", "ms_per_step": b["ms_total"] / K,
+                            "e2e": {"value": world * K / (b["e2e_ms"] * 1e-3), "unit": "pairs/s"},
+                            "gpu_launches": int(b["launches"]) * K,
+                            "roofline_k2": {"kernel": "tcgen05 implicit-GEMM kernels conv3d / conv3d_s2 / deconv3d_igemm_bf16 "
+                                                      "(%d launches/step)" % ig_n, "bound": "tensor", "achieved": tf,
+                                            "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak if tf else None,
+                                            "traffic": None, "algorithmic_flops_per_step": 2.0 * ig_macs,
+                                            "ms_per_step": ig_ms},
+                            "roofline_k1": k1(b, "bf16"), "kernels": shares(b), "clocks": b["clocks"]}
+        line["parity"] = parity_report(f["out"], legs["bf16"]["out"] if "bf16" in legs else None)
+        if sharded is not None:
+            line["sharded"] = sharded
+        if world == 1 and not args.no_baselines:
+            py = sys.executable
+            cpu = _json_from_subprocess([py, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "5",
+                                         "--warmup", "1"], 400)
+            line["cpu_baseline"] = cpu.get("cpu_baseline", cpu)
+            line["gpu_eager_baseline"] = _json_from_subprocess(
+                [py, os.path.join(ROOT, "tools", "time_reference_gpu.py"), "5"], 400)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -310,11 +564,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
-    ap.add_argument("--aggregation", default="fp32", choices=("fp32", "bf16"),
-                    help="3-D aggregation arithmetic: fp32 FMA (BASELINE config 2, default) or bf16 tcgen05")
+    ap.add_argument("--conv-engine", default="tc3", choices=("tc3", "ffma"),
+                    help="fp32 convs: tc3 = fp32-accurate split-bf16 on tcgen05 (default), ffma = CUDA cores only")
     ap.add_argument("--no-cuda-graph", action="store_true",
-                    help="launch the ~900 kernels of a forward one by one instead of replaying one CUDA graph")
-    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~30 s CPU oracle timing")
+                    help="launch the kernels of a forward one by one instead of replaying one CUDA graph")
+    ap.add_argument("--skip-bf16-leg", action="store_true", help="time the fp32 mode only")
+    ap.add_argument("--no-baselines", action="store_true", help="skip the CPU-reference and GPU-eager-reference timings")
+    ap.add_argument("--no-sharded", action="store_true", help="N>1: skip the data-parallel training / row-band legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

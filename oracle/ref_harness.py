@@ -24,8 +24,9 @@ def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "cmf", "models"))
 
 
-def import_reference():
-    """Returns (get_model, ref_module) where ref_module is the python module cmf.models.cmfsm."""
+def import_reference(force_cpu=False):
+    """Returns (get_model, ref_module) where ref_module is the python module cmf.models.cmfsm.
+    `force_cpu`: neutralise the hard-coded `.cuda()` calls even when a GPU is present (CPU baseline on the GPU box)."""
     import torch
 
     if not reference_available():
@@ -39,7 +40,7 @@ def import_reference():
     stub = types.ModuleType("cmf.caffe_pb2")
     sys.modules["cmf.caffe_pb2"] = stub
     cmf.caffe_pb2 = stub
-    if not torch.cuda.is_available():
+    if force_cpu or not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.nn.Module.cuda = lambda self, *a, **k: self
     else:
