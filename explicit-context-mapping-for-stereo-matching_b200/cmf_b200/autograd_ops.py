@@ -319,3 +319,37 @@ class _SoftargminCtxmap(Function):
 
 def softargmin_ctxmap(c1, c2, c3, weights9, scale):
     return _SoftargminCtxmap.apply(c1, c2, c3, weights9, scale)
+
+
+class _MaskedSmoothL1(Function):
+    """The reference training loss (train.py:162-174) as two fused kernels: one pass for the three masked sums + the
+    valid-pixel count, one pass for the three gradients.  `group`/`distributed`: the count is all-reduced so that every
+    rank divides by the GLOBAL number of valid pixels (summing gradients over ranks then reproduces the reference's
+    single-process DataParallel mean exactly)."""
+
+    @staticmethod
+    def forward(ctx, o1, o2, o3, disp, maxdisp, w1, w2, w3, distributed, group):
+        o1, o2, o3, disp = o1.contiguous(), o2.contiguous(), o3.contiguous(), disp.contiguous()
+        sums = ops.masked_smooth_l1_sums(o1, o2, o3, disp, maxdisp)
+        count = sums[3:4].clone()
+        if distributed:
+            import torch.distributed as dist
+
+            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        count = count.clamp_min(1.0)
+        wts = torch.tensor([w1, w2, w3], device=disp.device, dtype=torch.float64)
+        ctx.maxdisp = maxdisp
+        ctx.save_for_backward(o1, o2, o3, disp, (wts / count).float())
+        return ((sums[:3] * wts).sum() / count[0]).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        o1, o2, o3, disp, scale = ctx.saved_tensors
+        g1, g2, g3 = ops.masked_smooth_l1_grads(o1, o2, o3, disp, (scale * g).contiguous(), ctx.maxdisp)
+        return g1, g2, g3, None, None, None, None, None, None, None
+
+
+def masked_smooth_l1(outputs, disparity, maxdisp=192, weights=(0.5, 0.7, 1.0), distributed=False, group=None):
+    o1, o2, o3 = outputs
+    return _MaskedSmoothL1.apply(o1, o2, o3, disparity, float(maxdisp), float(weights[0]), float(weights[1]),
+                                 float(weights[2]), bool(distributed), group)

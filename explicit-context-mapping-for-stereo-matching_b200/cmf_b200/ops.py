@@ -91,6 +91,44 @@ def cost_volume_concat(L, R, D):
     return cost
 
 
+def cost_volume_corr(L, R, D, normalize=False):
+    """Correlation cost volume [B,D,h,w]: mean over channels of L[x] * R[x-d] (cosine similarity with `normalize`)."""
+    _req(L, R)
+    if L.shape != R.shape:
+        raise ValueError("left/right feature shapes differ: %s vs %s" % (tuple(L.shape), tuple(R.shape)))
+    B, C, h, w = L.shape
+    out = torch.empty((B, D, h, w), device=L.device, dtype=torch.float32)
+    with torch.cuda.device(L.device), _timed("cost_volume_corr_fwd"):
+        _lib.check(_lib.load().cmfb200_cost_volume_corr_fwd(_p(L), _p(R), _p(out), B, C, h, w, D, int(normalize), _stream()),
+                   "cost_volume_corr_fwd")
+    return out
+
+
+def masked_smooth_l1_sums(o1, o2, o3, disp, maxdisp):
+    """One pass over the three outputs and the target (train.py:162-174): returns a [4] double tensor
+    [sum smooth_l1(o1-d), sum smooth_l1(o2-d), sum smooth_l1(o3-d), count] over valid pixels 0 < d < maxdisp."""
+    _req(o1, o2, o3, disp)
+    n = disp.numel()
+    if not (o1.numel() == o2.numel() == o3.numel() == n):
+        raise ValueError("masked_smooth_l1: outputs and target differ in size")
+    sums = torch.zeros(4, device=disp.device, dtype=torch.float64)
+    with torch.cuda.device(disp.device), _timed("masked_smooth_l1_fwd"):
+        _lib.check(_lib.load().cmfb200_masked_smooth_l1_fwd(_p(o1), _p(o2), _p(o3), _p(disp), _p(sums), n, float(maxdisp),
+                                                            _stream()), "masked_smooth_l1_fwd")
+    return sums
+
+
+def masked_smooth_l1_grads(o1, o2, o3, disp, scale3, maxdisp):
+    """Gradients of the three outputs: scale3[i] * clamp(o_i - d, -1, 1) on valid pixels (scale3: 3 floats on device)."""
+    _req(o1, o2, o3, disp, scale3)
+    gs = [torch.empty_like(o) for o in (o1, o2, o3)]
+    with torch.cuda.device(disp.device), _timed("masked_smooth_l1_bwd"):
+        _lib.check(_lib.load().cmfb200_masked_smooth_l1_bwd(_p(o1), _p(o2), _p(o3), _p(disp), _p(scale3), _p(gs[0]),
+                                                            _p(gs[1]), _p(gs[2]), disp.numel(), float(maxdisp), _stream()),
+                   "masked_smooth_l1_bwd")
+    return gs
+
+
 def cost_volume_concat_bwd(g, C):
     _req(g)
     B, C2, D, h, w = g.shape

@@ -80,10 +80,17 @@ def broadcast_parameters(module, src=0, group=None):
         dist.broadcast(t.data, src=src, group=group)
 
 
-def masked_smooth_l1_dp(outputs, target, mask, weights=(0.5, 0.7, 1.0), group=None):
-    """The reference loss (train.py:168-174): sum_i w_i * smooth_l1(out_i[mask], target[mask]) with the MEAN taken
-    over the valid pixels of the GLOBAL batch.  Each rank contributes sum/global_count, so that summing gradients
-    over ranks (allreduce_gradients(average=False)) reproduces the single-process DataParallel gradient exactly."""
+def masked_smooth_l1_dp(outputs, target, maxdisp=192, weights=(0.5, 0.7, 1.0), group=None):
+    """The reference loss (train.py:162-174): sum_i w_i * smooth_l1(out_i[mask], target[mask]) with the MEAN taken
+    over the valid pixels (0 < target < maxdisp) of the GLOBAL batch.  Each rank contributes sum/global_count, so that
+    summing gradients over ranks (allreduce_gradients(average=False)) reproduces the single-process DataParallel
+    gradient exactly.  Two fused kernels (cmfb200_masked_smooth_l1_fwd/_bwd) instead of the reference's mask, gathers
+    and reductions; CPU tensors (the gloo tests of the sharding arithmetic) take the plain PyTorch statement."""
+    if outputs[0].is_cuda:
+        from . import autograd_ops as aops
+
+        return aops.masked_smooth_l1(outputs, target, maxdisp, weights, distributed=world(group) > 1, group=group)
+    mask = ((target < maxdisp) & (target > 0)).detach()
     count = mask.sum().to(torch.float64)
     if world(group) > 1:
         dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
@@ -97,10 +104,9 @@ def masked_smooth_l1_dp(outputs, target, mask, weights=(0.5, 0.7, 1.0), group=No
 
 def dp_train_step(model, optimizer, left, right, disparity, maxdisp=192):
     """One data-parallel training step on this rank's shard of the batch.  Returns the (global) loss value."""
-    mask = ((disparity < maxdisp) & (disparity > 0)).detach()  # train.py:162
     optimizer.zero_grad(set_to_none=True)
     outputs = model(left, right)
-    loss = masked_smooth_l1_dp(outputs, disparity, mask)
+    loss = masked_smooth_l1_dp(outputs, disparity, maxdisp)  # mask = (disparity < maxdisp) & (disparity > 0), train.py:162
     loss.backward()
     allreduce_gradients(list(model.parameters()), average=False)
     optimizer.step()

@@ -267,6 +267,24 @@ int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const double* gn_sums
 int cmfb200_cost_volume_concat_c8s3(const float* L, const float* R, void* cost_c8s3, int B, int C, int h, int w, int D,
                                     void* stream);
 
+/* ---- K1, correlation form: corr[b,d,y,x] = (1/C) sum_c L[b,c,y,x] R[b,c,y,x-d] for x >= d, +0.0 otherwise; with
+ * normalize != 0 the cosine similarity sum_c L R / max(|L| |R|, 1e-8) instead.  The reference has no live correlation
+ * path (its models build the concat volume); this is the cosine matching of the dead file
+ * "cmf/models/rstereo # dense volume match.py":309-311 with K1's shift / mask convention.  corr: [B][D][h][w]. */
+int cmfb200_cost_volume_corr_fwd(const float* L, const float* R, float* corr, int B, int C, int h, int w, int D,
+                                 int normalize, void* stream);
+
+/* ---- fused masked smooth-L1 training loss (train.py:162-174) --------------------------------------------------------
+ * valid = (disp < maxdisp) & (disp > 0).  fwd: sums4 (ZEROED, doubles) += [sum_valid smooth_l1(out_i - disp) for i = 1..3,
+ * number of valid pixels]; the caller forms loss = sum_i weight_i * sums[i] / count (count all-reduced over ranks in
+ * data-parallel training).  bwd: g_i = scale3[i] * clamp(out_i - disp, -1, 1) on valid pixels, 0 elsewhere, with
+ * scale3 (DEVICE, 3 floats) = weight_i * dLoss / count.  n = number of pixels (B*H*W). */
+int cmfb200_masked_smooth_l1_fwd(const float* out1, const float* out2, const float* out3, const float* disp, double* sums4,
+                                 long long n, float maxdisp, void* stream);
+int cmfb200_masked_smooth_l1_bwd(const float* out1, const float* out2, const float* out3, const float* disp,
+                                 const float* scale3, float* g1, float* g2, float* g3, long long n, float maxdisp,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

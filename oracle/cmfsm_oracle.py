@@ -184,6 +184,33 @@ def cost_volume_concat(L, R, D):
     return cost
 
 
+def cost_volume_corr(L, R, D, normalize=False):
+    """Correlation form of K1 -- PARITY UNPINNED: the reference has no live correlation path.  Restates the cosine
+    matching of the dead file "cmf/models/rstereo # dense volume match.py":309-311 (nn.CosineSimilarity(dim=1) of the
+    left features with shifted right features) with the shift / mask convention of the concat volume above:
+        corr[b,d,y,x] = mean_c L[b,c,y,x] * R[b,c,y,x-d]          (x >= d, +0.0 otherwise)
+        normalize:      sum_c L R / max(|L| |R|, 1e-8)            (torch.nn.functional.cosine_similarity, eps 1e-8)"""
+    B, C, h, w = L.shape
+    out = L.new_zeros((B, D, h, w))
+    for d in range(min(D, w)):
+        l, r = L[:, :, :, d:], R[:, :, :, :w - d]
+        if normalize:
+            out[:, d, :, d:] = (l * r).sum(1) / (l.norm(dim=1) * r.norm(dim=1)).clamp_min(1e-8)
+        else:
+            out[:, d, :, d:] = (l * r).mean(1)
+    return out
+
+
+def masked_smooth_l1(outputs, disparity, maxdisp=192, weights=(0.5, 0.7, 1.0)):
+    """The training loss of the reference drivers, train.py:162-174 (mask, three masked means, weighted sum)."""
+    mask = (disparity < maxdisp) & (disparity > 0)
+    loss = 0.0
+    for wgt, o in zip(weights, outputs):
+        o = torch.squeeze(o, 1)
+        loss = loss + wgt * F.smooth_l1_loss(o[mask], disparity[mask], reduction="mean")
+    return loss
+
+
 def cost_volume_concat_bwd(g, C):
     """Adjoint of cost_volume_concat: dL[x] = sum_{d<=x} g[c,d,x]; dR[x] = sum_{d,x+d<w} g[C+c,d,x+d]."""
     B, _, D, h, w = g.shape

@@ -599,3 +599,37 @@ def test_trilinear_softargmin_vs_oracle(B, Dl, h, w, maxdisp, H, W):
     for a, b in zip(got, want):
         assert a.shape == b.shape
         torch.testing.assert_close(a.cpu().double(), b, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,C,h,w,D,norm", [(1, 32, 6, 40, 12, False), (2, 32, 5, 77, 24, True), (1, 64, 3, 33, 48, False),
+                                             (1, 8, 4, 20, 30, True)])
+def test_cost_volume_corr_vs_oracle(B, C, h, w, D, norm):
+    """Correlation form of K1 (warp-shuffle channel reduction) vs the oracle restatement (parity unpinned by the
+    reference: it has no live correlation path, see oracle/cmfsm_oracle.py::cost_volume_corr)."""
+    from cmf_b200 import ops
+
+    L, R = _rand(B, C, h, w, seed=110), _rand(B, C, h, w, seed=111)
+    want = orc.cost_volume_corr(L.double(), R.double(), D, norm)
+    got = ops.cost_volume_corr(L.to(DEV), R.to(DEV), D, norm)
+    assert got.shape == want.shape
+    torch.testing.assert_close(got.cpu().double(), want, rtol=1e-5, atol=1e-6)
+    assert not torch.signbit(got.cpu()[want == 0]).any()  # +0.0 in the masked triangle, like the concat volume
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 16, 24), (3, 37, 53)])
+def test_masked_smooth_l1_fused_vs_reference_statement(B, H, W):
+    """The two fused loss kernels vs the reference drivers' statement (train.py:162-174), value and gradients."""
+    from cmf_b200 import autograd_ops as aops
+
+    g = torch.Generator().manual_seed(120)
+    disp = torch.rand(B, H, W, generator=g) * 260 - 30  # some targets outside (0, 192)
+    outs = [(disp + torch.randn(B, H, W, generator=g) * s).unsqueeze(1) for s in (0.3, 2.0, 20.0)]
+    ref_in = [o.clone().double().requires_grad_(True) for o in outs]
+    want = orc.masked_smooth_l1(ref_in, disp.double(), 192)
+    want.backward()
+    ours_in = [o.clone().to(DEV).requires_grad_(True) for o in outs]
+    got = aops.masked_smooth_l1(ours_in, disp.to(DEV), 192)
+    (got * 3.0).backward()
+    assert abs(float(got) - float(want)) < 1e-5 * abs(float(want))
+    for a, b in zip(ours_in, ref_in):
+        torch.testing.assert_close(a.grad.cpu().double(), 3.0 * b.grad, rtol=1e-5, atol=1e-9)

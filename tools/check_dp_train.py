@@ -75,8 +75,7 @@ def main():
     # ---- gradient equivalence: sharded (all-reduced) gradients vs one process on the whole batch, same weights
     def grads_of(net, l, r, d):
         net.zero_grad(set_to_none=True)
-        mask = ((d < 192) & (d > 0)).detach()
-        loss = par.masked_smooth_l1_dp(net(l, r), d, mask)
+        loss = par.masked_smooth_l1_dp(net(l, r), d, 192)
         loss.backward()
         return loss.detach()
 
@@ -89,7 +88,7 @@ def main():
     g_sharded = torch.cat([p.grad.reshape(-1) for p in probe.parameters()]).clone()
     if rank == 0 and world > 1:
         dist_world = par.world
-        par.world = lambda: 1  # single-process semantics for the reference pass
+        par.world = lambda group=None: 1  # single-process semantics for the reference pass
         try:
             loss_r = grads_of(probe, *[t.to(dev) for t in (left, right, disp)])
         finally:
