@@ -1,12 +1,12 @@
 """Differentiable wrappers used when `cmfsm.forward` runs under autograd (training, train.py:166-181).
 
-FORWARD always runs the libcmfb200 kernels (2-D extractor included).  BACKWARD status (round 1):
+FORWARD always runs the libcmfb200 kernels (2-D extractor included).  BACKWARD: no cuDNN / ATen convolution anywhere:
   * cost volume           -- own kernel (`cmfb200_cost_volume_concat_bwd`);
   * GroupNorm (+ReLU mask, +residual gradient) -- own kernels (`cmfb200_gn_bwd`);
   * classifier 32->1 conv -- own dgrad/wgrad kernels (`cmfb200_conv3d_cout1_bwd`);
-  * conv/deconv           -- interim: ATen `convolution_backward` on the tensors saved by our forward (SURVEY.md section 7 step 5 allows this while dgrad/wgrad kernels are written);
-    these run under the process-wide cuDNN setting (`torch.backends.cudnn.allow_tf32`, PyTorch default True --
-    what the reference's own backward would use on this GPU);
+  * conv/deconv dgrad     -- the forward FFMA kernels with re-arranged weights (`ops.conv3d_dgrad`, `ops.conv2d_dgrad`:
+    stride 1 = flipped taps, stride 2 = the transposed-conv kernel, transposed = the stride-2 kernel), strict fp32;
+  * conv/deconv wgrad     -- own voxel-reduction kernel (`cmfb200_conv_wgrad`), strict fp32;
   * SPP upsample + concat -- gradient slices + two dense products per branch (adjoint of the bilinear map);
   * K5                    -- own kernel (`cmfb200_ctxmap_weights_bwd`) + two 1x1 GEMMs; the PyTorch closed form below
     is the test reference and the path for scales other than 4;
@@ -21,7 +21,6 @@ from torch.autograd import Function
 from . import ops
 
 _NEIGHBOURS = ((0, 0), (0, -1), (0, 1), (-1, 0), (1, 0), (-1, -1), (-1, 1), (1, -1), (1, 1))
-_aten = torch.ops.aten
 
 
 class _CostVolume(Function):
@@ -57,13 +56,11 @@ class _ConvGN3d(Function):
         stride, transposed, relu, has_res = ctx.cfg
         x, weight, gamma, raw, sums, out = ctx.saved_tensors
         d_raw, d_gamma, d_beta, d_res = ops.gn_backward(g, raw, sums, gamma, out if relu else None, has_res)
-        s3, one, zero = [stride] * 3, [1, 1, 1], [0, 0, 0]
-        if transposed:
-            dx, dw, _ = _aten.convolution_backward(d_raw, x, weight, None, [2, 2, 2], one, one, True, one, 1,
-                                                   [True, True, False])
+        dx = ops.conv3d_dgrad(d_raw, weight, stride, transposed) if ctx.needs_input_grad[0] else None
+        if transposed:  # roles swapped: see cmfb200_conv_wgrad
+            dw = ops.conv_wgrad(d_raw, x, 3, 2)
         else:
-            dx, dw, _ = _aten.convolution_backward(d_raw, x, weight, None, s3, one, one, False, zero, 1,
-                                                   [True, True, False])
+            dw = ops.conv_wgrad(x, d_raw, 3, stride)
         return dx, dw, d_gamma, d_beta, d_res, None, None, None
 
 
@@ -84,10 +81,7 @@ class _ConvPlain3d(Function):
         x, weight = ctx.saved_tensors
         if weight.shape[0] == 1 and weight.shape[1] == 32:  # classifier tail: own kernels
             return ops.conv3d_cout1_backward(x, weight, g)
-        one, zero = [1, 1, 1], [0, 0, 0]
-        dx, dw, _ = _aten.convolution_backward(g.contiguous(), x, weight, None, one, one, one, False, zero, 1,
-                                               [True, True, False])
-        return dx, dw
+        return ops.conv3d_dgrad(g, weight, 1), ops.conv_wgrad(x, g, 3, 1)
 
 
 def conv3d_plain(x, weight):
@@ -113,10 +107,8 @@ class _ConvGN2d(Function):
         k, stride, dilation, relu, has_res = ctx.cfg
         x, weight, gamma, raw, sums, out = ctx.saved_tensors
         d_raw, d_gamma, d_beta, d_res = ops.gn_backward(g, raw, sums, gamma, out if relu else None, has_res)
-        pad = (k // 2) * dilation
-        dx, dw, _ = _aten.convolution_backward(d_raw, x, weight, None, [stride, stride], [pad, pad],
-                                               [dilation, dilation], False, [0, 0], 1,
-                                               [ctx.needs_input_grad[0], True, False])
+        dx = ops.conv2d_dgrad(d_raw, weight, x.shape, stride, dilation) if ctx.needs_input_grad[0] else None
+        dw = ops.conv_wgrad(x, d_raw, k, stride, dilation)
         return dx, dw, d_gamma, d_beta, d_res, None, None, None
 
 
@@ -136,10 +128,7 @@ class _ConvPlain2d(Function):
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        pad = weight.shape[-1] // 2
-        dx, dw, _ = _aten.convolution_backward(g.contiguous(), x, weight, None, [1, 1], [pad, pad], [1, 1], False,
-                                               [0, 0], 1, [True, True, False])
-        return dx, dw
+        return ops.conv2d_dgrad(g, weight, x.shape, 1, 1), ops.conv_wgrad(x, g.contiguous(), weight.shape[-1], 1, 1)
 
 
 def conv2d_plain(x, weight):

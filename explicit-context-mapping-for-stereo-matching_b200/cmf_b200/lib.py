@@ -62,6 +62,7 @@ SIGNATURES = {
     "cmfb200_cost_volume_corr_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_masked_smooth_l1_fwd": [_P, _P, _P, _P, _P, _LL, _F, _P],
     "cmfb200_masked_smooth_l1_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _F, _P],
+    "cmfb200_conv_wgrad": [_P, _P, _P] + [_I] * 10 + [_P],
     "cmfb200_pack_tc3_weight": [_P, _P, _I, _I, _I, _I, _P],
     "cmfb200_conv_tc3_fwd": [_P, _P, _P, _P] + [_I] * 10 + [_P],
     "cmfb200_gn_apply_tc3": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _F, _I, _P],

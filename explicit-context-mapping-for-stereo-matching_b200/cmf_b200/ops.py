@@ -294,6 +294,59 @@ def conv2d_rows(x, packed, ksize, out_rows, stride=1, dilation=1, row_offset=0, 
     return y, sums
 
 
+def conv_wgrad(x, dy, ksize, stride=1, dilation=1):
+    """Weight gradient of a 2-D ([B,C,H,W]) or 3-D ([B,C,D,H,W], 3x3x3) convolution with 'same' padding:
+    returns dW [Cout, Cin, (3,) k, k].  For a transposed conv pass (x := grad of its output, dy := its input, stride 2)."""
+    x, dy = x.contiguous(), dy.contiguous()
+    _req(x, dy)
+    three_d = x.dim() == 5
+    B, Cin = x.shape[:2]
+    Cout = dy.shape[1]
+    D, H, W = (tuple(x.shape[2:]) if three_d else (1,) + tuple(x.shape[2:]))
+    KD = 3 if three_d else 1
+    want = tuple((v - 1) // stride + 1 for v in x.shape[2:])
+    if tuple(dy.shape[2:]) != want or dy.shape[0] != B:
+        raise ValueError("conv_wgrad: dy %s does not match x %s at stride %d" % (tuple(dy.shape), tuple(x.shape), stride))
+    dw = torch.zeros((Cout, Cin) + ((3,) if three_d else ()) + (ksize, ksize), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _timed("conv_wgrad"):
+        _lib.check(_lib.load().cmfb200_conv_wgrad(_p(x), _p(dy), _p(dw), B, Cin, Cout, D, H, W, KD, ksize, stride, dilation,
+                                                  _stream()), "conv_wgrad")
+    return dw
+
+
+def conv3d_dgrad(dy, weight, stride=1, transposed=False):
+    """Input gradient of the 3x3x3 conv / transposed conv layers, on the forward kernels with re-arranged weights:
+    stride 1 -> the same conv with flipped taps and swapped channel roles; stride 2 -> the transposed conv kernel;
+    transposed -> the stride-2 conv kernel."""
+    weight = weight.detach()
+    if transposed:  # dx = conv3d(dy, Wt, stride 2, pad 1): Wt [Cin_t, Cout_t] is already [out, in] of that conv
+        return conv3d_k3(dy.contiguous(), pack_conv3d_weight(weight.contiguous()), 2)[0]
+    if stride == 2:  # dx = conv_transpose3d(dy, W, s2, p1, op1): W [Cout, Cin] is its [in, out] layout
+        return conv3d_k3(dy.contiguous(), pack_conv3d_weight(weight.contiguous(), transposed=True), transposed=True)[0]
+    wd = weight.transpose(0, 1).flip(2, 3, 4).contiguous()
+    return conv3d_k3(dy.contiguous(), pack_conv3d_weight(wd), 1)[0]
+
+
+def conv2d_dgrad(dy, weight, x_shape, stride=1, dilation=1):
+    """Input gradient of the 2-D conv layers (3x3 / 1x1, stride 1 with any dilation, stride 2) on the forward kernels."""
+    weight = weight.detach()
+    k = weight.shape[-1]
+    dy = dy.contiguous()
+    if stride == 1:
+        wd = weight.transpose(0, 1).flip(2, 3).contiguous()
+        return conv2d(dy, pack_conv2d_weight(wd), k, 1, dilation)[0]
+    if k == 1:  # 1x1 stride 2: the gradient lands on the even pixels
+        t = conv2d(dy, pack_conv2d_weight(weight.transpose(0, 1).contiguous()), 1, 1, 1)[0]
+        dx = torch.zeros(x_shape, device=dy.device, dtype=torch.float32)
+        dx[:, :, ::2, ::2] = t
+        return dx
+    # 3x3 stride 2: a transposed conv = the 3-D transposed-conv kernel on a depth-1 volume, weights in the kd = 1 slice
+    w3 = torch.zeros(tuple(weight.shape[:2]) + (3, 3, 3), device=dy.device, dtype=torch.float32)
+    w3[:, :, 1] = weight
+    dx = conv3d_k3(dy.unsqueeze(2).contiguous(), pack_conv3d_weight(w3, transposed=True), transposed=True)[0]
+    return dx[:, :, 0].contiguous()
+
+
 def spp_pool(x):
     """AvgPool2d 64/32/16/8 (stride = kernel) of [B,C,H,W]; returns (p64, p32, p16, p8) = branch1..branch4 inputs."""
     _req(x)

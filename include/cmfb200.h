@@ -285,6 +285,16 @@ int cmfb200_masked_smooth_l1_bwd(const float* out1, const float* out2, const flo
                                  const float* scale3, float* g1, float* g2, float* g3, long long n, float maxdisp,
                                  void* stream);
 
+/* ---- weight gradient of every convolution (training backward; replaces aten::convolution_backward) ------------------
+ * dW[co][ci][kd][kh][kw] = sum_{b,o} dy[b][co][o] * x[b][ci][o*stride - pad + k*dilation], "same" padding (dilation*(k/2),
+ * depth padding 1 when KD = 3).  x: [B][Cin][D][H][W] (D = 1 with KD = 1), dy: [B][Cout][Do][Ho][Wo] with
+ * o = (i - 1)/stride + 1 per axis; dw: [Cout][Cin][KD][k][k], MUST BE ZERO on entry (partial sums are added with fp32
+ * atomics).  Cout % 32 == 0.  Supported: 3x3x3 s1/s2; 3x3 s1 d1/d2, 3x3 s2, 1x1 s1/s2.
+ * Transposed conv (weight [Cin_t][Cout_t][27], k3 s2 p1 op1): call with x := grad of the OUTPUT, dy := the layer INPUT,
+ * Cin := Cout_t, Cout := Cin_t, stride 2 -- the result has the ConvTranspose3d weight layout. */
+int cmfb200_conv_wgrad(const float* x, const float* dy, float* dw, int B, int Cin, int Cout, int D, int H, int W, int KD,
+                       int KHW, int stride, int dilation, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,9 +283,10 @@ def test_training_step_gradients_flow(model):
 
 def test_training_gradients_match_fp64_oracle():
     """Gradients of the training path (own forward kernels + the backward of cmf_b200.autograd_ops) against
-    autograd through the fp64 CPU oracle on the same weights / inputs / loss.  The network amplifies rounding
-    (fp32 vs fp64 outputs differ by up to 1e-2 px), and ATen's conv backward runs under the
-    PyTorch-default cuDNN TF32 setting, so the gate is a relative L2 distance per tensor, not bit equality."""
+    autograd through the fp64 CPU oracle on the same weights / inputs / loss.  Every kernel of the backward is the
+    repo's own and strict fp32 (no cuDNN / TF32); what remains is the network's amplification of fp32 rounding
+    (fp32 vs fp64 outputs differ by up to 1e-2 px), so the gate is a relative L2 distance per
+    tensor, not bit equality.  Measured (round 2): worst tensor ~1e-3, median ~1e-4."""
     from cmf.models import get_model
 
     torch.manual_seed(2)
@@ -302,20 +303,30 @@ def test_training_gradients_match_fp64_oracle():
     sd64 = {k: v.detach().cpu().double().requires_grad_(True) for k, v in net.state_dict().items()}
     loss64 = loss_of(orc.forward(sd64, left.double(), right.double(), grad=True), target.double())
     loss64.backward()
-    assert abs(float(loss) - float(loss64)) < 1e-3 * abs(float(loss64))
-    worst = {}
+    # the reference's own fp32 arithmetic (CPU autograd through the fp32 oracle) against the same fp64 gradients: the
+    # yardstick, exactly as for the forward -- this network amplifies fp32 rounding in both directions
+    sd32 = {k: v.detach().cpu().requires_grad_(True) for k, v in net.state_dict().items()}
+    loss_of(orc.forward(sd32, left, right, grad=True), target).backward()
+    assert abs(float(loss.detach()) - float(loss64.detach())) < 1e-5 * abs(float(loss64.detach()))
+    ours, ref = {}, {}
     for name, p in net.named_parameters():
-        g, g64 = p.grad.detach().cpu().double(), sd64[name].grad
-        rel = float((g - g64).norm() / g64.norm().clamp_min(1e-30))
-        worst[name] = rel
-    top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
-    print("loss %.6f vs fp64 %.6f; worst gradient rel-L2:" % (float(loss), float(loss64)), top)
-    # every family of the backward: 2-D extractor, SPP branches, K5 MLP, 3-D convs / transposed convs, classifier
+        g64 = sd64[name].grad
+        n64 = g64.norm().clamp_min(1e-30)
+        ours[name] = float((p.grad.detach().cpu().double() - g64).norm() / n64)
+        ref[name] = float((sd32[name].grad.double() - g64).norm() / n64)
+    top = sorted(ours.items(), key=lambda kv: -kv[1])[:5]
+    med_o, med_r = sorted(ours.values())[len(ours) // 2], sorted(ref.values())[len(ref) // 2]
+    print("loss %.6f vs fp64 %.6f; gradient rel-L2 vs fp64: ours worst %.3e median %.3e ; reference fp32 worst %.3e median "
+          "%.3e ; our worst tensors: %s" % (float(loss.detach()), float(loss64.detach()), top[0][1], med_o,
+                                            max(ref.values()), med_r, top))
+    # gate: as close to the fp64 gradients as the reference's own fp32 arithmetic is (x2, + a 1e-4 floor), per tensor
+    # family of the backward (2-D extractor, SPP branches, K5 MLP, 3-D convs / transposed convs, classifier) and overall
     for key in ("feature_extraction.firstconv.0.0.weight", "feature_extraction.branch1.1.0.weight",
                 "feature_extraction.lastconv.2.weight", "mapping_matrix.similarity1.conv0.weight",
                 "dres0.0.0.weight", "dres2.conv5.0.weight", "classif3.2.weight"):
-        assert worst[key] < 0.1, (key, worst[key])
-    assert sorted(worst.values())[len(worst) // 2] < 0.05  # median over all 272 tensors
+        assert ours[key] <= 2 * max(ref.values()) + 1e-4, (key, ours[key], ref[key])
+    assert top[0][1] <= 2 * max(ref.values()) + 1e-4
+    assert med_o <= 2 * med_r + 1e-4
 
 
 def test_sub8_variant_matches_fp64_oracle():
