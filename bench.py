@@ -350,41 +350,32 @@ def sharded_legs(args, rank, world, dev, barrier):
         b1.record()
         barrier()
         ms_bands = b0.elapsed_time(b1) / 3
-        ms_one, max_abs = 0.0, 0.0
-        if rank == 0:  # the un-sharded forward of the same pair on ONE GPU, same arithmetic (FFMA fp32)
-            big.conv_engine = "ffma"
-            for _ in range(1):
+        ms_one, max_abs, ms_one_ffma = 0.0, 0.0, 0.0
+        if rank == 0:  # the un-sharded forward of the same pair on ONE GPU: same engine (tc3), then the FFMA engine
+            def time_whole():
                 whole = big(left, right)
-            torch.cuda.synchronize()
-            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            u0.record()
-            for _ in range(2):
-                whole = big(left, right)
-            u1.record()
-            torch.cuda.synchronize()
-            ms_one = u0.elapsed_time(u1) / 2
+                torch.cuda.synchronize()
+                u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                u0.record()
+                for _ in range(2):
+                    whole = big(left, right)
+                u1.record()
+                torch.cuda.synchronize()
+                return whole, u0.elapsed_time(u1) / 2
+
+            whole, ms_one = time_whole()
             max_abs = max(float((a - b).abs().max()) for a, b in zip(bands, whole))
-            big.conv_engine = "tc3"  # and the fastest one-GPU path (tensor-core fp32-accurate convs)
-            whole = big(left, right)
-            torch.cuda.synchronize()
-            u0.record()
-            for _ in range(2):
-                whole = big(left, right)
-            u1.record()
-            torch.cuda.synchronize()
-            ms_one_tc3 = u0.elapsed_time(u1) / 2
-        else:
-            ms_one_tc3 = 0.0
+            big.conv_engine = "ffma"
+            _, ms_one_ffma = time_whole()
+            big.conv_engine = "tc3"
         barrier()
-    t = torch.tensor([ms_bands, ms_one, max_abs, ms_one_tc3], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_bands, ms_one, max_abs, ms_one_ffma], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    out["c5_row_bands"] = {"workload": "ONE 2048x3072 pair, maxdisp 384, fp32, sharded by row bands over %d GPUs "
-                                       "(halo exchange per conv layer, GroupNorm sums all-reduced)" % world,
+    out["c5_row_bands"] = {"workload": "ONE 2048x3072 pair, maxdisp 384, fp32 (tensor-core fp32-accurate convs), sharded by row "
+                                       "bands over %d GPUs (halo exchange per conv layer, GroupNorm sums all-reduced)" % world,
                            "ms": float(t[0]), "ms_one_gpu_unsharded": float(t[1]),
                            "speedup_vs_1": float(t[1]) / float(t[0]), "max_abs_vs_unsharded": float(t[2]),
-                           "arithmetic": "bands and the un-sharded comparison run the fp32 FFMA kernels (bit-identical "
-                                         "results expected); ms_one_gpu_unsharded_tc3 is the fastest one-GPU path",
-                           "ms_one_gpu_unsharded_tc3": float(t[3])}
+                           "ms_one_gpu_unsharded_ffma_engine": float(t[3])}
     return out
 
 

@@ -558,6 +558,113 @@ class cmfsm(nn.Module):
         o = self._cg2_band(fe.lastconv[0], cat, h, relu=True)
         return self._conv2_band(fe.lastconv[2], o)[0], full
 
+    # ---- row bands on the tensor-core path (conv_engine == "tc3"): the same sharding, activations in C8S3 -----------
+    @staticmethod
+    def _band_sums(sums, band_rows, full_rows):
+        """All-reduce the band's GroupNorm sums and rescale them so that gn_apply (which derives mean / var from the
+        sums and the element count of THIS tensor) reproduces the statistics of the whole volume."""
+        return par.allreduce_gn_sums(sums) * (float(band_rows) / float(full_rows))
+
+    def _tc_band(self, block, x_s3, full_rows, res_s3=None, res_nchw=None, relu=False, want_s3=True, want_nchw=False):
+        """Stride-1 conv (2-D or 3-D) + GroupNorm on a row band: halo rows from the neighbours, row-window conv_tc3."""
+        conv, gn = block[0], block[1]
+        d = conv.dilation[0] if conv.kernel_size[-1] == 3 else 0
+        rows, hdim = x_s3.shape[-3], x_s3.dim() - 3
+        ext = par.exchange_row_halo(x_s3, d, d, dim=hdim) if d else x_s3
+        y, sums = ops.conv_tc3(ext, self._pack_tc3(conv), conv.dilation[0], True, row_off=d, out_rows=rows)
+        sums = self._band_sums(sums, rows, full_rows)
+        return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, True, res_s3=res_s3, res_nchw=res_nchw, relu=relu,
+                                want_s3=want_s3, want_nchw=want_nchw)
+
+    def _ffma2_band_to_s3(self, block, x_nchw, full_rows, relu=False):
+        y, sums = self._conv2_band(block[0], x_nchw, True)
+        sums = self._band_sums(sums, y.shape[2], full_rows)
+        return ops.gn_apply_tc3(y, sums, block[1].weight, block[1].bias, False, relu=relu)[0]
+
+    def _features_band_tc3(self, both, r0, r1):
+        fe = self.feature_extraction
+        H, h = both.shape[2], both.shape[2] // 4
+        x = both[:, :, 4 * r0:4 * r1].contiguous()
+        o = self._ffma2_band_to_s3(fe.firstconv[0], x, H, relu=True)
+        o, _ = self._tc_band(fe.firstconv[2], o, H, relu=True)
+        o, _ = self._tc_band(fe.firstconv[4], o, H, relu=True)
+        ext = par.exchange_row_halo(o, 1, 1, dim=o.dim() - 3)
+        full, fsums = ops.conv_tc3(ext, self._pack_tc3(fe.firstconv[6]), 1, True, out_nchw=True, row_off=1,
+                                   out_rows=o.shape[-3])
+        gn0 = fe.secondconv[0]
+        o = ops.gn_apply(full, self._band_sums(fsums, full.shape[2], H), gn0.weight, gn0.bias, None, True)
+        o = self._ffma2_band_to_s3(fe.secondconv[2], o, H // 2, relu=True)
+        o, o_nchw = self._tc_band(fe.secondconv[4], o, H // 2, relu=True)
+        raw_nchw = None
+        for name, rows in (("layer1", H // 2), ("layer2", h), ("layer3", h), ("layer4", h)):
+            units = getattr(fe, name)
+            for i, unit in enumerate(units):
+                last = i == len(units) - 1
+                want_nchw = last and name in ("layer1", "layer2", "layer4")
+                want_s3 = not (last and name == "layer4")
+                if unit.conv1[0][0].stride[0] == 2:
+                    t = self._ffma2_band_to_s3(unit.conv1[0], o_nchw, rows, relu=True)
+                    skip = self._ffma2_band_to_s3(unit.downsample, o_nchw, rows)
+                else:
+                    t, _ = self._tc_band(unit.conv1[0], o, rows, relu=True)
+                    skip = o if unit.downsample is None else self._tc_band(unit.downsample, o, rows)[0]
+                o, o_nchw = self._tc_band(unit.conv2, t, rows, res_s3=skip, want_s3=want_s3, want_nchw=want_nchw)
+            if name == "layer2":
+                raw_nchw = o_nchw
+        skip_nchw = o_nchw
+        pooled = [par.gather_bands(p, dim=2) for p in ops.spp_pool(skip_nchw)]  # whole-image pooled maps (tiny)
+        b1, b2, b3, b4 = [self._cg2(getattr(fe, "branch%d" % (i + 1))[1], p, relu=True) for i, p in enumerate(pooled)]
+        cat = ops.f32_to_c8s3(ops.spp_upsample_concat(raw_nchw, skip_nchw, b4, b3, b2, b1, full_rows=h, row_offset=r0))
+        o, _ = self._tc_band(fe.lastconv[0], cat, h, relu=True)
+        feat, _ = ops.conv_tc3(o, self._pack_tc3(fe.lastconv[2]), 1, False, out_nchw=True)
+        return feat, full
+
+    def _ffma3_band(self, block, x, full_rows, stride=1, res_nchw=None, relu=False, want_s3=False, want_nchw=True):
+        """Stride-2 / transposed conv (FFMA row-window kernels, NCDHW) + GroupNorm on a row band."""
+        conv, gn = block[0], block[1]
+        packed = self._pack(conv)
+        rows = x.shape[3]
+        if isinstance(conv, nn.ConvTranspose3d):
+            y, sums = ops.conv3d_k3_rows(par.exchange_row_halo(x, 0, 1, dim=3), packed, rows, transposed=True)
+        else:
+            y, sums = ops.conv3d_k3_rows(par.exchange_row_halo(x, 2, 0, dim=3), packed, rows // 2, stride=2, row_offset=2)
+        sums = self._band_sums(sums, y.shape[3], full_rows)
+        if not want_s3:
+            return None, ops.gn_apply(y, sums, gn.weight, gn.bias, res_nchw, relu, out=y)
+        return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, False, res_nchw=res_nchw, relu=relu, want_s3=True,
+                                want_nchw=want_nchw)
+
+    def _hourglass_band_tc3(self, hg, x, presqu, postsqu, resid, rows, out_nchw):
+        t, _ = self._ffma3_band(hg.conv1[0], x, rows // 2, 2, relu=True, want_s3=True, want_nchw=False)
+        _, pre = self._tc_band(hg.conv2, t, rows // 2, res_nchw=postsqu, relu=True, want_s3=False, want_nchw=True)
+        t, _ = self._ffma3_band(hg.conv3[0], pre, rows // 4, 2, relu=True, want_s3=True, want_nchw=False)
+        _, t = self._tc_band(hg.conv4[0], t, rows // 4, relu=True, want_s3=False, want_nchw=True)
+        _, post = self._ffma3_band(hg.conv5, t, rows // 2, res_nchw=presqu if presqu is not None else pre, relu=True)
+        o_s3, o = self._ffma3_band(hg.conv6, post, rows, res_nchw=resid, relu=False, want_s3=True, want_nchw=out_nchw)
+        return o_s3, o, pre, post
+
+    def _classify_band_tc3(self, head, x_s3, rows):
+        _, t = self._tc_band(head[0], x_s3, rows, relu=True, want_s3=False, want_nchw=True)
+        ext = par.exchange_row_halo(t, 1, 1, dim=3)
+        y, _ = ops.conv3d_k3_rows(ext, self._pack(head[2]), t.shape[3], stride=1, row_offset=1, want_stats=False)
+        return y[:, 0]
+
+    def _aggregate_band_tc3(self, lband, rband, D, h):
+        cost = ops.cost_volume_concat_c8s3(lband, rband, D)
+        t, _ = self._tc_band(self.dres0[0], cost, h, relu=True)
+        del cost
+        c0_s3, c0 = self._tc_band(self.dres0[2], t, h, relu=True, want_nchw=True)
+        t, _ = self._tc_band(self.dres1[0], c0_s3, h, relu=True)
+        del c0_s3
+        _, cost0 = self._tc_band(self.dres1[2], t, h, res_nchw=c0, want_s3=False, want_nchw=True)
+        del t, c0
+        o1_s3, out1, pre1, post1 = self._hourglass_band_tc3(self.dres2, cost0, None, None, cost0, h, True)
+        c1 = self._classify_band_tc3(self.classif1, o1_s3, h)
+        o2_s3, out2, _pre2, post2 = self._hourglass_band_tc3(self.dres3, out1, pre1, post1, cost0, h, True)
+        c2 = self._classify_band_tc3(self.classif2, o2_s3, h)
+        o3_s3, _o3, _pre3, _post3 = self._hourglass_band_tc3(self.dres4, out2, pre1, post2, cost0, h, False)
+        return c1, c2, self._classify_band_tc3(self.classif3, o3_s3, h)
+
     @torch.no_grad()
     def forward_row_bands(self, left, right, gather=True):
         """Sharded inference of ONE pair over all ranks (every rank passes the same images).  Returns the three
@@ -580,30 +687,33 @@ class cmfsm(nn.Module):
         if h % (64 * n) == 0:
             # bands are multiples of 64 rows: the 2-D extractor and K5 are sharded too
             r0, r1 = par.band_rows(h, n, r, multiple=64)
-            feat, full = self._features_band(both, r0, r1)
+            feat, full = (self._features_band_tc3 if self.conv_engine == "tc3" else self._features_band)(both, r0, r1)
             lband, rband = feat[:B].contiguous(), feat[B:].contiguous()
             lr_ext = par.exchange_row_halo(lband, 1, 1, dim=2)
             hr_ext = par.exchange_row_halo(full[:B].contiguous(), scale, scale, dim=2)
             valid = (1 if r0 == 0 else 0, lr_ext.shape[2] - (1 if r1 == h else 0))
             wband = ops.ctxmap_weights(lr_ext, hr_ext, *mlp, valid_rows=valid)  # rows of cells r0-1 .. r1
         else:
-            feat, full = self._features(both)  # replicated on every rank
+            feat, full = (self._features_tc3 if self.conv_engine == "tc3" else self._features)(both)  # replicated
             r0, r1 = par.band_rows(h, n, r, multiple=16)
             lband, rband = feat[:B, :, r0:r1].contiguous(), feat[B:, :, r0:r1].contiguous()
             weights9 = ops.ctxmap_weights(feat[:B], full[:B].contiguous(), *mlp)
             # weight rows outside the image are zero (those neighbours contribute nothing)
             wband = F.pad(weights9, (0, 0, scale, scale))[:, :, scale * r0:scale * (r1 + 2)].contiguous()
-        cost = ops.cost_volume_concat(lband, rband, D)
-        cost0 = self._cg_band(self.dres0[0], cost, h, relu=True)
-        del cost
-        cost0 = self._cg_band(self.dres0[2], cost0, h, relu=True)
-        t = self._cg_band(self.dres1[0], cost0, h, relu=True)
-        cost0 = self._cg_band(self.dres1[2], t, h, residual=cost0)
-        out1, pre1, post1 = self._hourglass_band(self.dres2, cost0, None, None, cost0, h)
-        out2, _p2, post2 = self._hourglass_band(self.dres3, out1, pre1, post1, cost0, h)
-        out3, _p3, _q3 = self._hourglass_band(self.dres4, out2, pre1, post2, cost0, h)
-        cs = [par.exchange_row_halo(self._classify_band(getattr(self, "classif%d" % i), o, h), 1, 1, dim=2)
-              for i, o in ((1, out1), (2, out2), (3, out3))]
+        if self.conv_engine == "tc3":
+            cs = [par.exchange_row_halo(c, 1, 1, dim=2) for c in self._aggregate_band_tc3(lband, rband, D, h)]
+        else:
+            cost = ops.cost_volume_concat(lband, rband, D)
+            cost0 = self._cg_band(self.dres0[0], cost, h, relu=True)
+            del cost
+            cost0 = self._cg_band(self.dres0[2], cost0, h, relu=True)
+            t = self._cg_band(self.dres1[0], cost0, h, relu=True)
+            cost0 = self._cg_band(self.dres1[2], t, h, residual=cost0)
+            out1, pre1, post1 = self._hourglass_band(self.dres2, cost0, None, None, cost0, h)
+            out2, _p2, post2 = self._hourglass_band(self.dres3, out1, pre1, post1, cost0, h)
+            out3, _p3, _q3 = self._hourglass_band(self.dres4, out2, pre1, post2, cost0, h)
+            cs = [par.exchange_row_halo(self._classify_band(getattr(self, "classif%d" % i), o, h), 1, 1, dim=2)
+                  for i, o in ((1, out1), (2, out2), (3, out3))]
         outs = ops.softargmin_ctxmap(cs[0], cs[1], cs[2], wband, scale)  # K4 on the band + 1-cell halo
         outs = [o[:, :, scale:-scale].contiguous() for o in outs]
         return tuple(par.gather_bands(o, dim=2) for o in outs) if gather else tuple(outs)
@@ -664,6 +774,7 @@ class cmfsm(nn.Module):
         left, right = left.float(), right.float()
         both = torch.cat([left, right], 0)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.feature_extraction.parameters()):
+            aops.ENGINE = self.conv_engine  # stride-1 convs of forward and dgrad: tensor cores or FFMA
             feat, full = self._features_train(both.contiguous())
         elif self.conv_engine == "tc3":
             feat, full = self._features_tc3(both.contiguous())

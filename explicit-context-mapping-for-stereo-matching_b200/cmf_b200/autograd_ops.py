@@ -14,11 +14,16 @@ FORWARD always runs the libcmfb200 kernels (2-D extractor included).  BACKWARD: 
     reference.
 None of this is reachable on CPU tensors (the forward kernels raise first).
 """
+import os
+
 import torch
 import torch.nn.functional as F
 from torch.autograd import Function
 
 from . import ops
+
+# "tc3": stride-1 convs of forward and dgrad on the tensor cores (fp32-accurate three-term split), "ffma": CUDA cores
+ENGINE = os.environ.get("CMF_B200_CONV", "tc3")
 
 _NEIGHBOURS = ((0, 0), (0, -1), (0, 1), (-1, 0), (1, 0), (-1, -1), (-1, 1), (1, -1), (1, 1))
 
@@ -43,8 +48,10 @@ class _ConvGN3d(Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, stride, transposed, relu):
         x = x.contiguous()
-        packed = ops.pack_conv3d_weight(weight, transposed)
-        raw, sums = ops.conv3d_k3(x, packed, stride, transposed, want_stats=True)
+        if stride == 1 and not transposed:
+            raw, sums = ops.conv_s1_nchw(x, weight, 1, True, ENGINE)
+        else:
+            raw, sums = ops.conv3d_k3(x, ops.pack_conv3d_weight(weight, transposed), stride, transposed, want_stats=True)
         res = residual.contiguous() if residual is not None else None
         out = ops.gn_apply(raw, sums, gamma, beta, res, relu)
         ctx.cfg = (stride, transposed, relu, residual is not None)
@@ -56,7 +63,7 @@ class _ConvGN3d(Function):
         stride, transposed, relu, has_res = ctx.cfg
         x, weight, gamma, raw, sums, out = ctx.saved_tensors
         d_raw, d_gamma, d_beta, d_res = ops.gn_backward(g, raw, sums, gamma, out if relu else None, has_res)
-        dx = ops.conv3d_dgrad(d_raw, weight, stride, transposed) if ctx.needs_input_grad[0] else None
+        dx = ops.conv3d_dgrad(d_raw, weight, stride, transposed, ENGINE) if ctx.needs_input_grad[0] else None
         if transposed:  # roles swapped: see cmfb200_conv_wgrad
             dw = ops.conv_wgrad(d_raw, x, 3, 2)
         else:
@@ -81,7 +88,7 @@ class _ConvPlain3d(Function):
         x, weight = ctx.saved_tensors
         if weight.shape[0] == 1 and weight.shape[1] == 32:  # classifier tail: own kernels
             return ops.conv3d_cout1_backward(x, weight, g)
-        return ops.conv3d_dgrad(g, weight, 1), ops.conv_wgrad(x, g, 3, 1)
+        return ops.conv3d_dgrad(g, weight, 1, False, ENGINE), ops.conv_wgrad(x, g, 3, 1)
 
 
 def conv3d_plain(x, weight):
@@ -95,7 +102,10 @@ class _ConvGN2d(Function):
     def forward(ctx, x, weight, gamma, beta, residual, stride, dilation, relu):
         x = x.contiguous()
         k = weight.shape[-1]
-        raw, sums = ops.conv2d(x, ops.pack_conv2d_weight(weight), k, stride, dilation, want_stats=True)
+        if stride == 1:
+            raw, sums = ops.conv_s1_nchw(x, weight, dilation, True, ENGINE)
+        else:
+            raw, sums = ops.conv2d(x, ops.pack_conv2d_weight(weight), k, stride, dilation, want_stats=True)
         res = residual.contiguous() if residual is not None else None
         out = ops.gn_apply(raw, sums, gamma, beta, res, relu)
         ctx.cfg = (k, stride, dilation, relu, residual is not None)
@@ -107,7 +117,7 @@ class _ConvGN2d(Function):
         k, stride, dilation, relu, has_res = ctx.cfg
         x, weight, gamma, raw, sums, out = ctx.saved_tensors
         d_raw, d_gamma, d_beta, d_res = ops.gn_backward(g, raw, sums, gamma, out if relu else None, has_res)
-        dx = ops.conv2d_dgrad(d_raw, weight, x.shape, stride, dilation) if ctx.needs_input_grad[0] else None
+        dx = ops.conv2d_dgrad(d_raw, weight, x.shape, stride, dilation, ENGINE) if ctx.needs_input_grad[0] else None
         dw = ops.conv_wgrad(x, d_raw, k, stride, dilation)
         return dx, dw, d_gamma, d_beta, d_res, None, None, None
 
@@ -120,15 +130,14 @@ class _ConvPlain2d(Function):
     @staticmethod
     def forward(ctx, x, weight):
         x = x.contiguous()
-        k = weight.shape[-1]
-        y, _ = ops.conv2d(x, ops.pack_conv2d_weight(weight), k, 1, 1, False)
+        y, _ = ops.conv_s1_nchw(x, weight, 1, False, ENGINE)
         ctx.save_for_backward(x, weight)
         return y
 
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        return ops.conv2d_dgrad(g, weight, x.shape, 1, 1), ops.conv_wgrad(x, g.contiguous(), weight.shape[-1], 1, 1)
+        return ops.conv2d_dgrad(g, weight, x.shape, 1, 1, ENGINE), ops.conv_wgrad(x, g.contiguous(), weight.shape[-1], 1, 1)
 
 
 def conv2d_plain(x, weight):

@@ -65,6 +65,7 @@ SIGNATURES = {
     "cmfb200_conv_wgrad": [_P, _P, _P] + [_I] * 10 + [_P],
     "cmfb200_pack_tc3_weight": [_P, _P, _I, _I, _I, _I, _P],
     "cmfb200_conv_tc3_fwd": [_P, _P, _P, _P] + [_I] * 10 + [_P],
+    "cmfb200_conv_tc3_rows_fwd": [_P, _P, _P, _P] + [_I] * 12 + [_P],
     "cmfb200_gn_apply_tc3": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _F, _I, _P],
 }
 _RESTYPES = {"cmfb200_last_error": _c.c_char_p, "cmfb200_launch_count": _c.c_ulonglong}

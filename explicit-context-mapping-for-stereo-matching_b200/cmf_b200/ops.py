@@ -294,6 +294,26 @@ def conv2d_rows(x, packed, ksize, out_rows, stride=1, dilation=1, row_offset=0, 
     return y, sums
 
 
+_TC3_SHAPES = {(3, 1): (32, 64, 128), (3, 2): (128,), (1, 1): (32, 128)}  # (k, dilation) -> Cout of conv_tc3
+
+
+def tc3_supported(cin, cout, ksize, dilation):
+    return cin % 16 == 0 and cout in _TC3_SHAPES.get((ksize, dilation if ksize == 3 else 1), ())
+
+
+def conv_s1_nchw(x, weight, dilation=1, want_stats=False, engine="tc3"):
+    """Stride-1 'same' conv of an NCHW / NCDHW fp32 tensor with an nn.Conv2d / nn.Conv3d weight, result NCHW fp32
+    (+ GroupNorm sums): on the tensor cores (three-term split, conv_tc3) when the shape is one it has, else FFMA.
+    The training path uses this for forward and dgrad; activations stay plain fp32 tensors in the autograd graph."""
+    weight = weight.detach()
+    cout, cin, k = weight.shape[0], weight.shape[1], weight.shape[-1]
+    if engine == "tc3" and tc3_supported(cin, cout, k, dilation):
+        return conv_tc3(f32_to_c8s3(x.contiguous()), pack_tc3_weight(weight.contiguous()), dilation, want_stats, out_nchw=True)
+    if x.dim() == 5:
+        return conv3d_k3(x.contiguous(), pack_conv3d_weight(weight.contiguous()), 1, want_stats=want_stats)
+    return conv2d(x.contiguous(), pack_conv2d_weight(weight.contiguous()), k, 1, dilation, want_stats)
+
+
 def conv_wgrad(x, dy, ksize, stride=1, dilation=1):
     """Weight gradient of a 2-D ([B,C,H,W]) or 3-D ([B,C,D,H,W], 3x3x3) convolution with 'same' padding:
     returns dW [Cout, Cin, (3,) k, k].  For a transposed conv pass (x := grad of its output, dy := its input, stride 2)."""
@@ -314,27 +334,27 @@ def conv_wgrad(x, dy, ksize, stride=1, dilation=1):
     return dw
 
 
-def conv3d_dgrad(dy, weight, stride=1, transposed=False):
+def conv3d_dgrad(dy, weight, stride=1, transposed=False, engine="tc3"):
     """Input gradient of the 3x3x3 conv / transposed conv layers, on the forward kernels with re-arranged weights:
-    stride 1 -> the same conv with flipped taps and swapped channel roles; stride 2 -> the transposed conv kernel;
-    transposed -> the stride-2 conv kernel."""
+    stride 1 -> the same conv with flipped taps and swapped channel roles (tensor cores when `engine` is tc3);
+    stride 2 -> the transposed conv kernel; transposed -> the stride-2 conv kernel."""
     weight = weight.detach()
     if transposed:  # dx = conv3d(dy, Wt, stride 2, pad 1): Wt [Cin_t, Cout_t] is already [out, in] of that conv
         return conv3d_k3(dy.contiguous(), pack_conv3d_weight(weight.contiguous()), 2)[0]
     if stride == 2:  # dx = conv_transpose3d(dy, W, s2, p1, op1): W [Cout, Cin] is its [in, out] layout
         return conv3d_k3(dy.contiguous(), pack_conv3d_weight(weight.contiguous(), transposed=True), transposed=True)[0]
     wd = weight.transpose(0, 1).flip(2, 3, 4).contiguous()
-    return conv3d_k3(dy.contiguous(), pack_conv3d_weight(wd), 1)[0]
+    return conv_s1_nchw(dy, wd, 1, False, engine)[0]
 
 
-def conv2d_dgrad(dy, weight, x_shape, stride=1, dilation=1):
+def conv2d_dgrad(dy, weight, x_shape, stride=1, dilation=1, engine="tc3"):
     """Input gradient of the 2-D conv layers (3x3 / 1x1, stride 1 with any dilation, stride 2) on the forward kernels."""
     weight = weight.detach()
     k = weight.shape[-1]
     dy = dy.contiguous()
     if stride == 1:
         wd = weight.transpose(0, 1).flip(2, 3).contiguous()
-        return conv2d(dy, pack_conv2d_weight(wd), k, 1, dilation)[0]
+        return conv_s1_nchw(dy, wd, dilation, False, engine)[0]
     if k == 1:  # 1x1 stride 2: the gradient lands on the even pixels
         t = conv2d(dy, pack_conv2d_weight(weight.transpose(0, 1).contiguous()), 1, 1, 1)[0]
         dx = torch.zeros(x_shape, device=dy.device, dtype=torch.float32)
@@ -658,9 +678,10 @@ def pack_tc3_weight(weight):
     return packed
 
 
-def conv_tc3(x_s3, packed, dilation=1, want_stats=True, out_nchw=False):
+def conv_tc3(x_s3, packed, dilation=1, want_stats=True, out_nchw=False, row_off=0, out_rows=None):
     """Stride-1 'same' conv (2-D or 3-D by the rank of x_s3) on the split-bf16 tensor-core path.
-    Returns (raw fp32 y in C8F -- or NCHW/NCDHW when out_nchw --, gn_sums or None)."""
+    Returns (raw fp32 y in C8F -- or NCHW/NCDHW when out_nchw --, gn_sums or None).
+    Row bands: `x_s3` carries halo rows; `out_rows` rows are produced, output row h centred on input row h + row_off."""
     _req(x_s3, packed, dtype=BF16)
     three_d = x_s3.dim() == 7
     B, NC = x_s3.shape[:2]
@@ -671,11 +692,13 @@ def conv_tc3(x_s3, packed, dilation=1, want_stats=True, out_nchw=False):
     KD = KS // (Cin // 16)
     if x_s3.shape[2] != 3 or KS != KD * (Cin // 16) or KD != (3 if three_d else 1):
         raise ValueError("conv_tc3: input %s does not match packed weight %s" % (tuple(x_s3.shape), tuple(packed.shape)))
-    y = torch.empty(((B, Cout) + sp) if out_nchw else ((B, Cout // 8) + sp + (8,)), device=x_s3.device, dtype=torch.float32)
+    Ho = H if out_rows is None else out_rows
+    osp = sp[:-2] + (Ho, W)
+    y = torch.empty(((B, Cout) + osp) if out_nchw else ((B, Cout // 8) + osp + (8,)), device=x_s3.device, dtype=torch.float32)
     sums = _new_sums(B, Cout, x_s3.device) if want_stats else None
     with torch.cuda.device(x_s3.device), _timed("conv_tc3_fwd"):
-        _lib.check(_lib.load().cmfb200_conv_tc3_fwd(_p(x_s3), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W, KD, k,
-                                                    dilation, int(out_nchw), _stream()), "conv_tc3_fwd")
+        _lib.check(_lib.load().cmfb200_conv_tc3_rows_fwd(_p(x_s3), _p(packed), _p(y), _p(sums), B, Cin, Cout, D, H, W, KD, k,
+                                                         dilation, int(out_nchw), row_off, Ho, _stream()), "conv_tc3_fwd")
     return y, sums
 
 

@@ -66,28 +66,14 @@ __host__ __device__ constexpr uint32_t tc3_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-// transposing warp reduction in double: lane l ends with the sum over the 32 lanes of v[l]
-__device__ __forceinline__ double warp_transpose_sum32(double (&v)[32], int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const double give = upper ? v[i] : v[i + off];
-            const double keep = upper ? v[i + off] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, give, off);
-        }
-    }
-    return v[0];
-}
-
 }  // namespace
 
-template <int COUT, int T, int DIL, int KHW, bool STACK, int NA, int NB, bool OUT_NCHW>
-__global__ void __launch_bounds__(kIgThreads, 1)
+template <int COUT, int T, int DIL, int KHW, bool STACK, int NA, int NB, bool OUT_NCHW, int MINB>
+__global__ void __launch_bounds__(kIgThreads, MINB)
     conv_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ wpk,
                     float* __restrict__ y, double* __restrict__ gn_sums, int D, int H, int W, int groups_w, int KD,
-                    int KC) {
+                    int KC, int row_off) {
+    // H = OUTPUT rows; the input may carry extra (halo) rows: output row h reads input rows h + row_off - halo ..
     using G = Tc3Cfg<COUT, T, DIL, KHW, STACK, NA, NB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -142,7 +128,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
 #pragma unroll
                 for (int t = 0; t < T; ++t)
                     tma_load_5d(sA + sa * G::A_STAGE + t * G::A_TILE, &tmap_x, fullA + sa,
-                                ((tx0 + t) * 8 - G::HALO) * 8, ty * 16 - G::HALO, dz, kc * 6, b);
+                                ((tx0 + t) * 8 - G::HALO) * 8, ty * 16 + row_off - G::HALO, dz, kc * 6, b);
                 for (int kh = 0; kh < KHW; ++kh) {
                     const int gb = ks * KHW + kh, sb = gb % NB;
                     if (gb >= NB) mbar_wait(emptyB + sb, ((gb / NB) - 1) & 1);
@@ -260,13 +246,18 @@ __global__ void __launch_bounds__(kIgThreads, 1)
                     }
                 }
                 if (gn_sums != nullptr) {
-                    double dv[32];
+                    // 32-position partials in fp32 (relative rounding ~3e-7 of a 32-term partial, random in sign),
+                    // accumulated in double across tiles / CTAs: the statistics of the >= 1e4 values per channel these
+                    // layers have keep ~1e-8 relative accuracy (the tiny SPP-branch GroupNorms, where partials in fp32
+                    // were measured to hurt, run on the FFMA kernels with double-from-the-first-element sums)
+                    float q[32];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) dv[c] = ok ? (double)o[c] : 0.0;
-                    tot_s[cb] += warp_transpose_sum32(dv, lane);
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) dv[c] = ok ? (double)o[c] * (double)o[c] : 0.0;
-                    tot_q[cb] += warp_transpose_sum32(dv, lane);
+                    for (int c = 0; c < 32; ++c) {
+                        o[c] = ok ? o[c] : 0.f;
+                        q[c] = o[c] * o[c];
+                    }
+                    tot_s[cb] += (double)warp_transpose_sum32(o, lane);
+                    tot_q[cb] += (double)warp_transpose_sum32(q, lane);
                 }
             }
         }
@@ -478,40 +469,43 @@ __global__ void __launch_bounds__(256) cost_volume_c8s3_kernel(const float* __re
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------
-template <int COUT, int T, int DIL, int KHW, bool STACK, int NA, int NB, bool OUT_NCHW>
-static int launch_tc3(const void* x, const void* wpk, float* y, double* gn, int B, int Cin, int D, int H, int W, int KD,
-                      cudaStream_t st) {
+template <int COUT, int T, int DIL, int KHW, bool STACK, int NA, int NB, bool OUT_NCHW, int MINB = 1>
+static int launch_tc3(const void* x, const void* wpk, float* y, double* gn, int B, int Cin, int D, int H_in, int W, int KD,
+                      int row_off, int H, cudaStream_t st) {
     using G = Tc3Cfg<COUT, T, DIL, KHW, STACK, NA, NB>;
     CUtensorMap tmap;
     const cuuint64_t NJ = (cuuint64_t)3 * (Cin / 8);
-    const cuuint64_t gdim[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, NJ, (cuuint64_t)B};
-    const cuuint64_t gstr[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
-                                NJ * D * H * W * 16};
+    const cuuint64_t gdim[5] = {(cuuint64_t)W * 8, (cuuint64_t)H_in, (cuuint64_t)D, NJ, (cuuint64_t)B};
+    const cuuint64_t gstr[4] = {(cuuint64_t)W * 16, (cuuint64_t)H_in * W * 16, (cuuint64_t)D * H_in * W * 16,
+                                NJ * D * H_in * W * 16};
     const cuuint32_t box[5] = {(cuuint32_t)G::PW * 8, (cuuint32_t)G::PH, 1, 6, 1};
     if (int rc = encode_tmap_5d(&tmap, x, gdim, gstr, box, "conv_tc3")) return rc;
-    auto kern = conv_tc3_kernel<COUT, T, DIL, KHW, STACK, NA, NB, OUT_NCHW>;
+    static_assert(MINB == 1 || (MINB * G::SMEM_BYTES <= 227 * 1024 && MINB * G::TMEM_COLS <= 512), "co-residency");
+    auto kern = conv_tc3_kernel<COUT, T, DIL, KHW, STACK, NA, NB, OUT_NCHW, MINB>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
     const int tiles_w = (int)cdiv(W, 8), tiles_h = (int)cdiv(H, 16), groups_w = (int)cdiv(tiles_w, T);
     dim3 grid((unsigned)(groups_w * tiles_h), (unsigned)D, (unsigned)B);
     CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv_tc3: grid too large");
     kern<<<grid, kIgThreads, G::SMEM_BYTES, st>>>(tmap, reinterpret_cast<const __nv_bfloat16*>(wpk), y, gn, D, H, W,
-                                                  groups_w, KD, Cin / 16);
+                                                  groups_w, KD, Cin / 16, row_off);
     CMF_LAUNCH_CHECK("conv_tc3_kernel");
     return CMFB200_OK;
 }
 
 template <bool OUT_NCHW>
 static int dispatch_tc3(const void* x, const void* wpk, float* y, double* gn, int B, int Cin, int Cout, int D, int H, int W,
-                        int KD, int KHW, int dil, cudaStream_t st) {
+                        int KD, int KHW, int dil, int row_off, int H_out, cudaStream_t st) {
     if (KHW == 3 && dil == 1) {
-        if (Cout == 32) return launch_tc3<32, 4, 1, 3, true, 2, 4, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, st);
-        if (Cout == 64) return launch_tc3<64, 2, 1, 3, true, 2, 4, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, st);
-        if (Cout == 128) return launch_tc3<128, 2, 1, 3, false, 2, 3, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, st);
+        // 32 output channels: 2 tiles per CTA and TWO co-resident CTAs per SM (108 KB, 256 TMEM columns each): the
+        // prologue / epilogue of one overlaps the MMA phase of the other (K is only 2-12 steps deep in these layers)
+        if (Cout == 32) return launch_tc3<32, 2, 1, 3, true, 2, 4, OUT_NCHW, 2>(x, wpk, y, gn, B, Cin, D, H, W, KD, row_off, H_out, st);
+        if (Cout == 64) return launch_tc3<64, 2, 1, 3, true, 2, 4, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, row_off, H_out, st);
+        if (Cout == 128) return launch_tc3<128, 2, 1, 3, false, 2, 3, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, row_off, H_out, st);
     } else if (KHW == 3 && dil == 2) {
-        if (Cout == 128) return launch_tc3<128, 2, 2, 3, false, 2, 3, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, st);
+        if (Cout == 128) return launch_tc3<128, 2, 2, 3, false, 2, 3, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, row_off, H_out, st);
     } else if (KHW == 1) {
-        if (Cout == 32) return launch_tc3<32, 4, 1, 1, true, 3, 3, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, st);
-        if (Cout == 128) return launch_tc3<128, 2, 1, 1, false, 3, 3, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, st);
+        if (Cout == 32) return launch_tc3<32, 4, 1, 1, true, 3, 3, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, row_off, H_out, st);
+        if (Cout == 128) return launch_tc3<128, 2, 1, 1, false, 3, 3, OUT_NCHW>(x, wpk, y, gn, B, Cin, D, H, W, KD, row_off, H_out, st);
     }
     CMF_REQUIRE(false, "conv_tc3_fwd: unsupported (Cout=%d, k=%d, dilation=%d); supported: 3x3 d1 Cout 32/64/128, "
                        "3x3 d2 Cout 128, 1x1 Cout 32/128", Cout, KHW, dil);
@@ -533,17 +527,27 @@ extern "C" int cmfb200_pack_tc3_weight(const float* weight, void* packed, int Co
     return CMFB200_OK;
 }
 
-extern "C" int cmfb200_conv_tc3_fwd(const void* x_c8s3, const void* packed_w, float* y, double* gn_sums, int B, int Cin,
-                                    int Cout, int D, int H, int W, int KD, int KHW, int dilation, int out_nchw,
-                                    void* stream) {
+extern "C" int cmfb200_conv_tc3_rows_fwd(const void* x_c8s3, const void* packed_w, float* y, double* gn_sums, int B,
+                                         int Cin, int Cout, int D, int H, int W, int KD, int KHW, int dilation,
+                                         int out_nchw, int row_off, int H_out, void* stream) {
     CMF_REQUIRE(x_c8s3 && packed_w && y, "conv_tc3_fwd: null pointer");
-    CMF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv_tc3_fwd: non-positive dimension");
+    CMF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && H_out > 0, "conv_tc3_fwd: non-positive dimension");
+    CMF_REQUIRE(row_off >= 0 && row_off + H_out <= H + 64, "conv_tc3_rows_fwd: row window [%d, %d) outside the input (%d rows)",
+                row_off, row_off + H_out, H);
     CMF_REQUIRE(Cin > 0 && Cin % 16 == 0, "conv_tc3_fwd: Cin=%d must be a multiple of 16", Cin);
     CMF_REQUIRE((KD == 1 || KD == 3), "conv_tc3_fwd: KD must be 1 or 3");
     CMF_REQUIRE((reinterpret_cast<uintptr_t>(x_c8s3) & 15) == 0, "conv_tc3_fwd: input must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_nchw) return dispatch_tc3<true>(x_c8s3, packed_w, y, gn_sums, B, Cin, Cout, D, H, W, KD, KHW, dilation, st);
-    return dispatch_tc3<false>(x_c8s3, packed_w, y, gn_sums, B, Cin, Cout, D, H, W, KD, KHW, dilation, st);
+    if (out_nchw)
+        return dispatch_tc3<true>(x_c8s3, packed_w, y, gn_sums, B, Cin, Cout, D, H, W, KD, KHW, dilation, row_off, H_out, st);
+    return dispatch_tc3<false>(x_c8s3, packed_w, y, gn_sums, B, Cin, Cout, D, H, W, KD, KHW, dilation, row_off, H_out, st);
+}
+
+extern "C" int cmfb200_conv_tc3_fwd(const void* x_c8s3, const void* packed_w, float* y, double* gn_sums, int B, int Cin,
+                                    int Cout, int D, int H, int W, int KD, int KHW, int dilation, int out_nchw,
+                                    void* stream) {
+    return cmfb200_conv_tc3_rows_fwd(x_c8s3, packed_w, y, gn_sums, B, Cin, Cout, D, H, W, KD, KHW, dilation, out_nchw, 0, H,
+                                     stream);
 }
 
 extern "C" int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma,

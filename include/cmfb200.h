@@ -255,6 +255,12 @@ int cmfb200_pack_tc3_weight(const float* weight, void* packed, int Cout, int Cin
  * must be zero on entry.  Supported: 3x3 d1 Cout 32/64/128, 3x3 d2 Cout 128, 1x1 Cout 32/128. */
 int cmfb200_conv_tc3_fwd(const void* x_c8s3, const void* packed_w, float* y, double* gn_sums, int B, int Cin, int Cout,
                          int D, int H, int W, int KD, int KHW, int dilation, int out_nchw, void* stream);
+/* Row-window form for row-band sharding: the input has H rows (the band plus halo rows received from the neighbour
+ * ranks, zeros at the image border); only H_out rows are produced -- output row h is centred on input row h + row_off --
+ * and only they enter gn_sums, so the epilogue's statistics are the band's statistics. */
+int cmfb200_conv_tc3_rows_fwd(const void* x_c8s3, const void* packed_w, float* y, double* gn_sums, int B, int Cin, int Cout,
+                              int D, int H, int W, int KD, int KHW, int dilation, int out_nchw, int row_off, int H_out,
+                              void* stream);
 /* y = GroupNorm(raw) (+residual) (ReLU) (nn.GroupNorm + the adds / ReLUs of convbn, BasicBlock, hourglass):
  * raw is C8F (raw_is_c8f) or [B][C][spatial] fp32; residual as C8S3 and/or [B][C][spatial] fp32 (either may be NULL);
  * the result is written split into three bf16 terms (y_c8s3) and/or as [B][C][spatial] fp32 (y_nchw).

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--width", type=int, default=512)
     ap.add_argument("--maxdisp", type=int, default=192)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--profile", action="store_true")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -52,6 +53,21 @@ def main():
         dist.all_gather(gathered, ms)
         per_rank = [float(t) for t in gathered]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if args.profile:  # where does a band forward spend its time?  (our kernels by event pairs vs the elapsed time)
+        from cmf_b200 import ops
+        ops.enable_event_timing(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        model.forward_row_bands(left, right)
+        p1.record()
+        kern = ops.drain_event_timing()
+        ops.enable_event_timing(False)
+        if rank == 0:
+            tot = sum(ms for _, ms in kern.values())
+            print("band forward with events: %.2f ms elapsed, %.2f ms inside libcmfb200 kernels (%d launches); rest = NCCL, "
+                  "torch.cat / contiguous copies, idle" % (p0.elapsed_time(p1), tot, sum(n for n, _ in kern.values())))
+            for k, (n, ms) in sorted(kern.items(), key=lambda kv: -kv[1][1])[:8]:
+                print("   %-28s %4d %.2f ms" % (k, n, ms))
     if rank == 0:
         with torch.no_grad():
             ref = model(left, right)
