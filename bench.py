@@ -457,14 +457,18 @@ def run_ours(args, rank, world, local_rank):
             return {k: {"launches": n // K, "ms_per_step": ms / K, "share": ms / leg["ms_eager"]}
                     for k, (n, ms) in sorted(leg["kernels"].items())}
 
-        # ---- dominant kernel of the fp32 step: conv_tc3 (every stride-1 conv, 2-D and 3-D)
-        tc_n, tc_ms = kern(f, "conv_tc3_fwd")
-        tc_macs = macs["tc3_2d"] + macs["tc3_3d"]
+        # ---- dominant kernels of the fp32 step: the tensor-core convs (stride-1 2-D / 3-D, stride-2, transposed)
+        tc_n, tc_ms, tc_macs = 0, 0.0, 0
+        for name, m in (("conv_tc3_fwd", macs["tc3_2d"] + macs["tc3_3d"]), ("conv_tc3_s2_fwd", macs["s2_3d"]),
+                        ("deconv_tc3_fwd", macs["deconv_3d"])):
+            n_, ms_ = kern(f, name)
+            if n_:
+                tc_n, tc_ms, tc_macs = tc_n + n_, tc_ms + ms_, tc_macs + m
         roof = None
         if tc_n:
             alg = 2.0 * tc_macs / (tc_ms * 1e-3) / 1e12
-            roof = {"kernel": "conv_tc3_kernel (fp32-accurate stride-1 convs on tcgen05, %d launches/step = %.1f%% of the "
-                              "step)" % (tc_n, 100.0 * tc_ms * K / f["ms_eager"]),
+            roof = {"kernel": "conv_tc3_kernel + conv_tc3g_kernel (fp32-accurate convs on tcgen05: stride-1 2-D/3-D, stride-2, "
+                              "transposed; %d launches/step = %.1f%% of the step)" % (tc_n, 100.0 * tc_ms * K / f["ms_eager"]),
                     "bound": "tensor", "achieved": alg, "peak": tpeak, "unit": "TFLOP/s", "frac": alg / tpeak,
                     "traffic": None, "peak_source": "bf16_tflops_sustained, " + peak_src,
                     "algorithmic_flops_per_step": 2.0 * tc_macs,
@@ -496,9 +500,10 @@ def run_ours(args, rank, world, local_rank):
                             "bytes_per_voxel_written": s_out}
             return None
 
-        precision = ("fp32 parity mode: stride-1 convs (2-D and 3-D) as three-term bf16 splits on tcgen05 with fp32 TMEM "
-                     "accumulation (fp32-accurate, csrc/conv_tc3.cu); stride-2 / transposed / 32->1 / 3->32 convs, K4, K5 "
-                     "fp32 FMA" if args.conv_engine == "tc3" else "fp32 FMA everywhere (CUDA cores)")
+        precision = ("fp32 parity mode: every conv of the 3-D aggregation (stride-1, stride-2, transposed) and every stride-1 "
+                     "conv of the 2-D extractor as three-term bf16 splits on tcgen05 with fp32 TMEM accumulation "
+                     "(fp32-accurate, csrc/conv_tc3*.cu); the 32->1 tails, the 3->32 stem, the three stride-2 2-D convs, "
+                     "K4, K5 fp32 FMA" if args.conv_engine == "tc3" else "fp32 FMA everywhere (CUDA cores)")
         line = {"metric": METRIC, "value": world * K / (f["ms_total"] * 1e-3), "unit": "pairs/s", "n_gpus": world,
                 "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": f["ms_total"] / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -370,31 +370,44 @@ class cmfsm(nn.Module):
         return (self._classify_bf16(self.classif1, out1), self._classify_bf16(self.classif2, out2),
                 self._classify_bf16(self.classif3, out3))
 
-    # ---- fp32 aggregation with the stride-1 3x3x3 convs on the tensor cores (fp32-accurate split-bf16, conv_tc3.cu);
-    # stride-2 / transposed / 32->1 layers stay on the FFMA kernels (NCDHW fp32), GroupNorm apply converts.
+    # ---- fp32 aggregation on the tensor cores (fp32-accurate split-bf16): stride-1 convs (conv_tc3.cu), stride-2 and
+    # transposed convs (conv_tc3_s2.cu); only the 32->1 classifier tails stay on the FFMA kernel (NCDHW fp32).
     def _cg3_tc(self, block, x_s3, res_nchw=None, relu=False, want_s3=True, want_nchw=False):
         conv, gn = block[0], block[1]
         y, sums = ops.conv_tc3(x_s3, self._pack_tc3(conv), 1, True)
         return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, True, res_nchw=res_nchw, relu=relu, want_s3=want_s3,
                                 want_nchw=want_nchw)
 
-    def _cg3_ffma(self, block, x, stride=1, res_nchw=None, relu=False, want_s3=False, want_nchw=True):
-        """FFMA conv / transposed conv on NCDHW fp32 + GroupNorm; result as (C8S3 or None, NCDHW or None)."""
-        conv, gn = block[0], block[1]
-        y, sums = ops.conv3d_k3(x, self._pack(conv), stride, isinstance(conv, nn.ConvTranspose3d), want_stats=True)
-        if not want_s3:
-            return None, ops.gn_apply(y, sums, gn.weight, gn.bias, res_nchw, relu, out=y)
-        return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, False, res_nchw=res_nchw, relu=relu, want_s3=True,
-                                want_nchw=want_nchw)
+    def _pack_tc3_s2(self, conv):
+        return self._cached(conv, "tc3s2", ops.pack_tc3_s2_weight)
 
-    def _hourglass_tc3(self, hg, x, presqu, postsqu, resid, out_s3, out_nchw):
-        t, _ = self._cg3_ffma(hg.conv1[0], x, 2, relu=True, want_s3=True, want_nchw=False)
-        _, pre = self._cg3_tc(hg.conv2, t, res_nchw=postsqu, relu=True, want_s3=False, want_nchw=True)
-        t, _ = self._cg3_ffma(hg.conv3[0], pre, 2, relu=True, want_s3=True, want_nchw=False)
-        _, t = self._cg3_tc(hg.conv4[0], t, relu=True, want_s3=False, want_nchw=True)
-        _, post = self._cg3_ffma(hg.conv5, t, res_nchw=presqu if presqu is not None else pre, relu=True)
-        o_s3, o = self._cg3_ffma(hg.conv6, post, res_nchw=resid, relu=False, want_s3=out_s3, want_nchw=out_nchw)
-        return o_s3, o, pre, post
+    def _pack_tc3_deconv(self, conv):
+        return self._cached(conv, "tc3dc", ops.pack_tc3_deconv_weight)
+
+    def _gn3(self, gn, y, sums, res_nchw=None, relu=False, s3=False, nchw=False, split=False):
+        """GroupNorm (+residual) (+ReLU) of a raw C8F volume -> (C8S3, NCDHW fp32, parity-split C8S3), each or None."""
+        out = ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, True, res_nchw=res_nchw, relu=relu, want_s3=s3, want_nchw=nchw,
+                               want_split=split)
+        return out if split else out + (None,)
+
+    def _hourglass_tc3(self, hg, x_split, presqu, postsqu, resid, next_split):
+        """One hourglass entirely on the tensor cores: stride-2 convs on the parity-split input, stride-1 convs, and the
+        two transposed convs as eight parity-class launches each (conv_tc3_s2.cu).  NCDHW fp32 copies exist only where a
+        tensor is used as a residual.  Returns (out C8S3, out parity-split or None, pre, post)."""
+        y, sums = ops.conv_tc3_s2(x_split, self._pack_tc3_s2(hg.conv1[0][0]))
+        t, _, _ = self._gn3(hg.conv1[0][1], y, sums, relu=True, s3=True)
+        y, sums = ops.conv_tc3(t, self._pack_tc3(hg.conv2[0]), 1, True)
+        _, pre, pre_split = self._gn3(hg.conv2[1], y, sums, res_nchw=postsqu, relu=True, nchw=True, split=True)
+        y, sums = ops.conv_tc3_s2(pre_split, self._pack_tc3_s2(hg.conv3[0][0]))
+        t, _, _ = self._gn3(hg.conv3[0][1], y, sums, relu=True, s3=True)
+        y, sums = ops.conv_tc3(t, self._pack_tc3(hg.conv4[0][0]), 1, True)
+        t, _, _ = self._gn3(hg.conv4[0][1], y, sums, relu=True, s3=True)
+        y, sums = ops.deconv_tc3(t, self._pack_tc3_deconv(hg.conv5[0]), 64)
+        p_s3, post, _ = self._gn3(hg.conv5[1], y, sums, res_nchw=presqu if presqu is not None else pre, relu=True,
+                                  s3=True, nchw=True)
+        y, sums = ops.deconv_tc3(p_s3, self._pack_tc3_deconv(hg.conv6[0]), 32)
+        o_s3, _, o_split = self._gn3(hg.conv6[1], y, sums, res_nchw=resid, s3=True, split=next_split)
+        return o_s3, o_split, pre, post
 
     def _classify_tc3(self, head, x_s3):
         _, t = self._cg3_tc(head[0], x_s3, relu=True, want_s3=False, want_nchw=True)
@@ -408,18 +421,20 @@ class cmfsm(nn.Module):
         c0_s3, c0 = self._cg3_tc(self.dres0[2], t, relu=True, want_nchw=True)
         t, _ = self._cg3_tc(self.dres1[0], c0_s3, relu=True)
         del c0_s3
-        _, cost0 = self._cg3_tc(self.dres1[2], t, res_nchw=c0, want_s3=False, want_nchw=True)
-        del t, c0
+        conv, gn = self.dres1[2][0], self.dres1[2][1]
+        y, sums = ops.conv_tc3(t, self._pack_tc3(conv), 1, True)
+        _, cost0, cost0_split = self._gn3(gn, y, sums, res_nchw=c0, nchw=True, split=True)
+        del t, c0, y
         single = not hasattr(self, "dres3")  # single-hourglass variants (cm_sub_*)
-        o1_s3, out1, pre1, post1 = self._hourglass_tc3(self.dres2, cost0, None, None, cost0, True, not single)
+        o1_s3, o1_split, pre1, post1 = self._hourglass_tc3(self.dres2, cost0_split, None, None, cost0, not single)
         c1 = self._classify_tc3(self.classif1, o1_s3)
         del o1_s3
         if single:
             return (c1,)
-        o2_s3, out2, _pre2, post2 = self._hourglass_tc3(self.dres3, out1, pre1, post1, cost0, True, True)
+        o2_s3, o2_split, _pre2, post2 = self._hourglass_tc3(self.dres3, o1_split, pre1, post1, cost0, True)
         c2 = self._classify_tc3(self.classif2, o2_s3)
-        del o2_s3, out1
-        o3_s3, _o3, _pre3, _post3 = self._hourglass_tc3(self.dres4, out2, pre1, post2, cost0, True, False)
+        del o2_s3, o1_split
+        o3_s3, _, _pre3, _post3 = self._hourglass_tc3(self.dres4, o2_split, pre1, post2, cost0, False)
         return c1, c2, self._classify_tc3(self.classif3, o3_s3)
 
     def _aggregate_fp32(self, lfeat, rfeat, D):
@@ -565,32 +580,39 @@ class cmfsm(nn.Module):
         sums and the element count of THIS tensor) reproduces the statistics of the whole volume."""
         return par.allreduce_gn_sums(sums) * (float(band_rows) / float(full_rows))
 
+    _BAND_PAD = 2  # spare rows above / below every C8S3 band activation (largest halo: dilation 2)
+
     def _tc_band(self, block, x_s3, full_rows, res_s3=None, res_nchw=None, relu=False, want_s3=True, want_nchw=False):
-        """Stride-1 conv (2-D or 3-D) + GroupNorm on a row band: halo rows from the neighbours, row-window conv_tc3."""
+        """Stride-1 conv (2-D or 3-D) + GroupNorm on a row band.  `x_s3` (and `res_s3`, and the C8S3 result) carry
+        _BAND_PAD spare rows on both sides: the halo rows are received straight into them and the row-window conv_tc3
+        reads the padded tensor -- no copy of the activation."""
         conv, gn = block[0], block[1]
+        P = self._BAND_PAD
         d = conv.dilation[0] if conv.kernel_size[-1] == 3 else 0
-        rows, hdim = x_s3.shape[-3], x_s3.dim() - 3
-        ext = par.exchange_row_halo(x_s3, d, d, dim=hdim) if d else x_s3
-        y, sums = ops.conv_tc3(ext, self._pack_tc3(conv), conv.dilation[0], True, row_off=d, out_rows=rows)
+        rows = x_s3.shape[-3] - 2 * P
+        if d:
+            par.fill_row_halo_(x_s3, P, d, d, dim=x_s3.dim() - 3)
+        y, sums = ops.conv_tc3(x_s3, self._pack_tc3(conv), conv.dilation[0], True, row_off=P, out_rows=rows)
         sums = self._band_sums(sums, rows, full_rows)
         return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, True, res_s3=res_s3, res_nchw=res_nchw, relu=relu,
-                                want_s3=want_s3, want_nchw=want_nchw)
+                                want_s3=want_s3, want_nchw=want_nchw, pad=P)
 
     def _ffma2_band_to_s3(self, block, x_nchw, full_rows, relu=False):
         y, sums = self._conv2_band(block[0], x_nchw, True)
         sums = self._band_sums(sums, y.shape[2], full_rows)
-        return ops.gn_apply_tc3(y, sums, block[1].weight, block[1].bias, False, relu=relu)[0]
+        return ops.gn_apply_tc3(y, sums, block[1].weight, block[1].bias, False, relu=relu, pad=self._BAND_PAD)[0]
 
     def _features_band_tc3(self, both, r0, r1):
         fe = self.feature_extraction
+        P = self._BAND_PAD
         H, h = both.shape[2], both.shape[2] // 4
         x = both[:, :, 4 * r0:4 * r1].contiguous()
         o = self._ffma2_band_to_s3(fe.firstconv[0], x, H, relu=True)
         o, _ = self._tc_band(fe.firstconv[2], o, H, relu=True)
         o, _ = self._tc_band(fe.firstconv[4], o, H, relu=True)
-        ext = par.exchange_row_halo(o, 1, 1, dim=o.dim() - 3)
-        full, fsums = ops.conv_tc3(ext, self._pack_tc3(fe.firstconv[6]), 1, True, out_nchw=True, row_off=1,
-                                   out_rows=o.shape[-3])
+        par.fill_row_halo_(o, P, 1, 1, dim=o.dim() - 3)
+        full, fsums = ops.conv_tc3(o, self._pack_tc3(fe.firstconv[6]), 1, True, out_nchw=True, row_off=P,
+                                   out_rows=o.shape[-3] - 2 * P)
         gn0 = fe.secondconv[0]
         o = ops.gn_apply(full, self._band_sums(fsums, full.shape[2], H), gn0.weight, gn0.bias, None, True)
         o = self._ffma2_band_to_s3(fe.secondconv[2], o, H // 2, relu=True)
@@ -614,9 +636,10 @@ class cmfsm(nn.Module):
         skip_nchw = o_nchw
         pooled = [par.gather_bands(p, dim=2) for p in ops.spp_pool(skip_nchw)]  # whole-image pooled maps (tiny)
         b1, b2, b3, b4 = [self._cg2(getattr(fe, "branch%d" % (i + 1))[1], p, relu=True) for i, p in enumerate(pooled)]
-        cat = ops.f32_to_c8s3(ops.spp_upsample_concat(raw_nchw, skip_nchw, b4, b3, b2, b1, full_rows=h, row_offset=r0))
+        cat = ops.f32_to_c8s3(ops.spp_upsample_concat(raw_nchw, skip_nchw, b4, b3, b2, b1, full_rows=h, row_offset=r0), pad=P)
         o, _ = self._tc_band(fe.lastconv[0], cat, h, relu=True)
-        feat, _ = ops.conv_tc3(o, self._pack_tc3(fe.lastconv[2]), 1, False, out_nchw=True)
+        feat, _ = ops.conv_tc3(o, self._pack_tc3(fe.lastconv[2]), 1, False, out_nchw=True, row_off=P,
+                               out_rows=o.shape[-3] - 2 * P)
         return feat, full
 
     def _ffma3_band(self, block, x, full_rows, stride=1, res_nchw=None, relu=False, want_s3=False, want_nchw=True):
@@ -632,7 +655,7 @@ class cmfsm(nn.Module):
         if not want_s3:
             return None, ops.gn_apply(y, sums, gn.weight, gn.bias, res_nchw, relu, out=y)
         return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, False, res_nchw=res_nchw, relu=relu, want_s3=True,
-                                want_nchw=want_nchw)
+                                want_nchw=want_nchw, pad=self._BAND_PAD)
 
     def _hourglass_band_tc3(self, hg, x, presqu, postsqu, resid, rows, out_nchw):
         t, _ = self._ffma3_band(hg.conv1[0], x, rows // 2, 2, relu=True, want_s3=True, want_nchw=False)
@@ -650,7 +673,7 @@ class cmfsm(nn.Module):
         return y[:, 0]
 
     def _aggregate_band_tc3(self, lband, rband, D, h):
-        cost = ops.cost_volume_concat_c8s3(lband, rband, D)
+        cost = ops.cost_volume_concat_c8s3(lband, rband, D, pad=self._BAND_PAD)
         t, _ = self._tc_band(self.dres0[0], cost, h, relu=True)
         del cost
         c0_s3, c0 = self._tc_band(self.dres0[2], t, h, relu=True, want_nchw=True)

@@ -702,10 +702,91 @@ def conv_tc3(x_s3, packed, dilation=1, want_stats=True, out_nchw=False, row_off=
     return y, sums
 
 
+def _split3_torch(w):
+    """Exact three-term bf16 split of an fp32 tensor (the same round-to-nearest steps as the kernels)."""
+    t0 = w.to(BF16)
+    r1 = w - t0.float()
+    t1 = r1.to(BF16)
+    return t0, t1, (r1 - t1.float()).to(BF16)
+
+
+def _pack_tc3_taps(w_oi, steps):
+    """w_oi: fp32 [Cout, Cin, 3, 3, 3] (conv orientation).  steps: list of (kc, [(kd,kh,kw), ...]) in kernel K-step
+    order.  Returns bf16 [sum taps, 2 chunks, 3 terms, Cout, 8] flattened = the B operand stream of conv_tc3g."""
+    Cout = w_oi.shape[0]
+    terms = _split3_torch(w_oi)
+    out = []
+    for kc, taps in steps:
+        for kd, kh, kw in taps:
+            blk = torch.stack([t[:, kc * 16:(kc + 1) * 16, kd, kh, kw] for t in terms])  # [3, Cout, 16]
+            out.append(blk.view(3, Cout, 2, 8).permute(2, 0, 1, 3))  # [2 chunks, 3 terms, Cout, 8]
+    return torch.stack(out).contiguous()
+
+
+def _axis_taps(bit, transposed):
+    """Kernel index k of the taps a parity bit contributes, in the order of csrc/conv_tc3_s2.cu."""
+    if not bit:
+        return [1]
+    return [2, 0] if transposed else [0, 2]
+
+
+def pack_tc3_s2_weight(weight):
+    """nn.Conv3d(k3, s2, p1) weight [Cout,Cin,3,3,3] -> packed operand of `conv_tc3_s2` (K steps: input parity class q,
+    depth tap, 16-channel chunk; 1..4 in-plane taps each)."""
+    w = weight.detach().float()
+    KC = w.shape[1] // 16
+    steps = []
+    for q in range(8):
+        qd, qh, qw = q >> 2, (q >> 1) & 1, q & 1
+        for kd in _axis_taps(qd, False):
+            for kc in range(KC):
+                steps.append((kc, [(kd, kh, kw) for kh in _axis_taps(qh, False) for kw in _axis_taps(qw, False)]))
+    return _pack_tc3_taps(w, steps)
+
+
+def pack_tc3_deconv_weight(weight):
+    """nn.ConvTranspose3d(k3, s2, p1, op1) weight [Cin,Cout,3,3,3] -> packed operand of `deconv_tc3` (eight output parity
+    classes back to back; per class: depth tap, 16-channel chunk; 1..4 in-plane taps each)."""
+    w = weight.detach().float().transpose(0, 1).contiguous()  # [Cout, Cin, 3,3,3]: out[2i-1+k] += W[ci][co][k] in[i]
+    KC = w.shape[1] // 16
+    steps = []
+    for p in range(8):
+        pd, ph, pw = p >> 2, (p >> 1) & 1, p & 1
+        for kd in _axis_taps(pd, True):
+            for kc in range(KC):
+                steps.append((kc, [(kd, kh, kw) for kh in _axis_taps(ph, True) for kw in _axis_taps(pw, True)]))
+    return _pack_tc3_taps(w, steps)
+
+
+def conv_tc3_s2(x_split, packed, Cout=64, want_stats=True):
+    """Stride-2 3x3x3 conv on the tensor cores: parity-split C8S3 [B,8,Cin/8,3,D/2,H/2,W/2,8] -> raw C8F [B,Cout/8,D/2,..,8]."""
+    _req(x_split, packed, dtype=BF16)
+    B, _, NC, _, Do, Ho, Wo, _ = x_split.shape
+    y = torch.empty((B, Cout // 8, Do, Ho, Wo, 8), device=x_split.device, dtype=torch.float32)
+    sums = _new_sums(B, Cout, x_split.device) if want_stats else None
+    with torch.cuda.device(x_split.device), _timed("conv_tc3_s2_fwd"):
+        _lib.check(_lib.load().cmfb200_conv_tc3_s2_fwd(_p(x_split), _p(packed), _p(y), _p(sums), B, NC * 8, Cout, Do, Ho, Wo,
+                                                       _stream()), "conv_tc3_s2_fwd")
+    return y, sums
+
+
+def deconv_tc3(x_s3, packed, Cout, want_stats=True):
+    """Transposed 3x3x3 conv (s2, p1, op1) on the tensor cores: C8S3 [B,Cin/8,3,D,H,W,8] -> raw C8F [B,Cout/8,2D,2H,2W,8]."""
+    _req(x_s3, packed, dtype=BF16)
+    B, NC, _, D, H, W, _ = x_s3.shape
+    y = torch.empty((B, Cout // 8, 2 * D, 2 * H, 2 * W, 8), device=x_s3.device, dtype=torch.float32)
+    sums = _new_sums(B, Cout, x_s3.device) if want_stats else None
+    with torch.cuda.device(x_s3.device), _timed("deconv_tc3_fwd"):
+        _lib.check(_lib.load().cmfb200_deconv_tc3_fwd(_p(x_s3), _p(packed), _p(y), _p(sums), B, NC * 8, Cout, D, H, W,
+                                                      _stream()), "deconv_tc3_fwd")
+    return y, sums
+
+
 def gn_apply_tc3(raw, sums, gamma, beta, raw_c8f, res_s3=None, res_nchw=None, relu=False, want_s3=True, want_nchw=False,
-                 groups=GN_GROUPS, eps=GN_EPS):
+                 groups=GN_GROUPS, eps=GN_EPS, pad=0, want_split=False):
     """GroupNorm (+residual) (+ReLU) of the tc3 pipeline.  raw: C8F (raw_c8f) or NCHW/NCDHW fp32; the result is returned
-    as (C8S3 or None, NCHW fp32 or None).  sums=None: layout conversion / three-term split only."""
+    as (C8S3 or None, NCHW fp32 or None).  sums=None: layout conversion / three-term split only.
+    Row bands: with `pad` the C8S3 result (and `res_s3`) carry `pad` halo rows above and below (left un-written)."""
     _req(raw, res_nchw)
     _req(res_s3, dtype=BF16)
     if sums is not None:
@@ -720,30 +801,39 @@ def gn_apply_tc3(raw, sums, gamma, beta, raw_c8f, res_s3=None, res_nchw=None, re
     spatial = 1
     for v in sp:
         spatial *= v
-    y_s3 = torch.empty((B, C // 8, 3) + sp + (8,), device=raw.device, dtype=BF16) if want_s3 else None
+    psp = sp[:-2] + (sp[-2] + 2 * pad, sp[-1])
+    if res_s3 is not None and tuple(res_s3.shape) != (B, C // 8, 3) + psp + (8,):
+        raise ValueError("gn_apply_tc3: residual %s does not match %s (pad %d)" % (tuple(res_s3.shape), (B, C // 8, 3) + psp, pad))
+    y_s3 = torch.empty((B, C // 8, 3) + psp + (8,), device=raw.device, dtype=BF16) if want_s3 else None
     y_nchw = torch.empty((B, C) + sp, device=raw.device, dtype=torch.float32) if want_nchw else None
+    y_split = (torch.empty((B, 8, C // 8, 3) + tuple(v // 2 for v in sp) + (8,), device=raw.device, dtype=BF16)
+               if want_split else None)
     with torch.cuda.device(raw.device), _timed("gn_apply_tc3"):
-        _lib.check(_lib.load().cmfb200_gn_apply_tc3(_p(raw), int(raw_c8f), _p(sums), _p(gamma) if sums is not None else None,
-                                                    _p(beta) if sums is not None else None, _p(res_s3), _p(res_nchw),
-                                                    _p(y_s3), _p(y_nchw), B, C, groups, spatial, eps, int(relu), _stream()),
-                   "gn_apply_tc3")
+        _lib.check(_lib.load().cmfb200_gn_apply_tc3_padded(_p(raw), int(raw_c8f), _p(sums),
+                                                           _p(gamma) if sums is not None else None,
+                                                           _p(beta) if sums is not None else None, _p(res_s3), _p(res_nchw),
+                                                           _p(y_s3), _p(y_nchw), B, C, groups, spatial, eps, int(relu), pad,
+                                                           sp[-2], sp[-1], _p(y_split), _stream()), "gn_apply_tc3")
+    if want_split:
+        return y_s3, y_nchw, y_split
     return y_s3, y_nchw
 
 
-def cost_volume_concat_c8s3(L, R, D):
-    """K1 in C8S3: [B,C,h,w] fp32 x2 -> [B, 2C/8, 3, D, h, w, 8] bf16 (terms sum to the fp32 volume exactly)."""
+def cost_volume_concat_c8s3(L, R, D, pad=0):
+    """K1 in C8S3: [B,C,h,w] fp32 x2 -> [B, 2C/8, 3, D, h + 2 pad, w, 8] bf16 (terms sum to the fp32 volume exactly;
+    `pad` un-written halo rows above and below for row-band sharding)."""
     _req(L, R)
     B, C, h, w = L.shape
-    cost = torch.empty((B, 2 * C // 8, 3, D, h, w, 8), device=L.device, dtype=BF16)
+    cost = torch.empty((B, 2 * C // 8, 3, D, h + 2 * pad, w, 8), device=L.device, dtype=BF16)
     with torch.cuda.device(L.device), _timed("cost_volume_concat_c8s3"):
-        _lib.check(_lib.load().cmfb200_cost_volume_concat_c8s3(_p(L), _p(R), _p(cost), B, C, h, w, D, _stream()),
+        _lib.check(_lib.load().cmfb200_cost_volume_concat_c8s3_padded(_p(L), _p(R), _p(cost), B, C, h, w, D, pad, _stream()),
                    "cost_volume_concat_c8s3")
     return cost
 
 
-def f32_to_c8s3(x):
+def f32_to_c8s3(x, pad=0):
     """[B,C,...] fp32 -> C8S3 (exact three-term bf16 split)."""
-    return gn_apply_tc3(x, None, None, None, raw_c8f=False)[0]
+    return gn_apply_tc3(x, None, None, None, raw_c8f=False, pad=pad)[0]
 
 
 def c8s3_to_f32(x_s3):

@@ -164,6 +164,43 @@ def exchange_row_halo(x, top=1, bottom=1, dim=-2, group=None):
     return torch.cat(parts, dim)
 
 
+def fill_row_halo_(x, pad, top, bottom, dim=-3, group=None):
+    """In-place halo exchange for activations that were ALLOCATED with `pad` spare rows above and below the band's rows
+    along `dim` (ops.gn_apply_tc3(pad=...), ops.cost_volume_concat_c8s3(pad=...)): fills the `top` rows just above the
+    band with the previous rank's bottom edge and the `bottom` rows just below with the next rank's top edge (zeros at
+    the image border = the conv's zero padding).  Only the boundary rows move; the activation itself is never copied."""
+    n, r = world(group), rank(group)
+    dim = dim % x.dim()
+    rows = x.shape[dim] - 2 * pad
+    if top > pad or bottom > pad:
+        raise ValueError("halo (%d, %d) exceeds the %d spare rows" % (top, bottom, pad))
+    recv_t = recv_b = None
+    ops = []
+    if n > 1:
+        if r > 0:
+            if bottom:
+                ops.append(dist.P2POp(dist.isend, x.narrow(dim, pad, bottom).contiguous(), _peer(group, r - 1), group))
+            if top:
+                recv_t = torch.empty_like(x.narrow(dim, pad - top, top), memory_format=torch.contiguous_format)
+                ops.append(dist.P2POp(dist.irecv, recv_t, _peer(group, r - 1), group))
+        if r < n - 1:
+            if top:
+                ops.append(dist.P2POp(dist.isend, x.narrow(dim, pad + rows - top, top).contiguous(), _peer(group, r + 1), group))
+            if bottom:
+                recv_b = torch.empty_like(x.narrow(dim, pad + rows, bottom), memory_format=torch.contiguous_format)
+                ops.append(dist.P2POp(dist.irecv, recv_b, _peer(group, r + 1), group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+    if top:
+        dst = x.narrow(dim, pad - top, top)
+        dst.copy_(recv_t) if recv_t is not None else dst.zero_()
+    if bottom:
+        dst = x.narrow(dim, pad + rows, bottom)
+        dst.copy_(recv_b) if recv_b is not None else dst.zero_()
+    return x
+
+
 def allreduce_gn_sums(sums, group=None):
     """Sum per-band GroupNorm statistics ([B,C,2] double: sum, sum of squares) over all bands, in place."""
     if world(group) > 1:

@@ -330,11 +330,13 @@ struct GnTc3Args {
     const __nv_bfloat16* res_s3;
     const float* res_nchw;
     __nv_bfloat16* y_s3;
+    __nv_bfloat16* y_split;  // parity-split C8S3 [B][8][C/8][3][D/2][H/2][W/2][8] (input of the stride-2 tensor-core conv)
     float* y_nchw;
     int C, cpg;
     long long spatial;
     float eps;
     int relu, raw_c8f;
+    int pad, H, W;  // row bands: y_s3 / res_s3 carry `pad` extra rows above and below the H rows (0 = dense)
 };
 
 __device__ __forceinline__ void split3(float v, __nv_bfloat16& t0, __nv_bfloat16& t1, __nv_bfloat16& t2) {
@@ -372,7 +374,14 @@ __global__ void __launch_bounds__(256) gn_apply_tc3_kernel(const GnTc3Args a) {
     }
     __syncthreads();
     const long long S = a.spatial;
+    const long long Sp = a.pad ? S / a.H * (a.H + 2 * a.pad) : S;  // positions of a padded (8-channel group, term) plane
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < S; p += (long long)gridDim.x * blockDim.x) {
+        long long pp = p;  // position inside a padded plane
+        if (a.pad) {
+            const long long hw = (long long)a.H * a.W;
+            const long long dz = p / hw, r = p - dz * hw;
+            pp = dz * (long long)(a.H + 2 * a.pad) * a.W + (long long)a.pad * a.W + r;
+        }
         float v[8];
         if (a.raw_c8f) {
             const float4 lo = *reinterpret_cast<const float4*>(a.raw + ((size_t)bg * S + p) * 8);
@@ -385,10 +394,10 @@ __global__ void __launch_bounds__(256) gn_apply_tc3_kernel(const GnTc3Args a) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[e], s_shift[e]);
         if (a.res_s3 != nullptr) {
-            const size_t base = ((size_t)bg * 3 * S + p) * 8;
+            const size_t base = ((size_t)bg * 3 * Sp + pp) * 8;
             uint4 q0 = *reinterpret_cast<const uint4*>(a.res_s3 + base);
-            uint4 q1 = *reinterpret_cast<const uint4*>(a.res_s3 + base + (size_t)S * 8);
-            uint4 q2 = *reinterpret_cast<const uint4*>(a.res_s3 + base + (size_t)2 * S * 8);
+            uint4 q1 = *reinterpret_cast<const uint4*>(a.res_s3 + base + (size_t)Sp * 8);
+            uint4 q2 = *reinterpret_cast<const uint4*>(a.res_s3 + base + (size_t)2 * Sp * 8);
             const __nv_bfloat16* r0 = reinterpret_cast<const __nv_bfloat16*>(&q0);
             const __nv_bfloat16* r1 = reinterpret_cast<const __nv_bfloat16*>(&q1);
             const __nv_bfloat16* r2 = reinterpret_cast<const __nv_bfloat16*>(&q2);
@@ -404,14 +413,26 @@ __global__ void __launch_bounds__(256) gn_apply_tc3_kernel(const GnTc3Args a) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
         }
-        if (a.y_s3 != nullptr) {
+        if (a.y_s3 != nullptr || a.y_split != nullptr) {
             __align__(16) __nv_bfloat16 t0[8], t1[8], t2[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) split3(v[e], t0[e], t1[e], t2[e]);
-            const size_t base = ((size_t)bg * 3 * S + p) * 8;
-            *reinterpret_cast<uint4*>(a.y_s3 + base) = *reinterpret_cast<const uint4*>(t0);
-            *reinterpret_cast<uint4*>(a.y_s3 + base + (size_t)S * 8) = *reinterpret_cast<const uint4*>(t1);
-            *reinterpret_cast<uint4*>(a.y_s3 + base + (size_t)2 * S * 8) = *reinterpret_cast<const uint4*>(t2);
+            if (a.y_s3 != nullptr) {
+                const size_t base = ((size_t)bg * 3 * Sp + pp) * 8;
+                *reinterpret_cast<uint4*>(a.y_s3 + base) = *reinterpret_cast<const uint4*>(t0);
+                *reinterpret_cast<uint4*>(a.y_s3 + base + (size_t)Sp * 8) = *reinterpret_cast<const uint4*>(t1);
+                *reinterpret_cast<uint4*>(a.y_s3 + base + (size_t)2 * Sp * 8) = *reinterpret_cast<const uint4*>(t2);
+            }
+            if (a.y_split != nullptr) {
+                const int w = (int)(p % a.W), h = (int)((p / a.W) % a.H), dz = (int)(p / ((long long)a.W * a.H));
+                const int q = ((dz & 1) << 2) | ((h & 1) << 1) | (w & 1);
+                const long long Sc = S >> 3;
+                const long long cell = ((long long)(dz >> 1) * (a.H >> 1) + (h >> 1)) * (a.W >> 1) + (w >> 1);
+                const size_t base = ((((size_t)b * 8 + q) * NG + g) * 3 * Sc + cell) * 8;
+                *reinterpret_cast<uint4*>(a.y_split + base) = *reinterpret_cast<const uint4*>(t0);
+                *reinterpret_cast<uint4*>(a.y_split + base + (size_t)Sc * 8) = *reinterpret_cast<const uint4*>(t1);
+                *reinterpret_cast<uint4*>(a.y_split + base + (size_t)2 * Sc * 8) = *reinterpret_cast<const uint4*>(t2);
+            }
         }
         if (a.y_nchw != nullptr) {
 #pragma unroll
@@ -431,7 +452,7 @@ __global__ void __launch_bounds__(256) gn_apply_tc3_kernel(const GnTc3Args a) {
 constexpr int kCvS3Rows = 2;
 __global__ void __launch_bounds__(256) cost_volume_c8s3_kernel(const float* __restrict__ L, const float* __restrict__ R,
                                                                __nv_bfloat16* __restrict__ cost, int C, int h, int w,
-                                                               int D, int DP) {
+                                                               int D, int DP, int pad) {
     extern __shared__ uint4 sv3[];  // [rows][DP + w]
     const int nc = C / 8;
     const int y0 = blockIdx.x * kCvS3Rows, chunk = blockIdx.y / 3, term = blockIdx.y % 3, b = blockIdx.z;
@@ -454,9 +475,11 @@ __global__ void __launch_bounds__(256) cost_volume_c8s3_kernel(const float* __re
     for (int i = threadIdx.x; i < rows * DP; i += 256) sv3[(i / DP) * pitch + (i % DP)] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint4* out = reinterpret_cast<uint4*>(cost) + ((((size_t)b * 2 * nc + chunk) * 3 + term) * D) * plane + (size_t)y0 * w;
+    const size_t oplane = (size_t)(h + 2 * pad) * w;  // row bands: `pad` extra rows above and below every depth plane
+    uint4* out = reinterpret_cast<uint4*>(cost) + ((((size_t)b * 2 * nc + chunk) * 3 + term) * D) * oplane +
+                 (size_t)(y0 + pad) * w;
     for (int d = warp; d < D; d += 8) {
-        uint4* o = out + (size_t)d * plane;
+        uint4* o = out + (size_t)d * oplane;
         for (int i = lane; i < rows * w; i += 32) {
             const int r = i / w, x = i - r * w;
             uint4 v = sv3[r * pitch + DP + (right ? x - d : x)];
@@ -550,11 +573,16 @@ extern "C" int cmfb200_conv_tc3_fwd(const void* x_c8s3, const void* packed_w, fl
                                      stream);
 }
 
-extern "C" int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma,
-                                    const float* beta, const void* residual_c8s3, const float* residual_nchw,
-                                    void* y_c8s3, float* y_nchw, int B, int C, int groups, long long spatial, float eps,
-                                    int relu, void* stream) {
-    CMF_REQUIRE(raw && (y_c8s3 || y_nchw), "gn_apply_tc3: null pointer");
+extern "C" int cmfb200_gn_apply_tc3_padded(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma,
+                                           const float* beta, const void* residual_c8s3, const float* residual_nchw,
+                                           void* y_c8s3, float* y_nchw, int B, int C, int groups, long long spatial,
+                                           float eps, int relu, int pad, int H, int W, void* y_split_c8s3, void* stream) {
+    CMF_REQUIRE(raw && (y_c8s3 || y_nchw || y_split_c8s3), "gn_apply_tc3: null pointer");
+    CMF_REQUIRE(y_split_c8s3 == nullptr || (H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && spatial % ((long long)H * W) == 0 &&
+                                            (spatial / ((long long)H * W)) % 2 == 0),
+                "gn_apply_tc3: the parity-split copy needs even D, H, W");
+    CMF_REQUIRE(pad >= 0 && (pad == 0 || (H > 0 && W > 0 && spatial % ((long long)H * W) == 0)),
+                "gn_apply_tc3: padded rows need H, W with spatial a multiple of H*W");
     CMF_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && spatial > 0, "gn_apply_tc3: bad shape");
     CMF_REQUIRE(gn_sums == nullptr || (gamma && beta && groups > 0 && C % groups == 0), "gn_apply_tc3: bad GroupNorm args");
     CMF_REQUIRE((long long)B * (C / 8) <= 65535, "gn_apply_tc3: B*C/8 exceeds the grid limit");
@@ -562,7 +590,9 @@ extern "C" int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const doub
     a.raw = raw, a.sums = gn_sums, a.gamma = gamma, a.beta = beta;
     a.res_s3 = reinterpret_cast<const __nv_bfloat16*>(residual_c8s3), a.res_nchw = residual_nchw;
     a.y_s3 = reinterpret_cast<__nv_bfloat16*>(y_c8s3), a.y_nchw = y_nchw;
+    a.y_split = reinterpret_cast<__nv_bfloat16*>(y_split_c8s3);
     a.C = C, a.cpg = gn_sums ? C / groups : 1, a.spatial = spatial, a.eps = eps, a.relu = relu, a.raw_c8f = raw_is_c8f;
+    a.pad = pad, a.H = H, a.W = W;
     long long bx = cdiv(spatial, 256 * 4);
     if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, (unsigned)(B * (C / 8)));
@@ -571,8 +601,16 @@ extern "C" int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const doub
     return CMFB200_OK;
 }
 
-extern "C" int cmfb200_cost_volume_concat_c8s3(const float* L, const float* R, void* cost_c8s3, int B, int C, int h, int w,
-                                               int D, void* stream) {
+extern "C" int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma,
+                                    const float* beta, const void* residual_c8s3, const float* residual_nchw,
+                                    void* y_c8s3, float* y_nchw, int B, int C, int groups, long long spatial, float eps,
+                                    int relu, void* stream) {
+    return cmfb200_gn_apply_tc3_padded(raw, raw_is_c8f, gn_sums, gamma, beta, residual_c8s3, residual_nchw, y_c8s3, y_nchw, B,
+                                       C, groups, spatial, eps, relu, 0, 0, 0, nullptr, stream);
+}
+
+extern "C" int cmfb200_cost_volume_concat_c8s3_padded(const float* L, const float* R, void* cost_c8s3, int B, int C, int h,
+                                                      int w, int D, int pad, void* stream) {
     CMF_REQUIRE(L && R && cost_c8s3, "cost_volume_concat_c8s3: null pointer");
     CMF_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && h > 0 && w > 0 && D > 0, "cost_volume_concat_c8s3: bad shape");
     CMF_REQUIRE(B <= 65535, "cost_volume_concat_c8s3: B exceeds grid limit");
@@ -583,7 +621,12 @@ extern "C" int cmfb200_cost_volume_concat_c8s3(const float* L, const float* R, v
         CMF_CUDA(cudaFuncSetAttribute(cost_volume_c8s3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)cdiv(h, kCvS3Rows), (unsigned)(3 * 2 * (C / 8)), (unsigned)B);
     cost_volume_c8s3_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(L, R, reinterpret_cast<__nv_bfloat16*>(cost_c8s3),
-                                                                        C, h, w, D, DP);
+                                                                        C, h, w, D, DP, pad);
     CMF_LAUNCH_CHECK("cost_volume_c8s3_kernel");
     return CMFB200_OK;
+}
+
+extern "C" int cmfb200_cost_volume_concat_c8s3(const float* L, const float* R, void* cost_c8s3, int B, int C, int h, int w,
+                                               int D, void* stream) {
+    return cmfb200_cost_volume_concat_c8s3_padded(L, R, cost_c8s3, B, C, h, w, D, 0, stream);
 }

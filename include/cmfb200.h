@@ -268,6 +268,17 @@ int cmfb200_conv_tc3_rows_fwd(const void* x_c8s3, const void* packed_w, float* y
 int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma, const float* beta,
                          const void* residual_c8s3, const float* residual_nchw, void* y_c8s3, float* y_nchw, int B,
                          int C, int groups, long long spatial, float eps, int relu, void* stream);
+/* y_split_c8s3 (optional): the result ALSO as the parity-split copy [B][8][C/8][3][D/2][H/2][W/2][8] that the stride-2
+ * tensor-core conv reads (D, H, W even; H and W must then be passed).
+ * Row-band forms: y_c8s3 / residual_c8s3 (and the K1 output) carry `pad` extra rows above and below the H rows of every
+ * depth plane ([...][D][H + 2 pad][W][8]); the kernels fill the H interior rows, the halo rows are filled by the halo
+ * exchange -- no re-copy of the activation to attach them.  pad = 0 is the dense form. */
+int cmfb200_gn_apply_tc3_padded(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma,
+                                const float* beta, const void* residual_c8s3, const float* residual_nchw, void* y_c8s3,
+                                float* y_nchw, int B, int C, int groups, long long spatial, float eps, int relu, int pad,
+                                int H, int W, void* y_split_c8s3, void* stream);
+int cmfb200_cost_volume_concat_c8s3_padded(const float* L, const float* R, void* cost_c8s3, int B, int C, int h, int w,
+                                           int D, int pad, void* stream);
 /* K1 written directly as C8S3 (cmfsm.py:667-682): cost [B][2C/8][3][D][h][w][8] bf16; the three terms of an element
  * sum to the fp32 feature value exactly (or to +0.0 in the masked triangle). */
 int cmfb200_cost_volume_concat_c8s3(const float* L, const float* R, void* cost_c8s3, int B, int C, int h, int w, int D,
@@ -300,6 +311,18 @@ int cmfb200_masked_smooth_l1_bwd(const float* out1, const float* out2, const flo
  * Cin := Cout_t, Cout := Cin_t, stride 2 -- the result has the ConvTranspose3d weight layout. */
 int cmfb200_conv_wgrad(const float* x, const float* dy, float* dw, int B, int Cin, int Cout, int D, int H, int W, int KD,
                        int KHW, int stride, int dilation, void* stream);
+
+/* ---- fp32-accurate stride-2 / transposed 3x3x3 convs of the hourglasses on the tensor cores (csrc/conv_tc3_s2.cu) ----
+ * Same arithmetic and layouts as cmfb200_conv_tc3_fwd.  Stride 2 (hourglass.conv1 / conv3, cmfsm.py:244-254): the input is
+ * the PARITY-SPLIT C8S3 copy written by cmfb200_gn_apply_tc3_padded (y_split_c8s3); (Do,Ho,Wo) = output = cell grid;
+ * (Cin,Cout) in {(32,64),(64,64)}.  Transposed (conv5 / conv6, :261-281, k3 s2 p1 op1): x_c8s3 [B][Cin/8][3][D][H][W][8] ->
+ * y_c8f [B][Cout/8][2D][2H][2W][8], eight launches (one per output parity class); (Cin,Cout) in {(64,64),(64,32)}.
+ * packed_w: bf16, three terms, in the K-step order of the kernels (cmf_b200.ops.pack_tc3_s2_weight /
+ * pack_tc3_deconv_weight).  gn_sums as for cmfb200_conv_tc3_fwd. */
+int cmfb200_conv_tc3_s2_fwd(const void* x_split_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B, int Cin,
+                            int Cout, int Do, int Ho, int Wo, void* stream);
+int cmfb200_deconv_tc3_fwd(const void* x_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B, int Cin, int Cout,
+                           int D, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

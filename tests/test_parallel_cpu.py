@@ -109,6 +109,18 @@ def _worker(rank, world, port, h_total):
     got = par.gather_bands(yn, dim=3)
     torch.testing.assert_close(got, F.group_norm(yfull, 8, eps=1e-5), rtol=1e-9, atol=1e-9)
 
+    # ---------------- 3b. in-place halo fill of an activation allocated WITH spare rows (no re-copy of the band)
+    P = 2
+    padded = torch.full((B, C, D, (r1 - r0) + 2 * P, W), float("nan"), dtype=torch.float64)
+    padded[:, :, :, P:P + (r1 - r0)] = xb
+    par.fill_row_halo_(padded, P, 1, 1, dim=3)
+    assert torch.equal(padded[:, :, :, P - 1:P + (r1 - r0) + 1], torch.cat([lo, xb, hi], 3))
+    assert torch.isnan(padded[:, :, :, 0]).all() and torch.isnan(padded[:, :, :, -1]).all()  # untouched spare rows
+    par.fill_row_halo_(padded, P, 2, 2, dim=3)
+    lo2 = xfull[:, :, :, r0 - 2:r0] if r0 > 0 else torch.zeros_like(xfull[:, :, :, :2])
+    hi2 = xfull[:, :, :, r1:r1 + 2] if r1 < h_total else torch.zeros_like(xfull[:, :, :, :2])
+    assert torch.equal(padded, torch.cat([lo2, xb, hi2], 3))
+
     # ---------------- 4. stride-2 conv: only a TOP halo row is needed (band edges are multiples of 4) ---
     ext = par.exchange_row_halo(xb, 1, 0, dim=3)
     w2 = torch.randn(8, C, 3, 3, 3, dtype=torch.float64) * 0.2

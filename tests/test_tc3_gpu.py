@@ -133,3 +133,41 @@ def test_k1_c8s3_reconstructs_the_bit_exact_volume(B, C, h, w, D):
     want = orc.cost_volume_concat(L, R, D)
     assert torch.equal(got, want)
     assert not torch.signbit(got[want == 0]).any()
+
+
+@pytest.mark.parametrize("B,Cin,D,H,W", [(1, 32, 4, 32, 16), (2, 64, 4, 20, 24), (1, 32, 6, 36, 44), (1, 64, 2, 34, 18)])
+def test_conv3d_s2_tc3_vs_fp64(B, Cin, D, H, W):
+    """Stride-2 3x3x3 conv on the tensor cores (parity-split input written by the GroupNorm apply) vs fp64."""
+    from cmf_b200 import ops
+
+    x = _rand(B, Cin, D, H, W, seed=90) + 0.3
+    wgt = _rand(64, Cin, 3, 3, 3, seed=91) * (2.0 / (27 * Cin)) ** 0.5
+    want = F.conv3d(x.double(), wgt.double(), None, 2, 1)
+    _, _, xs = ops.gn_apply_tc3(x.to(DEV), None, None, None, False, want_s3=False, want_split=True)
+    assert xs.shape == (B, 8, Cin // 8, 3, D // 2, H // 2, W // 2, 8)
+    y, sums = ops.conv_tc3_s2(xs, ops.pack_tc3_s2_weight(wgt.to(DEV)))
+    got = ops.c8f_to_f32(y)
+    assert got.shape == want.shape
+    res, shrink = _rel_l2_scaled(got, want)
+    print("conv3d_s2_tc3 %s rel-L2 %.2e ; shrink %.2e residual %.2e" % ((B, Cin, D, H, W), _rel_l2(got, want), shrink, res))
+    assert _rel_l2(got, want) < 4e-6 and res < 2e-6
+    torch.testing.assert_close(sums.cpu()[..., 0], want.sum((2, 3, 4)), rtol=2e-5, atol=1e-3)
+    torch.testing.assert_close(sums.cpu()[..., 1], (want * want).sum((2, 3, 4)), rtol=2e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,Cout,D,H,W", [(1, 64, 2, 16, 8), (2, 32, 3, 10, 12), (1, 64, 3, 18, 20), (1, 32, 5, 33, 9)])
+def test_deconv3d_tc3_vs_fp64(B, Cout, D, H, W):
+    """Transposed 3x3x3 conv (s2, p1, op1) on the tensor cores, eight parity-class launches, vs fp64."""
+    from cmf_b200 import ops
+
+    x = _rand(B, 64, D, H, W, seed=92) + 0.3
+    wgt = _rand(64, Cout, 3, 3, 3, seed=93) * (2.0 / (27 * 64)) ** 0.5
+    want = F.conv_transpose3d(x.double(), wgt.double(), None, 2, 1, 1)
+    y, sums = ops.deconv_tc3(ops.f32_to_c8s3(x.to(DEV)), ops.pack_tc3_deconv_weight(wgt.to(DEV)), Cout)
+    got = ops.c8f_to_f32(y)
+    assert got.shape == want.shape
+    res, shrink = _rel_l2_scaled(got, want)
+    print("deconv3d_tc3 %s rel-L2 %.2e ; shrink %.2e residual %.2e" % ((B, Cout, D, H, W), _rel_l2(got, want), shrink, res))
+    assert _rel_l2(got, want) < 4e-6 and res < 2e-6
+    torch.testing.assert_close(sums.cpu()[..., 0], want.sum((2, 3, 4)), rtol=2e-5, atol=1e-3)
+    torch.testing.assert_close(sums.cpu()[..., 1], (want * want).sum((2, 3, 4)), rtol=2e-5, atol=1e-3)

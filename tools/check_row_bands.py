@@ -63,11 +63,11 @@ def main():
         kern = ops.drain_event_timing()
         ops.enable_event_timing(False)
         if rank == 0:
-            tot = sum(ms for _, ms in kern.values())
+            tot = sum(t for _, t in kern.values())
             print("band forward with events: %.2f ms elapsed, %.2f ms inside libcmfb200 kernels (%d launches); rest = NCCL, "
                   "torch.cat / contiguous copies, idle" % (p0.elapsed_time(p1), tot, sum(n for n, _ in kern.values())))
-            for k, (n, ms) in sorted(kern.items(), key=lambda kv: -kv[1][1])[:8]:
-                print("   %-28s %4d %.2f ms" % (k, n, ms))
+            for k, (n, t) in sorted(kern.items(), key=lambda kv: -kv[1][1])[:8]:
+                print("   %-28s %4d %.2f ms" % (k, n, t))
     if rank == 0:
         with torch.no_grad():
             ref = model(left, right)
