@@ -307,7 +307,10 @@ def conv_s1_nchw(x, weight, dilation=1, want_stats=False, engine="tc3"):
     The training path uses this for forward and dgrad; activations stay plain fp32 tensors in the autograd graph."""
     weight = weight.detach()
     cout, cin, k = weight.shape[0], weight.shape[1], weight.shape[-1]
-    if engine == "tc3" and tc3_supported(cin, cout, k, dilation):
+    # the tiny SPP-branch maps (1x2 .. 8x16 pooled values per channel) stay on the FFMA kernel: their GroupNorm
+    # statistics need double-from-the-first-element sums (conv_common.cuh), and there is no work to speed up
+    big = x[0, 0].numel() >= 4096
+    if engine == "tc3" and big and tc3_supported(cin, cout, k, dilation):
         return conv_tc3(f32_to_c8s3(x.contiguous()), pack_tc3_weight(weight.contiguous()), dilation, want_stats, out_nchw=True)
     if x.dim() == 5:
         return conv3d_k3(x.contiguous(), pack_conv3d_weight(weight.contiguous()), 1, want_stats=want_stats)

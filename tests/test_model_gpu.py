@@ -306,8 +306,12 @@ def test_training_gradients_match_fp64_oracle():
     # the reference's own fp32 arithmetic (CPU autograd through the fp32 oracle) against the same fp64 gradients: the
     # yardstick, exactly as for the forward -- this network amplifies fp32 rounding in both directions
     sd32 = {k: v.detach().cpu().requires_grad_(True) for k, v in net.state_dict().items()}
-    loss_of(orc.forward(sd32, left, right, grad=True), target).backward()
-    assert abs(float(loss.detach()) - float(loss64.detach())) < 1e-5 * abs(float(loss64.detach()))
+    loss32 = loss_of(orc.forward(sd32, left, right, grad=True), target)
+    loss32.backward()
+    d_ours, d_ref = abs(float(loss.detach()) - float(loss64.detach())), abs(float(loss32.detach()) - float(loss64.detach()))
+    print("loss: ours %.6f reference-fp32 %.6f fp64 %.6f" % (float(loss.detach()), float(loss32.detach()), float(loss64.detach())))
+    # the loss is a mean of |disparity error| terms: its fp32-vs-fp64 distance follows the outputs' (1e-3 px mean)
+    assert d_ours <= 2 * d_ref + 1e-4 * abs(float(loss64.detach())), (d_ours, d_ref)
     ours, ref = {}, {}
     for name, p in net.named_parameters():
         g64 = sd64[name].grad
