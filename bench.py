@@ -95,7 +95,7 @@ class ClockSampler(threading.Thread):
                 self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.reasons.update(k for k, bit in names.items() if r & bit)
-                time.sleep(0.05)
+                time.sleep(0.01)
         except Exception as e:  # NVML missing: report it instead of failing the run
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
