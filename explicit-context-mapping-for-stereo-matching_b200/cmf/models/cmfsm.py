@@ -642,29 +642,40 @@ class cmfsm(nn.Module):
                                out_rows=o.shape[-3] - 2 * P)
         return feat, full
 
-    def _ffma3_band(self, block, x, full_rows, stride=1, res_nchw=None, relu=False, want_s3=False, want_nchw=True):
-        """Stride-2 / transposed conv (FFMA row-window kernels, NCDHW) + GroupNorm on a row band."""
-        conv, gn = block[0], block[1]
-        packed = self._pack(conv)
-        rows = x.shape[3]
-        if isinstance(conv, nn.ConvTranspose3d):
-            y, sums = ops.conv3d_k3_rows(par.exchange_row_halo(x, 0, 1, dim=3), packed, rows, transposed=True)
-        else:
-            y, sums = ops.conv3d_k3_rows(par.exchange_row_halo(x, 2, 0, dim=3), packed, rows // 2, stride=2, row_offset=2)
-        sums = self._band_sums(sums, y.shape[3], full_rows)
-        if not want_s3:
-            return None, ops.gn_apply(y, sums, gn.weight, gn.bias, res_nchw, relu, out=y)
-        return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, False, res_nchw=res_nchw, relu=relu, want_s3=True,
-                                want_nchw=want_nchw, pad=self._BAND_PAD)
+    def _gn3_band(self, gn, y, sums, full_rows, res_nchw=None, relu=False, s3=False, nchw=False, split=False):
+        """GroupNorm (+residual) (+ReLU) of a band's raw C8F volume with the statistics of the WHOLE volume; the C8S3 /
+        parity-split results carry _BAND_PAD spare (cell) rows.  Returns (C8S3, NCDHW, parity-split), each or None."""
+        sums = self._band_sums(sums, y.shape[-3], full_rows)
+        out = ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, True, res_nchw=res_nchw, relu=relu, want_s3=s3, want_nchw=nchw,
+                               want_split=split, pad=self._BAND_PAD)
+        return out if split else out + (None,)
 
-    def _hourglass_band_tc3(self, hg, x, presqu, postsqu, resid, rows, out_nchw):
-        t, _ = self._ffma3_band(hg.conv1[0], x, rows // 2, 2, relu=True, want_s3=True, want_nchw=False)
-        _, pre = self._tc_band(hg.conv2, t, rows // 2, res_nchw=postsqu, relu=True, want_s3=False, want_nchw=True)
-        t, _ = self._ffma3_band(hg.conv3[0], pre, rows // 4, 2, relu=True, want_s3=True, want_nchw=False)
-        _, t = self._tc_band(hg.conv4[0], t, rows // 4, relu=True, want_s3=False, want_nchw=True)
-        _, post = self._ffma3_band(hg.conv5, t, rows // 2, res_nchw=presqu if presqu is not None else pre, relu=True)
-        o_s3, o = self._ffma3_band(hg.conv6, post, rows, res_nchw=resid, relu=False, want_s3=True, want_nchw=out_nchw)
-        return o_s3, o, pre, post
+    def _hourglass_band_tc3(self, hg, x_split, presqu, postsqu, resid, h, next_split):
+        """One hourglass on a row band, every conv on the tensor cores (h = rows of the un-sharded 1/4-resolution volume).
+        Halo per layer: stride 2 -> the cell row above (row 2o-1 of the input), stride 1 -> one row each side,
+        transposed -> the row below; all received in place into the spare rows of the padded activations."""
+        P = self._BAND_PAD
+
+        def fill(t, top, bottom):
+            return par.fill_row_halo_(t, P, top, bottom, dim=t.dim() - 3)
+
+        def s1(conv, t):
+            return ops.conv_tc3(fill(t, 1, 1), self._pack_tc3(conv), 1, True, row_off=P, out_rows=t.shape[-3] - 2 * P)
+
+        y, sums = ops.conv_tc3_s2(fill(x_split, 1, 0), self._pack_tc3_s2(hg.conv1[0][0]), pad=P)
+        t, _, _ = self._gn3_band(hg.conv1[0][1], y, sums, h // 2, relu=True, s3=True)
+        y, sums = s1(hg.conv2[0], t)
+        _, pre, pre_split = self._gn3_band(hg.conv2[1], y, sums, h // 2, res_nchw=postsqu, relu=True, nchw=True, split=True)
+        y, sums = ops.conv_tc3_s2(fill(pre_split, 1, 0), self._pack_tc3_s2(hg.conv3[0][0]), pad=P)
+        t, _, _ = self._gn3_band(hg.conv3[0][1], y, sums, h // 4, relu=True, s3=True)
+        y, sums = s1(hg.conv4[0][0], t)
+        t, _, _ = self._gn3_band(hg.conv4[0][1], y, sums, h // 4, relu=True, s3=True)
+        y, sums = ops.deconv_tc3(fill(t, 0, 1), self._pack_tc3_deconv(hg.conv5[0]), 64, pad=P)
+        p_s3, post, _ = self._gn3_band(hg.conv5[1], y, sums, h // 2, res_nchw=presqu if presqu is not None else pre,
+                                       relu=True, s3=True, nchw=True)
+        y, sums = ops.deconv_tc3(fill(p_s3, 0, 1), self._pack_tc3_deconv(hg.conv6[0]), 32, pad=P)
+        o_s3, _, o_split = self._gn3_band(hg.conv6[1], y, sums, h, res_nchw=resid, s3=True, split=next_split)
+        return o_s3, o_split, pre, post
 
     def _classify_band_tc3(self, head, x_s3, rows):
         _, t = self._tc_band(head[0], x_s3, rows, relu=True, want_s3=False, want_nchw=True)
@@ -673,19 +684,22 @@ class cmfsm(nn.Module):
         return y[:, 0]
 
     def _aggregate_band_tc3(self, lband, rband, D, h):
-        cost = ops.cost_volume_concat_c8s3(lband, rband, D, pad=self._BAND_PAD)
+        P = self._BAND_PAD
+        cost = ops.cost_volume_concat_c8s3(lband, rband, D, pad=P)
         t, _ = self._tc_band(self.dres0[0], cost, h, relu=True)
         del cost
         c0_s3, c0 = self._tc_band(self.dres0[2], t, h, relu=True, want_nchw=True)
         t, _ = self._tc_band(self.dres1[0], c0_s3, h, relu=True)
         del c0_s3
-        _, cost0 = self._tc_band(self.dres1[2], t, h, res_nchw=c0, want_s3=False, want_nchw=True)
-        del t, c0
-        o1_s3, out1, pre1, post1 = self._hourglass_band_tc3(self.dres2, cost0, None, None, cost0, h, True)
+        par.fill_row_halo_(t, P, 1, 1, dim=t.dim() - 3)
+        y, sums = ops.conv_tc3(t, self._pack_tc3(self.dres1[2][0]), 1, True, row_off=P, out_rows=t.shape[-3] - 2 * P)
+        _, cost0, cost0_split = self._gn3_band(self.dres1[2][1], y, sums, h, res_nchw=c0, nchw=True, split=True)
+        del t, c0, y
+        o1_s3, o1_split, pre1, post1 = self._hourglass_band_tc3(self.dres2, cost0_split, None, None, cost0, h, True)
         c1 = self._classify_band_tc3(self.classif1, o1_s3, h)
-        o2_s3, out2, _pre2, post2 = self._hourglass_band_tc3(self.dres3, out1, pre1, post1, cost0, h, True)
+        o2_s3, o2_split, _pre2, post2 = self._hourglass_band_tc3(self.dres3, o1_split, pre1, post1, cost0, h, True)
         c2 = self._classify_band_tc3(self.classif2, o2_s3, h)
-        o3_s3, _o3, _pre3, _post3 = self._hourglass_band_tc3(self.dres4, out2, pre1, post2, cost0, h, False)
+        o3_s3, _, _pre3, _post3 = self._hourglass_band_tc3(self.dres4, o2_split, pre1, post2, cost0, h, False)
         return c1, c2, self._classify_band_tc3(self.classif3, o3_s3, h)
 
     @torch.no_grad()

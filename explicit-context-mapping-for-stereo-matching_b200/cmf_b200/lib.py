@@ -66,6 +66,8 @@ SIGNATURES = {
     "cmfb200_gn_apply_tc3_padded": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _F, _I, _I, _I, _I, _P, _P],
     "cmfb200_conv_tc3_s2_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_deconv_tc3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "cmfb200_conv_tc3_s2_rows_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cmfb200_deconv_tc3_rows_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_cost_volume_concat_c8s3_padded": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_pack_tc3_weight": [_P, _P, _I, _I, _I, _I, _P],
     "cmfb200_conv_tc3_fwd": [_P, _P, _P, _P] + [_I] * 10 + [_P],

@@ -761,27 +761,31 @@ def pack_tc3_deconv_weight(weight):
     return _pack_tc3_taps(w, steps)
 
 
-def conv_tc3_s2(x_split, packed, Cout=64, want_stats=True):
-    """Stride-2 3x3x3 conv on the tensor cores: parity-split C8S3 [B,8,Cin/8,3,D/2,H/2,W/2,8] -> raw C8F [B,Cout/8,D/2,..,8]."""
+def conv_tc3_s2(x_split, packed, Cout=64, want_stats=True, pad=0):
+    """Stride-2 3x3x3 conv on the tensor cores: parity-split C8S3 [B,8,Cin/8,3,D/2,H/2 + 2 pad,W/2,8] -> raw C8F
+    [B,Cout/8,D/2,H/2,W/2,8] (`pad` spare cell rows of the input for row bands)."""
     _req(x_split, packed, dtype=BF16)
-    B, _, NC, _, Do, Ho, Wo, _ = x_split.shape
+    B, _, NC, _, Do, Hp, Wo, _ = x_split.shape
+    Ho = Hp - 2 * pad
     y = torch.empty((B, Cout // 8, Do, Ho, Wo, 8), device=x_split.device, dtype=torch.float32)
     sums = _new_sums(B, Cout, x_split.device) if want_stats else None
     with torch.cuda.device(x_split.device), _timed("conv_tc3_s2_fwd"):
-        _lib.check(_lib.load().cmfb200_conv_tc3_s2_fwd(_p(x_split), _p(packed), _p(y), _p(sums), B, NC * 8, Cout, Do, Ho, Wo,
-                                                       _stream()), "conv_tc3_s2_fwd")
+        _lib.check(_lib.load().cmfb200_conv_tc3_s2_rows_fwd(_p(x_split), _p(packed), _p(y), _p(sums), B, NC * 8, Cout, Do, Ho,
+                                                            Wo, pad, _stream()), "conv_tc3_s2_fwd")
     return y, sums
 
 
-def deconv_tc3(x_s3, packed, Cout, want_stats=True):
-    """Transposed 3x3x3 conv (s2, p1, op1) on the tensor cores: C8S3 [B,Cin/8,3,D,H,W,8] -> raw C8F [B,Cout/8,2D,2H,2W,8]."""
+def deconv_tc3(x_s3, packed, Cout, want_stats=True, pad=0):
+    """Transposed 3x3x3 conv (s2, p1, op1) on the tensor cores: C8S3 [B,Cin/8,3,D,H + 2 pad,W,8] -> raw C8F
+    [B,Cout/8,2D,2H,2W,8] (`pad` spare rows of the input for row bands)."""
     _req(x_s3, packed, dtype=BF16)
-    B, NC, _, D, H, W, _ = x_s3.shape
+    B, NC, _, D, Hp, W, _ = x_s3.shape
+    H = Hp - 2 * pad
     y = torch.empty((B, Cout // 8, 2 * D, 2 * H, 2 * W, 8), device=x_s3.device, dtype=torch.float32)
     sums = _new_sums(B, Cout, x_s3.device) if want_stats else None
     with torch.cuda.device(x_s3.device), _timed("deconv_tc3_fwd"):
-        _lib.check(_lib.load().cmfb200_deconv_tc3_fwd(_p(x_s3), _p(packed), _p(y), _p(sums), B, NC * 8, Cout, D, H, W,
-                                                      _stream()), "deconv_tc3_fwd")
+        _lib.check(_lib.load().cmfb200_deconv_tc3_rows_fwd(_p(x_s3), _p(packed), _p(y), _p(sums), B, NC * 8, Cout, D, H, W, pad,
+                                                           _stream()), "deconv_tc3_fwd")
     return y, sums
 
 
@@ -809,7 +813,8 @@ def gn_apply_tc3(raw, sums, gamma, beta, raw_c8f, res_s3=None, res_nchw=None, re
         raise ValueError("gn_apply_tc3: residual %s does not match %s (pad %d)" % (tuple(res_s3.shape), (B, C // 8, 3) + psp, pad))
     y_s3 = torch.empty((B, C // 8, 3) + psp + (8,), device=raw.device, dtype=BF16) if want_s3 else None
     y_nchw = torch.empty((B, C) + sp, device=raw.device, dtype=torch.float32) if want_nchw else None
-    y_split = (torch.empty((B, 8, C // 8, 3) + tuple(v // 2 for v in sp) + (8,), device=raw.device, dtype=BF16)
+    csp = tuple(v // 2 for v in sp)
+    y_split = (torch.empty((B, 8, C // 8, 3) + csp[:-2] + (csp[-2] + 2 * pad, csp[-1]) + (8,), device=raw.device, dtype=BF16)
                if want_split else None)
     with torch.cuda.device(raw.device), _timed("gn_apply_tc3"):
         _lib.check(_lib.load().cmfb200_gn_apply_tc3_padded(_p(raw), int(raw_c8f), _p(sums),

@@ -426,8 +426,9 @@ __global__ void __launch_bounds__(256) gn_apply_tc3_kernel(const GnTc3Args a) {
             if (a.y_split != nullptr) {
                 const int w = (int)(p % a.W), h = (int)((p / a.W) % a.H), dz = (int)(p / ((long long)a.W * a.H));
                 const int q = ((dz & 1) << 2) | ((h & 1) << 1) | (w & 1);
-                const long long Sc = S >> 3;
-                const long long cell = ((long long)(dz >> 1) * (a.H >> 1) + (h >> 1)) * (a.W >> 1) + (w >> 1);
+                const long long Hc = (a.H >> 1) + 2 * a.pad;  // `pad` spare CELL rows above / below (row bands)
+                const long long Sc = (S >> 3) / (a.H >> 1) * Hc;
+                const long long cell = ((long long)(dz >> 1) * Hc + (h >> 1) + a.pad) * (a.W >> 1) + (w >> 1);
                 const size_t base = ((((size_t)b * 8 + q) * NG + g) * 3 * Sc + cell) * 8;
                 *reinterpret_cast<uint4*>(a.y_split + base) = *reinterpret_cast<const uint4*>(t0);
                 *reinterpret_cast<uint4*>(a.y_split + base + (size_t)Sc * 8) = *reinterpret_cast<const uint4*>(t1);

@@ -71,7 +71,8 @@ template <int COUT, int T, int NS>
 __global__ void __launch_bounds__(kIgThreads, 1)
     conv_tc3g_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ KTable tab,
                      const __nv_bfloat16* __restrict__ wpk, float* __restrict__ y, double* __restrict__ gn_sums, int Hc,
-                     int Wc, int groups_w, const OutMap om) {
+                     int Wc, int groups_w, const OutMap om, int row_off) {
+    // row bands: the input carries `row_off` spare (halo) rows above the Hc rows this launch computes
     using G = GCfg<COUT, T, NS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
                 uint8_t* stage = smem + s * G::STAGE;
 #pragma unroll
                 for (int t = 0; t < T; ++t)
-                    tma_load_5d(stage + t * kGATile, &tmap_x, full + s, ((tx0 + t) * 8 + st.ox) * 8, ty * 16 + st.oy,
+                    tma_load_5d(stage + t * kGATile, &tmap_x, full + s, ((tx0 + t) * 8 + st.ox) * 8, ty * 16 + st.oy + row_off,
                                 d + st.oz, st.j0, b * tab.bmul + st.bsel);
                 bulk_g2s(stage + G::A_STAGE, reinterpret_cast<const uint8_t*>(wpk) + st.b_off, wbytes, full + s);
             }
@@ -265,7 +266,7 @@ static unsigned build_table_deconv(KTable& t, int p, int KC, int B_TAP, unsigned
 
 template <int COUT, int T, int NS>
 static int launch_g(const CUtensorMap& tmap, const KTable& tab, const void* wpk, float* y, double* gn, int B, int Dc, int Hc,
-                    int Wc, const OutMap& om, cudaStream_t st) {
+                    int Wc, const OutMap& om, int row_off, cudaStream_t st) {
     using G = GCfg<COUT, T, NS>;
     auto kern = conv_tc3g_kernel<COUT, T, NS>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
@@ -273,7 +274,7 @@ static int launch_g(const CUtensorMap& tmap, const KTable& tab, const void* wpk,
     dim3 grid((unsigned)(groups_w * tiles_h), (unsigned)Dc, (unsigned)B);
     CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv_tc3g: grid too large");
     kern<<<grid, kIgThreads, G::SMEM_BYTES, st>>>(tmap, tab, reinterpret_cast<const __nv_bfloat16*>(wpk), y, gn, Hc, Wc,
-                                                  groups_w, om);
+                                                  groups_w, om, row_off);
     CMF_LAUNCH_CHECK("conv_tc3g_kernel");
     return CMFB200_OK;
 }
@@ -282,35 +283,44 @@ static int launch_g(const CUtensorMap& tmap, const KTable& tab, const void* wpk,
 
 using namespace cmfb200;
 
-extern "C" int cmfb200_conv_tc3_s2_fwd(const void* x_split_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B,
-                                       int Cin, int Cout, int Do, int Ho, int Wo, void* stream) {
+extern "C" int cmfb200_conv_tc3_s2_rows_fwd(const void* x_split_c8s3, const void* packed_w, float* y_c8f, double* gn_sums,
+                                            int B, int Cin, int Cout, int Do, int Ho, int Wo, int pad, void* stream) {
+    // pad: spare cell rows above and below the Ho cell rows of every parity class (row bands; 0 = dense)
     CMF_REQUIRE(x_split_c8s3 && packed_w && y_c8f, "conv_tc3_s2_fwd: null pointer");
-    CMF_REQUIRE(B > 0 && Do > 0 && Ho > 0 && Wo > 0, "conv_tc3_s2_fwd: non-positive dimension");
+    CMF_REQUIRE(B > 0 && Do > 0 && Ho > 0 && Wo > 0 && pad >= 0, "conv_tc3_s2_fwd: bad dimension");
     CMF_REQUIRE(Cout == 64 && (Cin == 32 || Cin == 64), "conv_tc3_s2_fwd: unsupported (Cin=%d, Cout=%d); supported: 32->64, 64->64",
                 Cin, Cout);
     const cuuint64_t NJ = (cuuint64_t)3 * (Cin / 8);
-    const cuuint64_t vol = (cuuint64_t)Do * Ho * Wo * 16;
+    const cuuint64_t Hp = (cuuint64_t)Ho + 2 * pad;
+    const cuuint64_t vol = (cuuint64_t)Do * Hp * Wo * 16;
     CUtensorMap tmap;
-    const cuuint64_t gdim[5] = {(cuuint64_t)Wo * 8, (cuuint64_t)Ho, (cuuint64_t)Do, NJ, (cuuint64_t)B * 8};
-    const cuuint64_t gstr[4] = {(cuuint64_t)Wo * 16, (cuuint64_t)Ho * Wo * 16, vol, vol * NJ};
+    const cuuint64_t gdim[5] = {(cuuint64_t)Wo * 8, Hp, (cuuint64_t)Do, NJ, (cuuint64_t)B * 8};
+    const cuuint64_t gstr[4] = {(cuuint64_t)Wo * 16, Hp * Wo * 16, vol, vol * NJ};
     const cuuint32_t box[5] = {kGPW * 8, kGPH, 1, 6, 1};
     if (int rc = encode_tmap_5d(&tmap, x_split_c8s3, gdim, gstr, box, "conv_tc3_s2")) return rc;
     KTable tab;
     build_table_s2(tab, Cin / 16, 6 * Cout * 16);
     const OutMap om = {Do, Ho, Wo, 1, 0, 0, 0};
-    return launch_g<64, 2, 3>(tmap, tab, packed_w, y_c8f, gn_sums, B, Do, Ho, Wo, om, (cudaStream_t)stream);
+    return launch_g<64, 2, 3>(tmap, tab, packed_w, y_c8f, gn_sums, B, Do, Ho, Wo, om, pad, (cudaStream_t)stream);
 }
 
-extern "C" int cmfb200_deconv_tc3_fwd(const void* x_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B, int Cin,
-                                      int Cout, int D, int H, int W, void* stream) {
+extern "C" int cmfb200_conv_tc3_s2_fwd(const void* x_split_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B,
+                                       int Cin, int Cout, int Do, int Ho, int Wo, void* stream) {
+    return cmfb200_conv_tc3_s2_rows_fwd(x_split_c8s3, packed_w, y_c8f, gn_sums, B, Cin, Cout, Do, Ho, Wo, 0, stream);
+}
+
+extern "C" int cmfb200_deconv_tc3_rows_fwd(const void* x_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B,
+                                           int Cin, int Cout, int D, int H, int W, int pad, void* stream) {
+    // pad: spare rows above and below the H rows of x (row bands: the row below the band holds the neighbour's first row)
     CMF_REQUIRE(x_c8s3 && packed_w && y_c8f, "deconv_tc3_fwd: null pointer");
-    CMF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "deconv_tc3_fwd: non-positive dimension");
+    CMF_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && pad >= 0, "deconv_tc3_fwd: bad dimension");
     CMF_REQUIRE(Cin == 64 && (Cout == 32 || Cout == 64), "deconv_tc3_fwd: unsupported (Cin=%d, Cout=%d); supported: 64->64, 64->32",
                 Cin, Cout);
     const cuuint64_t NJ = (cuuint64_t)3 * (Cin / 8);
     CUtensorMap tmap;
-    const cuuint64_t gdim[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, NJ, (cuuint64_t)B};
-    const cuuint64_t gstr[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16, NJ * D * H * W * 16};
+    const cuuint64_t Hp = (cuuint64_t)H + 2 * pad;
+    const cuuint64_t gdim[5] = {(cuuint64_t)W * 8, Hp, (cuuint64_t)D, NJ, (cuuint64_t)B};
+    const cuuint64_t gstr[4] = {(cuuint64_t)W * 16, Hp * W * 16, (cuuint64_t)D * Hp * W * 16, NJ * D * Hp * W * 16};
     const cuuint32_t box[5] = {kGPW * 8, kGPH, 1, 6, 1};
     if (int rc = encode_tmap_5d(&tmap, x_c8s3, gdim, gstr, box, "deconv_tc3")) return rc;
     unsigned off = 0;
@@ -318,9 +328,14 @@ extern "C" int cmfb200_deconv_tc3_fwd(const void* x_c8s3, const void* packed_w, 
         KTable tab;
         off = build_table_deconv(tab, p, Cin / 16, 6 * Cout * 16, off);
         const OutMap om = {2 * D, 2 * H, 2 * W, 2, p >> 2, (p >> 1) & 1, p & 1};
-        const int rc = Cout == 64 ? launch_g<64, 2, 3>(tmap, tab, packed_w, y_c8f, gn_sums, B, D, H, W, om, (cudaStream_t)stream)
-                                  : launch_g<32, 4, 3>(tmap, tab, packed_w, y_c8f, gn_sums, B, D, H, W, om, (cudaStream_t)stream);
+        const int rc = Cout == 64 ? launch_g<64, 2, 3>(tmap, tab, packed_w, y_c8f, gn_sums, B, D, H, W, om, pad, (cudaStream_t)stream)
+                                  : launch_g<32, 4, 3>(tmap, tab, packed_w, y_c8f, gn_sums, B, D, H, W, om, pad, (cudaStream_t)stream);
         if (rc) return rc;
     }
     return CMFB200_OK;
+}
+
+extern "C" int cmfb200_deconv_tc3_fwd(const void* x_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B, int Cin,
+                                      int Cout, int D, int H, int W, void* stream) {
+    return cmfb200_deconv_tc3_rows_fwd(x_c8s3, packed_w, y_c8f, gn_sums, B, Cin, Cout, D, H, W, 0, stream);
 }

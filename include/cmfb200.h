@@ -323,6 +323,12 @@ int cmfb200_conv_tc3_s2_fwd(const void* x_split_c8s3, const void* packed_w, floa
                             int Cout, int Do, int Ho, int Wo, void* stream);
 int cmfb200_deconv_tc3_fwd(const void* x_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B, int Cin, int Cout,
                            int D, int H, int W, void* stream);
+/* Row-band forms: the inputs carry `pad` spare rows (cell rows for the parity-split input) above and below the H (Ho)
+ * rows; the halo exchange fills the one row each layer needs (stride 2: the cell row above; transposed: the row below). */
+int cmfb200_conv_tc3_s2_rows_fwd(const void* x_split_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B,
+                                 int Cin, int Cout, int Do, int Ho, int Wo, int pad, void* stream);
+int cmfb200_deconv_tc3_rows_fwd(const void* x_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B, int Cin,
+                                int Cout, int D, int H, int W, int pad, void* stream);
 
 #ifdef __cplusplus
 }
