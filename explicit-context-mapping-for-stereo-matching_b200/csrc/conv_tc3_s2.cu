@@ -9,8 +9,9 @@
 //     offsets in {-1, 0}: K steps run over (q, depth tap, 16-channel chunk), each with its own 1..4 in-plane taps, all into
 //     ONE accumulator set.  27 taps of work, no zero insertion, no strided gather.
 //   * transposed: out index o' = 2i - 1 + k.  Output parity 0 takes tap k = 1 of cell i; parity 1 takes k = 2 of cell i and
-//     k = 0 of cell i + 1.  One launch per output parity class p (1..8 taps, cell offsets in {0, +1}); the epilogue writes
-//     the class's voxels (2i + p) of the C8F output and adds to the same GroupNorm sums.
+//     k = 0 of cell i + 1.  Every output parity class p is its own small conv (1..8 taps, cell offsets in {0, +1}); all
+//     eight run in ONE launch (blockIdx.z = b * 8 + p), the epilogue writes the class's voxels (2i + p) of the C8F output
+//     and adds to the same GroupNorm sums.
 // The kernel is conv_tc3's with the fixed 3x3(x3) tap loops replaced by a K-step TABLE (box origin, depth offset, channel
 // chunk, batch-dimension index, number of in-plane taps and their offsets inside the 17 x 9 box, weight offset) built on
 // the host and passed as a __grid_constant__ parameter; one ring stage = the T activation boxes + the <= 4 weight taps
@@ -28,7 +29,6 @@ namespace {
 constexpr int kGPW = 9, kGPH = 17;             // 8 x 16 tile + one halo voxel on one side
 constexpr int kGPlane = kGPH * kGPW * 16;      // one (8-channel chunk, term) plane of a box
 constexpr int kGATile = (6 * kGPlane + 127) & ~127;  // 2 chunks x 3 terms, rounded up: TMA destinations are 128-byte aligned
-constexpr int kMaxSteps = 48;
 
 struct KStep {
     short ox, oy, oz;        // box origin relative to the tile origin (voxels) / depth offset relative to d
@@ -38,12 +38,21 @@ struct KStep {
     short hoff[2], woff[2];  // tap offsets inside the box (voxels)
     unsigned b_off;          // byte offset of this step's taps in the packed weights
 };
+template <int MAXSTEPS>
 struct KTable {
-    int n, bmul;
-    KStep s[kMaxSteps];
+    int n;
+    short od0, oh0, ow0, pad_;  // output voxel of compute position (d,h,w): (d*os+od0, h*os+oh0, w*os+ow0)
+    KStep s[MAXSTEPS];
+};
+// NTAB tables served by ONE launch (blockIdx.z = b * NTAB + table): the eight output parity classes of the transposed
+// conv run concurrently instead of as eight latency-bound launches
+template <int NTAB, int MAXSTEPS>
+struct KTableSet {
+    int bmul;
+    KTable<MAXSTEPS> t[NTAB];
 };
 struct OutMap {
-    int Do, Ho, Wo, os, od0, oh0, ow0;  // output voxel of compute position (d,h,w): (d*os+od0, h*os+oh0, w*os+ow0)
+    int Do, Ho, Wo, os;
 };
 
 template <int COUT, int T, int NS>
@@ -67,9 +76,9 @@ __host__ __device__ constexpr uint32_t g_idesc(int n) {
 
 }  // namespace
 
-template <int COUT, int T, int NS>
+template <int COUT, int T, int NS, int NTAB, int MAXSTEPS>
 __global__ void __launch_bounds__(kIgThreads, 1)
-    conv_tc3g_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ KTable tab,
+    conv_tc3g_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ KTableSet<NTAB, MAXSTEPS> tabs,
                      const __nv_bfloat16* __restrict__ wpk, float* __restrict__ y, double* __restrict__ gn_sums, int Hc,
                      int Wc, int groups_w, const OutMap om, int row_off) {
     // row bands: the input carries `row_off` spare (halo) rows above the Hc rows this launch computes
@@ -85,7 +94,8 @@ __global__ void __launch_bounds__(kIgThreads, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gx = blockIdx.x % groups_w, ty = blockIdx.x / groups_w;
-    const int tx0 = gx * T, d = blockIdx.y, b = blockIdx.z;
+    const int tx0 = gx * T, d = blockIdx.y, b = blockIdx.z / NTAB;
+    const KTable<MAXSTEPS>& tab = tabs.t[blockIdx.z % NTAB];
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) {
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
 #pragma unroll
                 for (int t = 0; t < T; ++t)
                     tma_load_5d(stage + t * kGATile, &tmap_x, full + s, ((tx0 + t) * 8 + st.ox) * 8, ty * 16 + st.oy + row_off,
-                                d + st.oz, st.j0, b * tab.bmul + st.bsel);
+                                d + st.oz, st.j0, b * tabs.bmul + st.bsel);
                 bulk_g2s(stage + G::A_STAGE, reinterpret_cast<const uint8_t*>(wpk) + st.b_off, wbytes, full + s);
             }
         }
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(kIgThreads, 1)
         for (int t = 0; t < T; ++t) {
             const int h = ty * 16 + (row >> 3), w = (tx0 + t) * 8 + (row & 7);
             const bool ok = (h < Hc) && (w < Wc);
-            const size_t opos = ((size_t)(d * om.os + om.od0)) * oplane + (size_t)(h * om.os + om.oh0) * om.Wo + (w * om.os + om.ow0);
+            const size_t opos = ((size_t)(d * om.os + tab.od0)) * oplane + (size_t)(h * om.os + tab.oh0) * om.Wo + (w * om.os + tab.ow0);
 #pragma unroll 1
             for (int cb = 0; cb < COUT / 32; ++cb) {
                 float o[32];
@@ -233,8 +243,8 @@ __global__ void __launch_bounds__(kIgThreads, 1)
 // One axis of a class with parity bit `bit`: number of taps, and for tap index i the offset INSIDE the box.
 //   stride 2   (box origin at cell -1): bit 0 -> 1 tap (k=1) at box index 1 ; bit 1 -> k=0 at index 0, k=2 at index 1
 //   transposed (box origin at cell  0): bit 0 -> 1 tap (k=1) at box index 0 ; bit 1 -> k=2 at index 0, k=0 at index 1
-static void build_table_s2(KTable& t, int KC, int B_TAP) {
-    t.n = 0, t.bmul = 8;
+static void build_table_s2(KTable<48>& t, int KC, int B_TAP) {
+    t.n = 0, t.od0 = t.oh0 = t.ow0 = t.pad_ = 0;
     unsigned off = 0;
     for (int q = 0; q < 8; ++q) {
         const int qd = q >> 2, qh = (q >> 1) & 1, qw = q & 1;
@@ -249,9 +259,9 @@ static void build_table_s2(KTable& t, int KC, int B_TAP) {
             }
     }
 }
-static unsigned build_table_deconv(KTable& t, int p, int KC, int B_TAP, unsigned off) {
-    t.n = 0, t.bmul = 1;
+static unsigned build_table_deconv(KTable<8>& t, int p, int KC, int B_TAP, unsigned off) {
     const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
+    t.n = 0, t.od0 = (short)pd, t.oh0 = (short)ph, t.ow0 = (short)pw, t.pad_ = 0;
     for (int kdi = 0; kdi < 1 + pd; ++kdi)
         for (int kc = 0; kc < KC; ++kc) {
             KStep& s = t.s[t.n++];
@@ -264,16 +274,16 @@ static unsigned build_table_deconv(KTable& t, int p, int KC, int B_TAP, unsigned
     return off;
 }
 
-template <int COUT, int T, int NS>
-static int launch_g(const CUtensorMap& tmap, const KTable& tab, const void* wpk, float* y, double* gn, int B, int Dc, int Hc,
-                    int Wc, const OutMap& om, int row_off, cudaStream_t st) {
+template <int COUT, int T, int NS, int NTAB, int MAXSTEPS>
+static int launch_g(const CUtensorMap& tmap, const KTableSet<NTAB, MAXSTEPS>& tabs, const void* wpk, float* y, double* gn,
+                    int B, int Dc, int Hc, int Wc, const OutMap& om, int row_off, cudaStream_t st) {
     using G = GCfg<COUT, T, NS>;
-    auto kern = conv_tc3g_kernel<COUT, T, NS>;
+    auto kern = conv_tc3g_kernel<COUT, T, NS, NTAB, MAXSTEPS>;
     CMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
     const int tiles_w = (int)cdiv(Wc, 8), tiles_h = (int)cdiv(Hc, 16), groups_w = (int)cdiv(tiles_w, T);
-    dim3 grid((unsigned)(groups_w * tiles_h), (unsigned)Dc, (unsigned)B);
+    dim3 grid((unsigned)(groups_w * tiles_h), (unsigned)Dc, (unsigned)(B * NTAB));
     CMF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv_tc3g: grid too large");
-    kern<<<grid, kIgThreads, G::SMEM_BYTES, st>>>(tmap, tab, reinterpret_cast<const __nv_bfloat16*>(wpk), y, gn, Hc, Wc,
+    kern<<<grid, kIgThreads, G::SMEM_BYTES, st>>>(tmap, tabs, reinterpret_cast<const __nv_bfloat16*>(wpk), y, gn, Hc, Wc,
                                                   groups_w, om, row_off);
     CMF_LAUNCH_CHECK("conv_tc3g_kernel");
     return CMFB200_OK;
@@ -298,10 +308,11 @@ extern "C" int cmfb200_conv_tc3_s2_rows_fwd(const void* x_split_c8s3, const void
     const cuuint64_t gstr[4] = {(cuuint64_t)Wo * 16, Hp * Wo * 16, vol, vol * NJ};
     const cuuint32_t box[5] = {kGPW * 8, kGPH, 1, 6, 1};
     if (int rc = encode_tmap_5d(&tmap, x_split_c8s3, gdim, gstr, box, "conv_tc3_s2")) return rc;
-    KTable tab;
-    build_table_s2(tab, Cin / 16, 6 * Cout * 16);
-    const OutMap om = {Do, Ho, Wo, 1, 0, 0, 0};
-    return launch_g<64, 2, 3>(tmap, tab, packed_w, y_c8f, gn_sums, B, Do, Ho, Wo, om, pad, (cudaStream_t)stream);
+    KTableSet<1, 48> tabs;
+    tabs.bmul = 8;
+    build_table_s2(tabs.t[0], Cin / 16, 6 * Cout * 16);
+    const OutMap om = {Do, Ho, Wo, 1};
+    return launch_g<64, 2, 3, 1, 48>(tmap, tabs, packed_w, y_c8f, gn_sums, B, Do, Ho, Wo, om, pad, (cudaStream_t)stream);
 }
 
 extern "C" int cmfb200_conv_tc3_s2_fwd(const void* x_split_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B,
@@ -323,16 +334,13 @@ extern "C" int cmfb200_deconv_tc3_rows_fwd(const void* x_c8s3, const void* packe
     const cuuint64_t gstr[4] = {(cuuint64_t)W * 16, Hp * W * 16, (cuuint64_t)D * Hp * W * 16, NJ * D * Hp * W * 16};
     const cuuint32_t box[5] = {kGPW * 8, kGPH, 1, 6, 1};
     if (int rc = encode_tmap_5d(&tmap, x_c8s3, gdim, gstr, box, "deconv_tc3")) return rc;
+    KTableSet<8, 8> tabs;  // the eight output parity classes, one launch
+    tabs.bmul = 1;
     unsigned off = 0;
-    for (int p = 0; p < 8; ++p) {  // one launch per output parity class
-        KTable tab;
-        off = build_table_deconv(tab, p, Cin / 16, 6 * Cout * 16, off);
-        const OutMap om = {2 * D, 2 * H, 2 * W, 2, p >> 2, (p >> 1) & 1, p & 1};
-        const int rc = Cout == 64 ? launch_g<64, 2, 3>(tmap, tab, packed_w, y_c8f, gn_sums, B, D, H, W, om, pad, (cudaStream_t)stream)
-                                  : launch_g<32, 4, 3>(tmap, tab, packed_w, y_c8f, gn_sums, B, D, H, W, om, pad, (cudaStream_t)stream);
-        if (rc) return rc;
-    }
-    return CMFB200_OK;
+    for (int p = 0; p < 8; ++p) off = build_table_deconv(tabs.t[p], p, Cin / 16, 6 * Cout * 16, off);
+    const OutMap om = {2 * D, 2 * H, 2 * W, 2};
+    if (Cout == 64) return launch_g<64, 2, 3, 8, 8>(tmap, tabs, packed_w, y_c8f, gn_sums, B, D, H, W, om, pad, (cudaStream_t)stream);
+    return launch_g<32, 4, 3, 8, 8>(tmap, tabs, packed_w, y_c8f, gn_sums, B, D, H, W, om, pad, (cudaStream_t)stream);
 }
 
 extern "C" int cmfb200_deconv_tc3_fwd(const void* x_c8s3, const void* packed_w, float* y_c8f, double* gn_sums, int B, int Cin,

@@ -630,6 +630,6 @@ def test_masked_smooth_l1_fused_vs_reference_statement(B, H, W):
     ours_in = [o.clone().to(DEV).requires_grad_(True) for o in outs]
     got = aops.masked_smooth_l1(ours_in, disp.to(DEV), 192)
     (got * 3.0).backward()
-    assert abs(float(got) - float(want)) < 1e-5 * abs(float(want))
+    assert abs(float(got.detach()) - float(want.detach())) < 1e-5 * abs(float(want.detach()))
     for a, b in zip(ours_in, ref_in):
         torch.testing.assert_close(a.grad.cpu().double(), 3.0 * b.grad, rtol=1e-5, atol=1e-9)
