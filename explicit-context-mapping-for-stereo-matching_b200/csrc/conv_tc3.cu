@@ -346,7 +346,7 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& t0, __nv_bfloat16
     t2 = __float2bfloat16_rn(r1 - __bfloat162float(t1));
 }
 
-__global__ void __launch_bounds__(256) gn_apply_tc3_kernel(const GnTc3Args a) {
+__global__ void __launch_bounds__(256, 4) gn_apply_tc3_kernel(const GnTc3Args a) {
     __shared__ float s_scale[8], s_shift[8];
     const int bg = blockIdx.y;  // b * C/8 + g
     const int NG = a.C / 8;
@@ -373,73 +373,102 @@ __global__ void __launch_bounds__(256) gn_apply_tc3_kernel(const GnTc3Args a) {
         s_shift[threadIdx.x] = shift;
     }
     __syncthreads();
-    const long long S = a.spatial;
-    const long long Sp = a.pad ? S / a.H * (a.H + 2 * a.pad) : S;  // positions of a padded (8-channel group, term) plane
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < S; p += (long long)gridDim.x * blockDim.x) {
-        long long pp = p;  // position inside a padded plane
-        if (a.pad) {
-            const long long hw = (long long)a.H * a.W;
-            const long long dz = p / hw, r = p - dz * hw;
-            pp = dz * (long long)(a.H + 2 * a.pad) * a.W + (long long)a.pad * a.W + r;
-        }
-        float v[8];
-        if (a.raw_c8f) {
-            const float4 lo = *reinterpret_cast<const float4*>(a.raw + ((size_t)bg * S + p) * 8);
-            const float4 hi = *reinterpret_cast<const float4*>(a.raw + ((size_t)bg * S + p) * 8 + 4);
-            v[0] = lo.x, v[1] = lo.y, v[2] = lo.z, v[3] = lo.w, v[4] = hi.x, v[5] = hi.y, v[6] = hi.z, v[7] = hi.w;
-        } else {
+    // 32-bit position arithmetic (spatial < 2^31 is checked on the host); two positions per thread and iteration, every
+    // load issued before the first use (the kernel is a pure HBM stream: bytes in flight are what matters)
+    const unsigned S = (unsigned)a.spatial;
+    const unsigned H = (unsigned)a.H, W = (unsigned)a.W, hw = H * W;
+    const unsigned Hp = H + 2 * a.pad;
+    const size_t Sp = a.pad ? (size_t)(S / H) * Hp : S;  // positions of a padded (8-channel group, term) plane
+    const bool need_dhw = a.pad != 0 || a.y_split != nullptr;
+    constexpr int U = 2;
+    const unsigned step = gridDim.x * blockDim.x;
+    for (unsigned p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < S; p0 += U * step) {
+        float v[U][8], rn[U][8];
+        uint4 rq[U][3];
+        unsigned pos[U];
+        size_t pp[U];
+        bool on[U];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = a.raw[((size_t)b * a.C + g * 8 + e) * S + p];
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[e], s_shift[e]);
-        if (a.res_s3 != nullptr) {
-            const size_t base = ((size_t)bg * 3 * Sp + pp) * 8;
-            uint4 q0 = *reinterpret_cast<const uint4*>(a.res_s3 + base);
-            uint4 q1 = *reinterpret_cast<const uint4*>(a.res_s3 + base + (size_t)Sp * 8);
-            uint4 q2 = *reinterpret_cast<const uint4*>(a.res_s3 + base + (size_t)2 * Sp * 8);
-            const __nv_bfloat16* r0 = reinterpret_cast<const __nv_bfloat16*>(&q0);
-            const __nv_bfloat16* r1 = reinterpret_cast<const __nv_bfloat16*>(&q1);
-            const __nv_bfloat16* r2 = reinterpret_cast<const __nv_bfloat16*>(&q2);
-#pragma unroll
-            for (int e = 0; e < 8; ++e)  // the three terms reconstruct the fp32 residual exactly
-                v[e] += (__bfloat162float(r0[e]) + __bfloat162float(r1[e])) + __bfloat162float(r2[e]);
-        }
-        if (a.res_nchw != nullptr) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += a.res_nchw[((size_t)b * a.C + g * 8 + e) * S + p];
-        }
-        if (a.relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-        }
-        if (a.y_s3 != nullptr || a.y_split != nullptr) {
-            __align__(16) __nv_bfloat16 t0[8], t1[8], t2[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) split3(v[e], t0[e], t1[e], t2[e]);
-            if (a.y_s3 != nullptr) {
-                const size_t base = ((size_t)bg * 3 * Sp + pp) * 8;
-                *reinterpret_cast<uint4*>(a.y_s3 + base) = *reinterpret_cast<const uint4*>(t0);
-                *reinterpret_cast<uint4*>(a.y_s3 + base + (size_t)Sp * 8) = *reinterpret_cast<const uint4*>(t1);
-                *reinterpret_cast<uint4*>(a.y_s3 + base + (size_t)2 * Sp * 8) = *reinterpret_cast<const uint4*>(t2);
+        for (int u = 0; u < U; ++u) {
+            pos[u] = p0 + u * step;
+            on[u] = pos[u] < S;
+            const unsigned p = on[u] ? pos[u] : 0u;
+            pp[u] = p;
+            if (a.pad) {
+                const unsigned dz = p / hw, r = p - dz * hw;
+                pp[u] = (size_t)dz * Hp * W + (size_t)a.pad * W + r;
             }
-            if (a.y_split != nullptr) {
-                const int w = (int)(p % a.W), h = (int)((p / a.W) % a.H), dz = (int)(p / ((long long)a.W * a.H));
-                const int q = ((dz & 1) << 2) | ((h & 1) << 1) | (w & 1);
-                const long long Hc = (a.H >> 1) + 2 * a.pad;  // `pad` spare CELL rows above / below (row bands)
-                const long long Sc = (S >> 3) / (a.H >> 1) * Hc;
-                const long long cell = ((long long)(dz >> 1) * Hc + (h >> 1) + a.pad) * (a.W >> 1) + (w >> 1);
-                const size_t base = ((((size_t)b * 8 + q) * NG + g) * 3 * Sc + cell) * 8;
-                *reinterpret_cast<uint4*>(a.y_split + base) = *reinterpret_cast<const uint4*>(t0);
-                *reinterpret_cast<uint4*>(a.y_split + base + (size_t)Sc * 8) = *reinterpret_cast<const uint4*>(t1);
-                *reinterpret_cast<uint4*>(a.y_split + base + (size_t)2 * Sc * 8) = *reinterpret_cast<const uint4*>(t2);
+            if (a.raw_c8f) {
+                const float4 lo = ld_streaming_f4(a.raw + ((size_t)bg * S + p) * 8);
+                const float4 hi = ld_streaming_f4(a.raw + ((size_t)bg * S + p) * 8 + 4);
+                v[u][0] = lo.x, v[u][1] = lo.y, v[u][2] = lo.z, v[u][3] = lo.w;
+                v[u][4] = hi.x, v[u][5] = hi.y, v[u][6] = hi.z, v[u][7] = hi.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[u][e] = __ldg(a.raw + ((size_t)b * a.C + g * 8 + e) * S + p);
+            }
+            if (a.res_s3 != nullptr) {
+                const size_t base = ((size_t)bg * 3 * Sp + pp[u]) * 8;
+                rq[u][0] = *reinterpret_cast<const uint4*>(a.res_s3 + base);
+                rq[u][1] = *reinterpret_cast<const uint4*>(a.res_s3 + base + Sp * 8);
+                rq[u][2] = *reinterpret_cast<const uint4*>(a.res_s3 + base + 2 * Sp * 8);
+            }
+            if (a.res_nchw != nullptr) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) rn[u][e] = __ldg(a.res_nchw + ((size_t)b * a.C + g * 8 + e) * S + p);
             }
         }
-        if (a.y_nchw != nullptr) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a.y_nchw[((size_t)b * a.C + g * 8 + e) * S + p] = v[e];
+        for (int u = 0; u < U; ++u) {
+            if (!on[u]) continue;
+            const unsigned p = pos[u];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u][e] = fmaf(v[u][e], s_scale[e], s_shift[e]);
+            if (a.res_s3 != nullptr) {
+                const __nv_bfloat16* r0 = reinterpret_cast<const __nv_bfloat16*>(&rq[u][0]);
+                const __nv_bfloat16* r1 = reinterpret_cast<const __nv_bfloat16*>(&rq[u][1]);
+                const __nv_bfloat16* r2 = reinterpret_cast<const __nv_bfloat16*>(&rq[u][2]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)  // the three terms reconstruct the fp32 residual exactly
+                    v[u][e] += (__bfloat162float(r0[e]) + __bfloat162float(r1[e])) + __bfloat162float(r2[e]);
+            }
+            if (a.res_nchw != nullptr) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[u][e] += rn[u][e];
+            }
+            if (a.relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[u][e] = fmaxf(v[u][e], 0.f);
+            }
+            if (a.y_s3 != nullptr || a.y_split != nullptr) {
+                __align__(16) __nv_bfloat16 t0[8], t1[8], t2[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split3(v[u][e], t0[e], t1[e], t2[e]);
+                if (a.y_s3 != nullptr) {
+                    const size_t base = ((size_t)bg * 3 * Sp + pp[u]) * 8;
+                    *reinterpret_cast<uint4*>(a.y_s3 + base) = *reinterpret_cast<const uint4*>(t0);
+                    *reinterpret_cast<uint4*>(a.y_s3 + base + Sp * 8) = *reinterpret_cast<const uint4*>(t1);
+                    *reinterpret_cast<uint4*>(a.y_s3 + base + 2 * Sp * 8) = *reinterpret_cast<const uint4*>(t2);
+                }
+                if (a.y_split != nullptr) {
+                    const unsigned dz = p / hw, r = p - dz * hw, h = r / W, w = r - h * W;
+                    const unsigned q = ((dz & 1) << 2) | ((h & 1) << 1) | (w & 1);
+                    const size_t Hc = (H >> 1) + 2 * a.pad;  // `pad` spare CELL rows above / below (row bands)
+                    const size_t Sc = (size_t)(S >> 3) / (H >> 1) * Hc;
+                    const size_t cell = ((size_t)(dz >> 1) * Hc + (h >> 1) + a.pad) * (W >> 1) + (w >> 1);
+                    const size_t base = ((((size_t)b * 8 + q) * NG + g) * 3 * Sc + cell) * 8;
+                    *reinterpret_cast<uint4*>(a.y_split + base) = *reinterpret_cast<const uint4*>(t0);
+                    *reinterpret_cast<uint4*>(a.y_split + base + Sc * 8) = *reinterpret_cast<const uint4*>(t1);
+                    *reinterpret_cast<uint4*>(a.y_split + base + 2 * Sc * 8) = *reinterpret_cast<const uint4*>(t2);
+                }
+            }
+            if (a.y_nchw != nullptr) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a.y_nchw[((size_t)b * a.C + g * 8 + e) * S + p] = v[u][e];
+            }
         }
     }
+    (void)need_dhw;
 }
 
 
@@ -584,7 +613,7 @@ extern "C" int cmfb200_gn_apply_tc3_padded(const float* raw, int raw_is_c8f, con
                 "gn_apply_tc3: the parity-split copy needs even D, H, W");
     CMF_REQUIRE(pad >= 0 && (pad == 0 || (H > 0 && W > 0 && spatial % ((long long)H * W) == 0)),
                 "gn_apply_tc3: padded rows need H, W with spatial a multiple of H*W");
-    CMF_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && spatial > 0, "gn_apply_tc3: bad shape");
+    CMF_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && spatial > 0 && spatial < (1LL << 31), "gn_apply_tc3: bad shape");
     CMF_REQUIRE(gn_sums == nullptr || (gamma && beta && groups > 0 && C % groups == 0), "gn_apply_tc3: bad GroupNorm args");
     CMF_REQUIRE((long long)B * (C / 8) <= 65535, "gn_apply_tc3: B*C/8 exceeds the grid limit");
     GnTc3Args a;
@@ -594,8 +623,8 @@ extern "C" int cmfb200_gn_apply_tc3_padded(const float* raw, int raw_is_c8f, con
     a.y_split = reinterpret_cast<__nv_bfloat16*>(y_split_c8s3);
     a.C = C, a.cpg = gn_sums ? C / groups : 1, a.spatial = spatial, a.eps = eps, a.relu = relu, a.raw_c8f = raw_is_c8f;
     a.pad = pad, a.H = H, a.W = W;
-    long long bx = cdiv(spatial, 256 * 4);
-    if (bx > 4096) bx = 4096;
+    long long bx = cdiv(spatial, 256 * 4);  // 4 positions per thread, all loads of an iteration in flight together
+    if (bx > 8192) bx = 8192;
     dim3 grid((unsigned)bx, (unsigned)(B * (C / 8)));
     gn_apply_tc3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     CMF_LAUNCH_CHECK("gn_apply_tc3_kernel");
