@@ -470,7 +470,11 @@ def run_ours(args, rank, world, local_rank):
             roof = {"kernel": "conv_tc3_kernel + conv_tc3g_kernel (fp32-accurate convs on tcgen05: stride-1 2-D/3-D, stride-2, "
                               "transposed; %d launches/step = %.1f%% of the step)" % (tc_n, 100.0 * tc_ms * K / f["ms_eager"]),
                     "bound": "tensor", "achieved": alg, "peak": tpeak, "unit": "TFLOP/s", "frac": alg / tpeak,
-                    "traffic": None, "peak_source": "bf16_tflops_sustained, " + peak_src,
+                    "traffic": {"what": "dram read + write bytes per launch of the largest class (3-D 32->32 at full resolution, "
+                                        "7 of the launches), ncu --set full, profiles/r02_conv_tc3_final_ncu_raw.csv",
+                                "bytes": 318719232 + 184648192,
+                                "algorithmic_bytes": 32 * D * h * w * 6 + 32 * D * h * w * 4},
+                    "peak_source": "bf16_tflops_sustained, " + peak_src,
                     "algorithmic_flops_per_step": 2.0 * tc_macs,
                     "executed_bf16_mma": {"tflops": 6.0 * alg, "frac": 6.0 * alg / tpeak,
                                           "note": "every fp32 product = 6 exact bf16 MMAs (three-term split), so the "
@@ -492,7 +496,7 @@ def run_ours(args, rank, world, local_rank):
                     gbs = nbytes * n / (ms * 1e-3) / 1e9
                     tr = None
                     tpath = os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")
-                    if os.path.exists(tpath):
+                    if os.path.exists(tpath):  # dram read + write bytes per launch from the committed ncu --set full capture
                         tr = json.load(open(tpath)).get(name)
                     return {"kernel": name + " (K1)", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                             "frac": gbs / hbm_peak, "traffic": tr, "peak_source": "hbm_gbs, " + peak_src,

@@ -10,11 +10,11 @@
 // strict fp32 FMAs.
 //
 // A voxel-reduction GEMM: M x N = Cout x (Cin * taps) is small, K = all output positions is huge.  Register tiling on the
-// PACKED fp32 pipe: a CTA owns a 32 (co) x 32 (ci) x taps block of dW and a contiguous range of (b, d, h, 32-wide w
-// segment) "stages"; a thread keeps 2 co x (2 ci as one float2) x taps accumulators (54 float2 for a 3x3x3 kernel).
-// Stages are double-buffered with cp.async (zero fill = the conv padding and the ragged tails), input channels
-// interleaved in pairs and dy duplicated so that every FFMA2 operand pair is one aligned shared-memory word pair.
-// Partial blocks are added to dW with fp32 atomics (dW must be zero on entry).
+// fp32 pipe: a CTA owns a 32 (co) x 32 (ci) x taps block of dW and a contiguous range of (b, d, h, 32-wide w segment)
+// "stages"; warp = 4 output channels, lane = input channel, so a thread keeps 4 x taps accumulators (108 for a 3x3x3
+// kernel) and per group of 4 output positions does 4*4*taps FMAs for 16 broadcast dy loads + taps/3 * 6..9 x loads
+// (7:1 FMA per shared-memory load).  Stages are double-buffered with cp.async (zero fill = the conv padding and the
+// ragged tails).  Partial blocks are added to dW with fp32 atomics (dW must be zero on entry).
 #include "common.cuh"
 #include "conv_common.cuh"
 
@@ -23,6 +23,7 @@ namespace cmfb200 {
 namespace {
 
 constexpr int kWgThreads = 256;
+constexpr int kWgPitch = 36;  // floats per staged input row: bank-conflict-free for lane = channel (9*36 = 4 mod 32)
 
 template <int KD, int KHW, int STRIDE, int DIL>
 struct WgCfg {
@@ -30,14 +31,11 @@ struct WgCfg {
     static constexpr int ROWS = KD * KHW;                        // staged input rows per channel
     static constexpr int P = STRIDE == 1 ? 32 : 16;              // output positions per stage
     static constexpr int SPAN = (P - 1) * STRIDE + (KHW - 1) * DIL + 1;  // input columns a stage touches
-    // columns per staged row: the stride between two channel PAIRS (ROWS * PITCH * 2 floats) must be 4 mod 32 so that the
-    // 16 lanes of a half-warp (lane = channel pair) read 16-byte units from disjoint banks: 2 wavefronts per LDS.128
-    static constexpr int PITCH = ROWS == 3 ? 38 : 34;
-    static constexpr int X_FLOATS = 16 * ROWS * PITCH * 2;       // [16 channel pairs][ROWS][PITCH][2 channels]
-    static constexpr int DY_FLOATS = 32 * P * 2;                 // [32 co][P][value twice]: LDS gives the (g, g) pair of FFMA2
+    static constexpr int X_FLOATS = 32 * ROWS * kWgPitch;
+    static constexpr int DY_FLOATS = 32 * P;
     static constexpr int STAGE_FLOATS = X_FLOATS + DY_FLOATS;
     static constexpr int SMEM_BYTES = 2 * STAGE_FLOATS * 4;
-    static_assert(SPAN <= PITCH && (ROWS * PITCH * 2) % 32 == 4, "row pitch");
+    static_assert(SPAN <= kWgPitch, "stage does not fit the row pitch");
 };
 
 struct WgDims {
@@ -47,17 +45,12 @@ struct WgDims {
 
 }  // namespace
 
-// Thread = 2 output channels x one PAIR of input channels x all taps, accumulated as float2 (x: even channel, y: odd
-// channel) with the packed fp32 pipe (`__ffma2_rn` -> FFMA2: two IEEE fp32 FMAs per issue slot): per group of 4 output
-// positions 2*4*taps FFMA2 for 4 + 3*rows 128-bit shared-memory loads.  Warp = 4 output channels (two half-warps of 2)
-// x 32 input channels; 8 warps = the 32 x 32 block.
 template <int KD, int KHW, int STRIDE, int DIL>
 __global__ void __launch_bounds__(kWgThreads, 1)
     conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, const WgDims dm) {
     using G = WgCfg<KD, KHW, STRIDE, DIL>;
     extern __shared__ float smem_wg[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cpair = lane & 15, cosub = lane >> 4;
     const int ci_tiles = (dm.Cin + 31) / 32;
     const int co0 = (blockIdx.y / ci_tiles) * 32, ci0 = (blockIdx.y % ci_tiles) * 32;
     const int pad_hw = (KHW / 2) * DIL, pad_d = KD / 2;
@@ -76,7 +69,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
         const int b = (int)(r / dm.Do);
         const int wo0 = seg * G::P;
         const int wi0 = wo0 * STRIDE - pad_hw;
-        // input patch: [16 pairs][KD*KHW rows][SPAN][2] (4-byte copies: the row start is not 16-byte aligned in general)
+        // input patch: [32 ci][KD*KHW rows][SPAN] (4-byte copies: the row start is not 16-byte aligned in general)
         for (int i = threadIdx.x; i < 32 * G::ROWS * G::SPAN; i += kWgThreads) {
             const int col = i % G::SPAN;
             const int row = (i / G::SPAN) % G::ROWS;
@@ -87,24 +80,24 @@ __global__ void __launch_bounds__(kWgThreads, 1)
             const int wi = wi0 + col;
             const bool ok = (ci0 + c < dm.Cin) && di >= 0 && di < dm.D && hi >= 0 && hi < dm.H && wi >= 0 && wi < dm.W;
             const float* src = ok ? x + (((size_t)b * dm.Cin + ci0 + c) * dm.D + di) * in_plane + (size_t)hi * dm.W + wi : x;
-            cp_async_4_zfill(sx + ((((c >> 1) * G::ROWS + row) * G::PITCH + col) << 1) + (c & 1), src, ok);
+            cp_async_4_zfill(sx + (c * G::ROWS + row) * kWgPitch + col, src, ok);
         }
-        // dy segment: [32 co][P][2], every value stored twice
-        for (int i = threadIdx.x; i < 32 * G::P * 2; i += kWgThreads) {
-            const int p = (i >> 1) % G::P, c = (i >> 1) / G::P;
+        // dy segment: [32 co][P]
+        for (int i = threadIdx.x; i < 32 * G::P; i += kWgThreads) {
+            const int p = i % G::P, c = i / G::P;
             const bool ok = wo0 + p < dm.Wo;
             const float* src = ok ? dy + (((size_t)b * dm.Cout + co0 + c) * dm.Do + dz) * out_plane + (size_t)ho * dm.Wo + wo0 + p
                                   : dy;
-            cp_async_4_zfill(sdy + i, src, ok);
+            cp_async_4_zfill(sdy + c * G::P + p, src, ok);
         }
         cp_async_commit();
     };
 
-    float2 acc[2][G::TAPS];
+    float acc[4][G::TAPS];
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int t = 0; t < G::TAPS; ++t) acc[j][t] = make_float2(0.f, 0.f);
+        for (int t = 0; t < G::TAPS; ++t) acc[j][t] = 0.f;
 
     if (s_beg < s_end) stage_load(s_beg, 0);
     for (long long s = s_beg; s < s_end; ++s) {
@@ -116,52 +109,43 @@ __global__ void __launch_bounds__(kWgThreads, 1)
             cp_async_wait<0>();
         }
         __syncthreads();
-        const float* sx = smem_wg + buf * G::STAGE_FLOATS + cpair * G::ROWS * G::PITCH * 2;
-        const float* sdy = smem_wg + buf * G::STAGE_FLOATS + G::X_FLOATS + (warp * 4 + cosub * 2) * G::P * 2;
+        const float* sx = smem_wg + buf * G::STAGE_FLOATS + lane * G::ROWS * kWgPitch;
+        const float* sdy = smem_wg + buf * G::STAGE_FLOATS + G::X_FLOATS + warp * 4 * G::P;
 #pragma unroll 1
         for (int p0 = 0; p0 < G::P; p0 += 4) {
-            float2 g[2][4];
+            float g[4][4];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const float4 v0 = *reinterpret_cast<const float4*>(sdy + (j * G::P + p0) * 2);      // (g0,g0,g1,g1)
-                const float4 v1 = *reinterpret_cast<const float4*>(sdy + (j * G::P + p0) * 2 + 4);  // (g2,g2,g3,g3)
-                g[j][0] = make_float2(v0.x, v0.y), g[j][1] = make_float2(v0.z, v0.w);
-                g[j][2] = make_float2(v1.x, v1.y), g[j][3] = make_float2(v1.z, v1.w);
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(sdy + j * G::P + p0);  // warp-wide broadcast
+                g[j][0] = v.x, g[j][1] = v.y, g[j][2] = v.z, g[j][3] = v.w;
             }
             constexpr int NX = 3 * STRIDE + (KHW - 1) * DIL + 1;  // input columns of 4 outputs
-            constexpr int NX2 = (NX + 1) / 2;
+            constexpr int NX4 = (NX + 3) / 4;
 #pragma unroll
             for (int row = 0; row < G::ROWS; ++row) {
-                float2 xv[NX2 * 2];
+                float xv[NX4 * 4];
 #pragma unroll
-                for (int q = 0; q < NX2; ++q) {
-                    const float4 v = *reinterpret_cast<const float4*>(sx + (row * G::PITCH + p0 * STRIDE + 2 * q) * 2);
-                    xv[2 * q] = make_float2(v.x, v.y), xv[2 * q + 1] = make_float2(v.z, v.w);
+                for (int q = 0; q < NX4; ++q) {
+                    const float4 v = *reinterpret_cast<const float4*>(sx + row * kWgPitch + p0 * STRIDE + 4 * q);
+                    xv[4 * q] = v.x, xv[4 * q + 1] = v.y, xv[4 * q + 2] = v.z, xv[4 * q + 3] = v.w;
                 }
 #pragma unroll
                 for (int kw = 0; kw < KHW; ++kw)
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
+                    for (int j = 0; j < 4; ++j)
 #pragma unroll
                         for (int p = 0; p < 4; ++p)
-                            acc[j][row * KHW + kw] = __ffma2_rn(g[j][p], xv[p * STRIDE + kw * DIL], acc[j][row * KHW + kw]);
+                            acc[j][row * KHW + kw] = fmaf(g[j][p], xv[p * STRIDE + kw * DIL], acc[j][row * KHW + kw]);
             }
         }
         __syncthreads();
     }
+    if (ci0 + lane < dm.Cin) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int co = co0 + warp * 4 + cosub * 2 + j;
-        const int ci = ci0 + cpair * 2;
-        if (ci < dm.Cin) {
-            float* dst = dw + ((size_t)co * dm.Cin + ci) * G::TAPS;
+        for (int j = 0; j < 4; ++j) {
+            float* dst = dw + ((size_t)(co0 + warp * 4 + j) * dm.Cin + ci0 + lane) * G::TAPS;
 #pragma unroll
-            for (int t = 0; t < G::TAPS; ++t) atomicAdd(dst + t, acc[j][t].x);
-        }
-        if (ci + 1 < dm.Cin) {
-            float* dst = dw + ((size_t)co * dm.Cin + ci + 1) * G::TAPS;
-#pragma unroll
-            for (int t = 0; t < G::TAPS; ++t) atomicAdd(dst + t, acc[j][t].y);
+            for (int t = 0; t < G::TAPS; ++t) atomicAdd(dst + t, acc[j][t]);
         }
     }
 }
