@@ -706,8 +706,50 @@ class cmfsm(nn.Module):
     def forward_row_bands(self, left, right, gather=True):
         """Sharded inference of ONE pair over all ranks (every rank passes the same images).  Returns the three
         disparity maps ([B,1,H,W] when `gather`, else this rank's rows [B,1,H/world,W])."""
+        if self._graphs is not None and par.world() > 1:
+            with torch.cuda.device(left.device):
+                return self._bands_graphed(left, right, gather)
+        return self._bands_eager(left, right, gather)
+
+    def _bands_eager(self, left, right, gather):
         with ops.sums_pool():
-            return self._forward_row_bands_body(left, right, gather)
+            outs = self._forward_row_bands_body(left, right, gather)
+        par.band_fence(left.device)
+        return outs
+
+    def _bands_graphed(self, left, right, gather):
+        """enable_cuda_graph(): every rank captures its own band forward -- kernels, peer-memory halo copies and the
+        device-side signal barriers between them -- and replays it: the ~1500 host-side launches of a band forward become
+        one graph launch per rank.  Needs the peer-memory mailbox transport (NCCL point-to-point inside a capture hangs on
+        this stack); with NCCL transport the forward stays eager."""
+        fp = self._weights_fingerprint()
+        if self._graphs.get("weights") != fp:
+            self._graphs.clear()
+            self._graphs["weights"] = fp
+        key = ("bands", tuple(left.shape), left.device.index, self.conv_engine, par.world(), gather)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_l, static_r = left.float().clone(), right.float().clone()
+            for _ in range(2):  # packs weights, sizes the mailbox, fills the allocator pools
+                self._bands_eager(static_l, static_r, gather)
+            cap = par.mailbox_capacity(None, left.device)
+            if cap == 0:
+                self._graphs[key] = entry = "eager"
+            else:
+                torch.cuda.synchronize()
+                torch.distributed.barrier()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    outs = self._bands_eager(static_l, static_r, gather)
+                assert par.mailbox_capacity(None, left.device) == cap
+                self._graphs[key] = entry = (graph, static_l, static_r, outs)
+        if entry == "eager":
+            return self._bands_eager(left, right, gather)
+        graph, static_l, static_r, outs = entry
+        static_l.copy_(left)
+        static_r.copy_(right)
+        graph.replay()
+        return tuple(o.clone() for o in outs)
 
     def _forward_row_bands_body(self, left, right, gather):
         self._check(left, right, self.maxdisp)

@@ -13,6 +13,8 @@ Two sharding modes, both without any hidden collective:
   every GroupNorm needs the per-(sample,channel) sum / sum-of-squares summed over bands (`allreduce_gn_sums`),
   64-128 doubles per layer.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -116,6 +118,136 @@ def dp_train_step(model, optimizer, left, right, disparity, maxdisp=192):
     return float(total)
 
 
+# ------------------------------------------------------------------------------------------ peer-memory mailbox
+class _Mailbox:
+    """Symmetric-memory mailbox of the row-band forward (torch.distributed._symmetric_memory: CUDA VMM peer mappings over
+    NVLink + device-side signal barriers).  Every rank owns one buffer that all peers can read directly; an exchange is
+    "write my boundary rows into my buffer -> barrier -> copy the neighbours' rows out of THEIR buffers" -- no NCCL call, no
+    host synchronisation, and (unlike NCCL point-to-point) capturable in a CUDA graph.  Two slots alternate so that one
+    barrier per exchange suffices: the barrier of exchange k+1 orders every read of exchange k before the next write of
+    that slot."""
+
+    def __init__(self, group, nbytes, device):
+        import torch.distributed._symmetric_memory as sm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.cap = int(nbytes)
+        self.buf = sm.empty(2 * self.cap, dtype=torch.uint8, device=device)
+        self.hdl = sm.rendezvous(self.buf, self.group)
+        self.n, self.r = self.hdl.world_size, self.hdl.rank
+        self.k = 0
+
+    def slot(self):
+        self.k += 1
+        return (self.k & 1) * self.cap, self.k & 1
+
+    def mine(self, off, like):
+        nb = like.numel() * like.element_size()
+        return self.buf[off:off + nb].view(like.dtype).view(like.shape)
+
+    def peer(self, rank, off, like):
+        nb = like.numel() * like.element_size()
+        return self.hdl.get_buffer(rank, (nb,), torch.uint8, off).view(like.dtype).view(like.shape)
+
+    def barrier(self, channel):
+        self.hdl.barrier(channel=channel)
+
+
+_MAILBOX = {}
+
+
+def _align(nb):
+    return (nb + 255) & ~255
+
+
+def _mailbox(group, device, need):
+    """The mailbox of (group, device), grown (collectively: every rank sees the same shapes) when a message needs more;
+    None when peer memory is switched off (CMF_B200_BANDS_COMM=nccl) or unavailable."""
+    if os.environ.get("CMF_B200_BANDS_COMM", "symm") != "symm":
+        return None
+    key = (id(group), device.index)
+    mb = _MAILBOX.get(key)
+    if mb is False:
+        return None
+    if mb is None or mb.cap < need:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("the peer-memory mailbox must be sized by an eager warm-up pass before graph capture")
+        if mb is not None:  # growing: nobody may still be reading the old buffer
+            torch.cuda.synchronize(device)
+            dist.barrier(group=group)
+        try:
+            mb = _Mailbox(group, max(need, 1 << 22) if mb is None else max(need, 2 * mb.cap), device)
+        except Exception:  # no symmetric-memory support on this stack: NCCL send/recv + all-reduce instead
+            _MAILBOX[key] = False
+            return None
+        _MAILBOX[key] = mb
+    return mb
+
+
+def band_fence(device, group=None):
+    """End-of-forward fence of the peer-memory transport: one more barrier, so that every read of this forward's last
+    exchange has completed on every rank before the next forward (or the next replay of a captured graph, whose slot
+    sequence is baked in) writes that slot again.  Returns True when the mailbox transport is active."""
+    mb = _MAILBOX.get((id(group), device.index))
+    if not mb:
+        return False
+    _off, ch = mb.slot()
+    mb.barrier(ch)
+    return True
+
+
+def mailbox_capacity(group=None, device=None):
+    """Bytes per slot of the current mailbox (0 = none): lets a caller see whether a warm-up pass re-allocated it."""
+    mb = _MAILBOX.get((id(group), device.index if device is not None else torch.cuda.current_device()))
+    return mb.cap if mb else 0
+
+
+def _exchange(x, dim, pad_lo, n_up, n_dn, top, bottom, group):
+    """Core of the two halo functions.  Sends x[pad_lo : pad_lo+bottom] (my first rows) to the previous rank and my last
+    `top` rows to the next one; returns (rows received from the previous rank or None, from the next rank or None)."""
+    n, r = world(group), rank(group)
+    rows_hi = n_up  # index one past my last row along dim
+    up = x.narrow(dim, pad_lo, bottom) if bottom else None        # -> previous rank's bottom halo
+    dn = x.narrow(dim, rows_hi - top, top) if top else None      # -> next rank's top halo
+    mb = None
+    if x.is_cuda and n > 1:
+        nb_up = _align(up.numel() * up.element_size()) if up is not None else 0
+        nb_dn = _align(dn.numel() * dn.element_size()) if dn is not None else 0
+        mb = _mailbox(group, x.device, nb_up + nb_dn)
+    got_t = got_b = None
+    if n == 1:
+        return None, None
+    if mb is not None:
+        off, ch = mb.slot()
+        if up is not None and r > 0:
+            mb.mine(off, up).copy_(up)
+        if dn is not None and r < n - 1:
+            mb.mine(off + nb_up, dn).copy_(dn)
+        mb.barrier(ch)
+        if top and r > 0:
+            got_t = mb.peer(r - 1, off + nb_up, dn)   # the previous rank's "down" region (same shape as my own)
+        if bottom and r < n - 1:
+            got_b = mb.peer(r + 1, off, up)           # the next rank's "up" region
+        return got_t, got_b
+    ops = []
+    if r > 0:
+        if bottom:
+            ops.append(dist.P2POp(dist.isend, up.contiguous(), _peer(group, r - 1), group))
+        if top:
+            got_t = torch.empty_like(dn, memory_format=torch.contiguous_format)
+            ops.append(dist.P2POp(dist.irecv, got_t, _peer(group, r - 1), group))
+    if r < n - 1:
+        if top:
+            ops.append(dist.P2POp(dist.isend, dn.contiguous(), _peer(group, r + 1), group))
+        if bottom:
+            got_b = torch.empty_like(up, memory_format=torch.contiguous_format)
+            ops.append(dist.P2POp(dist.irecv, got_b, _peer(group, r + 1), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return got_t, got_b
+
+
 # ------------------------------------------------------------------------------------------ row bands
 def band_rows(h, n, r, multiple=4):
     """Rows [r0, r1) of a height-`h` volume owned by rank `r` of `n`; boundaries are multiples of `multiple`
@@ -134,33 +266,15 @@ def band_rows(h, n, r, multiple=4):
 def exchange_row_halo(x, top=1, bottom=1, dim=-2, group=None):
     """Return `x` extended along the row axis `dim` with `top` rows from the previous rank's bottom edge and
     `bottom` rows from the next rank's top edge (zeros at the image border = the conv's zero padding).
-
-    Grouped point-to-point send/recv: each rank posts at most 2 sends + 2 recvs (`batch_isend_irecv`), which
-    NCCL fuses into one launch."""
-    n, r = world(group), rank(group)
+    Transport: the peer-memory mailbox (`_Mailbox`) on CUDA tensors, NCCL/gloo grouped send/recv otherwise."""
     dim = dim % x.dim()
-    shape_t = list(x.shape)
-    shape_t[dim] = top
-    shape_b = list(x.shape)
-    shape_b[dim] = bottom
-    halo_t, halo_b = x.new_zeros(shape_t), x.new_zeros(shape_b)
-    if n > 1:
-        ops = []
-        rows = x.shape[dim]
-        if r > 0:
-            if bottom:
-                ops.append(dist.P2POp(dist.isend, x.narrow(dim, 0, bottom).contiguous(), _peer(group, r - 1), group))
-            if top:
-                ops.append(dist.P2POp(dist.irecv, halo_t, _peer(group, r - 1), group))
-        if r < n - 1:
-            if top:
-                ops.append(dist.P2POp(dist.isend, x.narrow(dim, rows - top, top).contiguous(), _peer(group, r + 1), group))
-            if bottom:
-                ops.append(dist.P2POp(dist.irecv, halo_b, _peer(group, r + 1), group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-    parts = ([halo_t] if top else []) + [x] + ([halo_b] if bottom else [])
+    got_t, got_b = _exchange(x, dim, 0, x.shape[dim], 0, top, bottom, group)
+    parts = []
+    if top:
+        parts.append(got_t if got_t is not None else x.new_zeros(x.narrow(dim, 0, top).shape))
+    parts.append(x)
+    if bottom:
+        parts.append(got_b if got_b is not None else x.new_zeros(x.narrow(dim, 0, bottom).shape))
     return torch.cat(parts, dim)
 
 
@@ -169,42 +283,37 @@ def fill_row_halo_(x, pad, top, bottom, dim=-3, group=None):
     along `dim` (ops.gn_apply_tc3(pad=...), ops.cost_volume_concat_c8s3(pad=...)): fills the `top` rows just above the
     band with the previous rank's bottom edge and the `bottom` rows just below with the next rank's top edge (zeros at
     the image border = the conv's zero padding).  Only the boundary rows move; the activation itself is never copied."""
-    n, r = world(group), rank(group)
     dim = dim % x.dim()
     rows = x.shape[dim] - 2 * pad
     if top > pad or bottom > pad:
         raise ValueError("halo (%d, %d) exceeds the %d spare rows" % (top, bottom, pad))
-    recv_t = recv_b = None
-    ops = []
-    if n > 1:
-        if r > 0:
-            if bottom:
-                ops.append(dist.P2POp(dist.isend, x.narrow(dim, pad, bottom).contiguous(), _peer(group, r - 1), group))
-            if top:
-                recv_t = torch.empty_like(x.narrow(dim, pad - top, top), memory_format=torch.contiguous_format)
-                ops.append(dist.P2POp(dist.irecv, recv_t, _peer(group, r - 1), group))
-        if r < n - 1:
-            if top:
-                ops.append(dist.P2POp(dist.isend, x.narrow(dim, pad + rows - top, top).contiguous(), _peer(group, r + 1), group))
-            if bottom:
-                recv_b = torch.empty_like(x.narrow(dim, pad + rows, bottom), memory_format=torch.contiguous_format)
-                ops.append(dist.P2POp(dist.irecv, recv_b, _peer(group, r + 1), group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+    got_t, got_b = _exchange(x, dim, pad, pad + rows, 0, top, bottom, group)
     if top:
         dst = x.narrow(dim, pad - top, top)
-        dst.copy_(recv_t) if recv_t is not None else dst.zero_()
+        dst.copy_(got_t) if got_t is not None else dst.zero_()
     if bottom:
         dst = x.narrow(dim, pad + rows, bottom)
-        dst.copy_(recv_b) if recv_b is not None else dst.zero_()
+        dst.copy_(got_b) if got_b is not None else dst.zero_()
     return x
 
 
 def allreduce_gn_sums(sums, group=None):
-    """Sum per-band GroupNorm statistics ([B,C,2] double: sum, sum of squares) over all bands, in place."""
-    if world(group) > 1:
+    """Sum per-band GroupNorm statistics ([B,C,2] double: sum, sum of squares) over all bands, in place.  Peer-memory
+    path: every rank publishes its sums, one barrier, every rank adds the n buffers in rank order (identical result on
+    every rank); otherwise one all-reduce."""
+    n = world(group)
+    if n == 1:
+        return sums
+    mb = _mailbox(group, sums.device, _align(sums.numel() * sums.element_size())) if sums.is_cuda else None
+    if mb is None:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        return sums
+    off, ch = mb.slot()
+    mb.mine(off, sums).copy_(sums)
+    mb.barrier(ch)
+    sums.copy_(mb.peer(0, off, sums))
+    for r in range(1, n):
+        sums.add_(mb.peer(r, off, sums))
     return sums
 
 
@@ -213,6 +322,13 @@ def gather_bands(x, dim=-2, group=None):
     n = world(group)
     if n == 1:
         return x
-    parts = [torch.empty_like(x) for _ in range(n)]
-    dist.all_gather(parts, x.contiguous(), group=group)
-    return torch.cat(parts, dim % x.dim())
+    x = x.contiguous()
+    mb = _mailbox(group, x.device, _align(x.numel() * x.element_size())) if x.is_cuda else None
+    if mb is None:
+        parts = [torch.empty_like(x) for _ in range(n)]
+        dist.all_gather(parts, x, group=group)
+        return torch.cat(parts, dim % x.dim())
+    off, ch = mb.slot()
+    mb.mine(off, x).copy_(x)
+    mb.barrier(ch)
+    return torch.cat([mb.peer(r, off, x) for r in range(n)], dim % x.dim())

@@ -24,7 +24,7 @@ def _port():
 def _torchrun(script, *args):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(_port()), os.path.join(ROOT, "tools", script)] + list(args)
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     return json.loads(lines[-1])
@@ -33,7 +33,15 @@ def _torchrun(script, *args):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_row_band_sharding_matches_single_gpu():
     rep = _torchrun("check_row_bands.py", "--height", "512", "--width", "512", "--steps", "1")
-    assert rep["world"] == 2 and rep["pred3_max_abs"] < 3e-2
+    # the same arithmetic per voxel, only the GroupNorm summation order can differ: measured 0.0 on the B200
+    assert rep["world"] == 2 and rep["pred3_max_abs"] < 1e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_row_band_forward_as_one_cuda_graph_per_rank():
+    """Peer-memory halo transport + CUDA-graph replay of the whole band forward: still bit-identical to one GPU."""
+    rep = _torchrun("check_row_bands.py", "--height", "512", "--width", "768", "--steps", "2", "--graph")
+    assert rep["world"] == 2 and rep["pred1_max_abs"] == 0.0 and rep["pred3_max_abs"] == 0.0, rep
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

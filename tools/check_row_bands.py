@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--maxdisp", type=int, default=192)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the band forward as one CUDA graph per rank")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -35,6 +36,8 @@ def main():
     g = torch.Generator().manual_seed(5)
     left = torch.rand(1, 3, args.height, args.width, generator=g).to(dev)
     right = torch.rand(1, 3, args.height, args.width, generator=g).to(dev)
+    if args.graph:
+        model.enable_cuda_graph(True)
     model.forward_row_bands(left, right)  # warm-up (kernel loading, NCCL connections)
     outs = model.forward_row_bands(left, right)  # second warm-up + result
     torch.cuda.synchronize()
