@@ -815,7 +815,7 @@ class cmfsm(nn.Module):
         if self._graphs.get("weights") != fp:
             self._graphs.clear()  # stale graphs replay stale packed weights: drop them all
             self._graphs["weights"] = fp
-        key = (tuple(left.shape), left.device.index, self.aggregation)
+        key = (tuple(left.shape), left.device.index, self.aggregation, self.conv_engine)
         entry = self._graphs.get(key)
         if entry is None:
             static_l, static_r = left.float().clone(), right.float().clone()
