@@ -582,6 +582,28 @@ class cmfsm(nn.Module):
 
     _BAND_PAD = 2  # spare rows above / below every C8S3 band activation (largest halo: dilation 2)
 
+    def _band_apply(self, raw, sums, gamma, beta, raw_c8f, **kw):
+        """gn_apply_tc3 for a band: the C8S3 result carries _BAND_PAD spare rows, and -- with the peer-memory transport --
+        its first / last _BAND_PAD rows are pushed by the SAME kernel into the neighbour ranks' mailboxes (NVLink stores):
+        the halo exchange of the consuming conv is then only a signal wait + a local copy (`par.fill_row_halo_`)."""
+        P = self._BAND_PAD
+        push = None
+        if kw.get("want_s3", True):
+            if raw_c8f:
+                shape = (raw.shape[0], raw.shape[1], 3) + tuple(raw.shape[2:-1])
+            else:
+                shape = (raw.shape[0], raw.shape[1] // 8, 3) + tuple(raw.shape[2:])
+            shape = shape[:-2] + (shape[-2] + 2 * P, shape[-1], 8)
+            if shape[-3] - 2 * P >= P:
+                push = par.reserve_halo_push(shape, P, len(shape) - 3, raw.device)
+        out = ops.gn_apply_tc3(raw, sums, gamma, beta, raw_c8f, pad=P, push=push.args() if push else None, **kw)
+        if push is not None:
+            # drain the slot right away (signal wait + local copy of the P rows each neighbour pushed): a mailbox slot
+            # is reused two exchanges later, and a residual-branch tensor may be consumed only after several layers
+            out[0]._halo_push = push
+            par.fill_row_halo_(out[0], P, P, P, dim=out[0].dim() - 3)
+        return out
+
     def _tc_band(self, block, x_s3, full_rows, res_s3=None, res_nchw=None, relu=False, want_s3=True, want_nchw=False):
         """Stride-1 conv (2-D or 3-D) + GroupNorm on a row band.  `x_s3` (and `res_s3`, and the C8S3 result) carry
         _BAND_PAD spare rows on both sides: the halo rows are received straight into them and the row-window conv_tc3
@@ -594,13 +616,13 @@ class cmfsm(nn.Module):
             par.fill_row_halo_(x_s3, P, d, d, dim=x_s3.dim() - 3)
         y, sums = ops.conv_tc3(x_s3, self._pack_tc3(conv), conv.dilation[0], True, row_off=P, out_rows=rows)
         sums = self._band_sums(sums, rows, full_rows)
-        return ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, True, res_s3=res_s3, res_nchw=res_nchw, relu=relu,
-                                want_s3=want_s3, want_nchw=want_nchw, pad=P)
+        return self._band_apply(y, sums, gn.weight, gn.bias, True, res_s3=res_s3, res_nchw=res_nchw, relu=relu,
+                                want_s3=want_s3, want_nchw=want_nchw)
 
     def _ffma2_band_to_s3(self, block, x_nchw, full_rows, relu=False):
         y, sums = self._conv2_band(block[0], x_nchw, True)
         sums = self._band_sums(sums, y.shape[2], full_rows)
-        return ops.gn_apply_tc3(y, sums, block[1].weight, block[1].bias, False, relu=relu, pad=self._BAND_PAD)[0]
+        return self._band_apply(y, sums, block[1].weight, block[1].bias, False, relu=relu)[0]
 
     def _features_band_tc3(self, both, r0, r1):
         fe = self.feature_extraction
@@ -636,7 +658,8 @@ class cmfsm(nn.Module):
         skip_nchw = o_nchw
         pooled = [par.gather_bands(p, dim=2) for p in ops.spp_pool(skip_nchw)]  # whole-image pooled maps (tiny)
         b1, b2, b3, b4 = [self._cg2(getattr(fe, "branch%d" % (i + 1))[1], p, relu=True) for i, p in enumerate(pooled)]
-        cat = ops.f32_to_c8s3(ops.spp_upsample_concat(raw_nchw, skip_nchw, b4, b3, b2, b1, full_rows=h, row_offset=r0), pad=P)
+        cat = self._band_apply(ops.spp_upsample_concat(raw_nchw, skip_nchw, b4, b3, b2, b1, full_rows=h, row_offset=r0), None,
+                               None, None, False)[0]
         o, _ = self._tc_band(fe.lastconv[0], cat, h, relu=True)
         feat, _ = ops.conv_tc3(o, self._pack_tc3(fe.lastconv[2]), 1, False, out_nchw=True, row_off=P,
                                out_rows=o.shape[-3] - 2 * P)
@@ -646,8 +669,8 @@ class cmfsm(nn.Module):
         """GroupNorm (+residual) (+ReLU) of a band's raw C8F volume with the statistics of the WHOLE volume; the C8S3 /
         parity-split results carry _BAND_PAD spare (cell) rows.  Returns (C8S3, NCDHW, parity-split), each or None."""
         sums = self._band_sums(sums, y.shape[-3], full_rows)
-        out = ops.gn_apply_tc3(y, sums, gn.weight, gn.bias, True, res_nchw=res_nchw, relu=relu, want_s3=s3, want_nchw=nchw,
-                               want_split=split, pad=self._BAND_PAD)
+        out = self._band_apply(y, sums, gn.weight, gn.bias, True, res_nchw=res_nchw, relu=relu, want_s3=s3, want_nchw=nchw,
+                               want_split=split)
         return out if split else out + (None,)
 
     def _hourglass_band_tc3(self, hg, x_split, presqu, postsqu, resid, h, next_split):

@@ -790,10 +790,12 @@ def deconv_tc3(x_s3, packed, Cout, want_stats=True, pad=0):
 
 
 def gn_apply_tc3(raw, sums, gamma, beta, raw_c8f, res_s3=None, res_nchw=None, relu=False, want_s3=True, want_nchw=False,
-                 groups=GN_GROUPS, eps=GN_EPS, pad=0, want_split=False):
+                 groups=GN_GROUPS, eps=GN_EPS, pad=0, want_split=False, push=None):
     """GroupNorm (+residual) (+ReLU) of the tc3 pipeline.  raw: C8F (raw_c8f) or NCHW/NCDHW fp32; the result is returned
     as (C8S3 or None, NCHW fp32 or None).  sums=None: layout conversion / three-term split only.
-    Row bands: with `pad` the C8S3 result (and `res_s3`) carry `pad` halo rows above and below (left un-written)."""
+    Row bands: with `pad` the C8S3 result (and `res_s3`) carry `pad` halo rows above and below (left un-written);
+    `push` = (up, dn, rows): bf16 landing buffers IN THE NEIGHBOUR RANKS' memory (or None) that receive the first / last
+    `rows` rows of the C8S3 result -- the next conv's halo exchange fused into this kernel."""
     _req(raw, res_nchw)
     _req(res_s3, dtype=BF16)
     if sums is not None:
@@ -821,7 +823,9 @@ def gn_apply_tc3(raw, sums, gamma, beta, raw_c8f, res_s3=None, res_nchw=None, re
                                                            _p(gamma) if sums is not None else None,
                                                            _p(beta) if sums is not None else None, _p(res_s3), _p(res_nchw),
                                                            _p(y_s3), _p(y_nchw), B, C, groups, spatial, eps, int(relu), pad,
-                                                           sp[-2], sp[-1], _p(y_split), _stream()), "gn_apply_tc3")
+                                                           sp[-2], sp[-1], _p(y_split), _p(push[0]) if push else None,
+                                                           _p(push[1]) if push else None, push[2] if push else 0,
+                                                           _stream()), "gn_apply_tc3")
     if want_split:
         return y_s3, y_nchw, y_split
     return y_s3, y_nchw

@@ -141,13 +141,20 @@ class _Mailbox:
         self.k += 1
         return (self.k & 1) * self.cap, self.k & 1
 
-    def mine(self, off, like):
-        nb = like.numel() * like.element_size()
-        return self.buf[off:off + nb].view(like.dtype).view(like.shape)
+    @staticmethod
+    def _nbytes(shape, dtype):
+        n = torch.empty(0, dtype=dtype).element_size()
+        for v in shape:
+            n *= v
+        return n
 
-    def peer(self, rank, off, like):
-        nb = like.numel() * like.element_size()
-        return self.hdl.get_buffer(rank, (nb,), torch.uint8, off).view(like.dtype).view(like.shape)
+    def mine(self, off, like=None, shape=None, dtype=None):
+        shape, dtype = (like.shape, like.dtype) if like is not None else (shape, dtype)
+        return self.buf[off:off + self._nbytes(shape, dtype)].view(dtype).view(shape)
+
+    def peer(self, rank, off, like=None, shape=None, dtype=None):
+        shape, dtype = (like.shape, like.dtype) if like is not None else (shape, dtype)
+        return self.hdl.get_buffer(rank, (self._nbytes(shape, dtype),), torch.uint8, off).view(dtype).view(shape)
 
     def barrier(self, channel):
         self.hdl.barrier(channel=channel)
@@ -182,6 +189,44 @@ def _mailbox(group, device, need):
             return None
         _MAILBOX[key] = mb
     return mb
+
+
+class HaloPush:
+    """A reserved mailbox slot into which the PRODUCING kernel (gn_apply_tc3) pushes a band's boundary rows: `up` / `dn`
+    are bf16 views of the landing regions in the previous / next rank's mailbox (peer memory), `rows` rows each.  The
+    consumer side (`fill_row_halo_`) only waits on the slot's barrier and copies out of ITS OWN mailbox."""
+
+    def __init__(self, mb, off, ch, nb, rows_shape, dim, group):
+        self.mb, self.off, self.ch, self.nb, self.shape, self.dim, self.done = mb, off, ch, nb, rows_shape, dim, False
+        self.k = mb.k  # exchange counter at reservation: the slot is overwritten two exchanges later
+        n, r = mb.n, mb.r
+        # my TOP rows land in rank r-1's "from next" region (off + nb); my BOTTOM rows in rank r+1's "from previous" (off)
+        self.up = mb.peer(r - 1, off + nb, shape=rows_shape, dtype=torch.bfloat16) if r > 0 else None
+        self.dn = mb.peer(r + 1, off, shape=rows_shape, dtype=torch.bfloat16) if r < n - 1 else None
+        self.rows = rows_shape[dim]
+
+    def args(self):
+        return (self.up, self.dn, self.rows)
+
+
+def reserve_halo_push(full_shape, pad, dim, device, group=None):
+    """Reserve the next mailbox slot for a C8S3 band activation of (padded) shape `full_shape` about to be produced by
+    gn_apply_tc3; returns a HaloPush (its `.args()` go to the kernel) or None when peer memory is not in use."""
+    n = world(group)
+    if n == 1:
+        return None
+    dim = dim % len(full_shape)
+    rows_shape = list(full_shape)
+    rows_shape[dim] = pad
+    nelem = 1
+    for v in rows_shape:
+        nelem *= v
+    nb = _align(nelem * 2)
+    mb = _mailbox(group, device, 2 * nb)
+    if mb is None:
+        return None
+    off, ch = mb.slot()
+    return HaloPush(mb, off, ch, nb, tuple(rows_shape), dim, group)
 
 
 def band_fence(device, group=None):
@@ -287,6 +332,20 @@ def fill_row_halo_(x, pad, top, bottom, dim=-3, group=None):
     rows = x.shape[dim] - 2 * pad
     if top > pad or bottom > pad:
         raise ValueError("halo (%d, %d) exceeds the %d spare rows" % (top, bottom, pad))
+    push = getattr(x, "_halo_push", None)
+    if push is not None:  # the producing kernel already pushed `pad` boundary rows to the neighbours: wait + local copy
+        if not push.done:
+            mb, n, r = push.mb, push.mb.n, push.mb.r
+            if mb.k - push.k >= 2:
+                raise RuntimeError("halo push consumed too late: its mailbox slot has been reused (%d exchanges ago)"
+                                   % (mb.k - push.k))
+            mb.barrier(push.ch)
+            like = x.narrow(dim, 0, pad)
+            lo, hi = x.narrow(dim, 0, pad), x.narrow(dim, pad + rows, pad)
+            lo.copy_(mb.mine(push.off, like)) if r > 0 else lo.zero_()             # from the previous rank's bottom rows
+            hi.copy_(mb.mine(push.off + push.nb, like)) if r < n - 1 else hi.zero_()  # from the next rank's top rows
+            push.done = True
+        return x
     got_t, got_b = _exchange(x, dim, pad, pad + rows, 0, top, bottom, group)
     if top:
         dst = x.narrow(dim, pad - top, top)

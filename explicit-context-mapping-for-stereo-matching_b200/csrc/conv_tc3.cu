@@ -337,6 +337,11 @@ struct GnTc3Args {
     float eps;
     int relu, raw_c8f;
     int pad, H, W;  // row bands: y_s3 / res_s3 carry `pad` extra rows above and below the H rows (0 = dense)
+    // row bands, fused halo push: the first / last `push_rows` rows of the C8S3 result are ALSO stored into the neighbour
+    // ranks' landing buffers (peer-mapped memory over NVLink), dense [B*C/8][3][D][push_rows][W][8]; either may be null
+    __nv_bfloat16* push_up;
+    __nv_bfloat16* push_dn;
+    int push_rows;
 };
 
 __device__ __forceinline__ void split3(float v, __nv_bfloat16& t0, __nv_bfloat16& t1, __nv_bfloat16& t2) {
@@ -346,6 +351,7 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& t0, __nv_bfloat16
     t2 = __float2bfloat16_rn(r1 - __bfloat162float(t1));
 }
 
+template <bool PUSH>
 __global__ void __launch_bounds__(256, 4) gn_apply_tc3_kernel(const GnTc3Args a) {
     __shared__ float s_scale[8], s_shift[8];
     const int bg = blockIdx.y;  // b * C/8 + g
@@ -449,6 +455,23 @@ __global__ void __launch_bounds__(256, 4) gn_apply_tc3_kernel(const GnTc3Args a)
                     *reinterpret_cast<uint4*>(a.y_s3 + base) = *reinterpret_cast<const uint4*>(t0);
                     *reinterpret_cast<uint4*>(a.y_s3 + base + Sp * 8) = *reinterpret_cast<const uint4*>(t1);
                     *reinterpret_cast<uint4*>(a.y_s3 + base + 2 * Sp * 8) = *reinterpret_cast<const uint4*>(t2);
+                    if (PUSH && a.push_rows > 0) {  // boundary rows go straight to the neighbours (stores over NVLink)
+                        const unsigned dz = p / hw, r = p - dz * hw, h = r / W, w = r - h * W;
+                        const unsigned pr = (unsigned)a.push_rows;
+                        const size_t Ss = (size_t)(S / H) * pr;  // positions of a pushed (group, term) plane
+                        if (a.push_up != nullptr && h < pr) {
+                            const size_t q = ((size_t)bg * 3 * Ss + ((size_t)dz * pr + h) * W + w) * 8;
+                            *reinterpret_cast<uint4*>(a.push_up + q) = *reinterpret_cast<const uint4*>(t0);
+                            *reinterpret_cast<uint4*>(a.push_up + q + Ss * 8) = *reinterpret_cast<const uint4*>(t1);
+                            *reinterpret_cast<uint4*>(a.push_up + q + 2 * Ss * 8) = *reinterpret_cast<const uint4*>(t2);
+                        }
+                        if (a.push_dn != nullptr && h + pr >= H) {
+                            const size_t q = ((size_t)bg * 3 * Ss + ((size_t)dz * pr + (h + pr - H)) * W + w) * 8;
+                            *reinterpret_cast<uint4*>(a.push_dn + q) = *reinterpret_cast<const uint4*>(t0);
+                            *reinterpret_cast<uint4*>(a.push_dn + q + Ss * 8) = *reinterpret_cast<const uint4*>(t1);
+                            *reinterpret_cast<uint4*>(a.push_dn + q + 2 * Ss * 8) = *reinterpret_cast<const uint4*>(t2);
+                        }
+                    }
                 }
                 if (a.y_split != nullptr) {
                     const unsigned dz = p / hw, r = p - dz * hw, h = r / W, w = r - h * W;
@@ -606,8 +629,11 @@ extern "C" int cmfb200_conv_tc3_fwd(const void* x_c8s3, const void* packed_w, fl
 extern "C" int cmfb200_gn_apply_tc3_padded(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma,
                                            const float* beta, const void* residual_c8s3, const float* residual_nchw,
                                            void* y_c8s3, float* y_nchw, int B, int C, int groups, long long spatial,
-                                           float eps, int relu, int pad, int H, int W, void* y_split_c8s3, void* stream) {
+                                           float eps, int relu, int pad, int H, int W, void* y_split_c8s3, void* push_up,
+                                           void* push_dn, int push_rows, void* stream) {
     CMF_REQUIRE(raw && (y_c8s3 || y_nchw || y_split_c8s3), "gn_apply_tc3: null pointer");
+    CMF_REQUIRE(push_rows >= 0 && (push_rows == 0 || (y_c8s3 && H >= push_rows && W > 0)),
+                "gn_apply_tc3: the halo push needs the C8S3 output and push_rows <= H");
     CMF_REQUIRE(y_split_c8s3 == nullptr || (H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && spatial % ((long long)H * W) == 0 &&
                                             (spatial / ((long long)H * W)) % 2 == 0),
                 "gn_apply_tc3: the parity-split copy needs even D, H, W");
@@ -621,12 +647,17 @@ extern "C" int cmfb200_gn_apply_tc3_padded(const float* raw, int raw_is_c8f, con
     a.res_s3 = reinterpret_cast<const __nv_bfloat16*>(residual_c8s3), a.res_nchw = residual_nchw;
     a.y_s3 = reinterpret_cast<__nv_bfloat16*>(y_c8s3), a.y_nchw = y_nchw;
     a.y_split = reinterpret_cast<__nv_bfloat16*>(y_split_c8s3);
+    a.push_up = reinterpret_cast<__nv_bfloat16*>(push_up), a.push_dn = reinterpret_cast<__nv_bfloat16*>(push_dn);
+    a.push_rows = (push_up || push_dn) ? push_rows : 0;
     a.C = C, a.cpg = gn_sums ? C / groups : 1, a.spatial = spatial, a.eps = eps, a.relu = relu, a.raw_c8f = raw_is_c8f;
     a.pad = pad, a.H = H, a.W = W;
     long long bx = cdiv(spatial, 256 * 4);  // 4 positions per thread, all loads of an iteration in flight together
     if (bx > 8192) bx = 8192;
     dim3 grid((unsigned)bx, (unsigned)(B * (C / 8)));
-    gn_apply_tc3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    if (a.push_rows > 0)
+        gn_apply_tc3_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else
+        gn_apply_tc3_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     CMF_LAUNCH_CHECK("gn_apply_tc3_kernel");
     return CMFB200_OK;
 }
@@ -636,7 +667,7 @@ extern "C" int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const doub
                                     void* y_c8s3, float* y_nchw, int B, int C, int groups, long long spatial, float eps,
                                     int relu, void* stream) {
     return cmfb200_gn_apply_tc3_padded(raw, raw_is_c8f, gn_sums, gamma, beta, residual_c8s3, residual_nchw, y_c8s3, y_nchw, B,
-                                       C, groups, spatial, eps, relu, 0, 0, 0, nullptr, stream);
+                                       C, groups, spatial, eps, relu, 0, 0, 0, nullptr, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int cmfb200_cost_volume_concat_c8s3_padded(const float* L, const float* R, void* cost_c8s3, int B, int C, int h,

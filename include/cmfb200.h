@@ -268,7 +268,10 @@ int cmfb200_conv_tc3_rows_fwd(const void* x_c8s3, const void* packed_w, float* y
 int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma, const float* beta,
                          const void* residual_c8s3, const float* residual_nchw, void* y_c8s3, float* y_nchw, int B,
                          int C, int groups, long long spatial, float eps, int relu, void* stream);
-/* y_split_c8s3 (optional): the result ALSO as the parity-split copy [B][8][C/8][3][D/2][H/2][W/2][8] that the stride-2
+/* push_up / push_dn (optional, row bands): DEVICE POINTERS INTO THE NEIGHBOUR RANKS' MEMORY (peer-mapped over NVLink): the
+ * first / last push_rows rows of the C8S3 result are also stored there, dense [B*C/8][3][D][push_rows][W][8] -- the halo
+ * exchange of the next conv is fused into this kernel's epilogue (the consumer only waits on a signal and copies locally).
+ * y_split_c8s3 (optional): the result ALSO as the parity-split copy [B][8][C/8][3][D/2][H/2][W/2][8] that the stride-2
  * tensor-core conv reads (D, H, W even; H and W must then be passed).
  * Row-band forms: y_c8s3 / residual_c8s3 (and the K1 output) carry `pad` extra rows above and below the H rows of every
  * depth plane ([...][D][H + 2 pad][W][8]); the kernels fill the H interior rows, the halo rows are filled by the halo
@@ -276,7 +279,7 @@ int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const double* gn_sums
 int cmfb200_gn_apply_tc3_padded(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma,
                                 const float* beta, const void* residual_c8s3, const float* residual_nchw, void* y_c8s3,
                                 float* y_nchw, int B, int C, int groups, long long spatial, float eps, int relu, int pad,
-                                int H, int W, void* y_split_c8s3, void* stream);
+                                int H, int W, void* y_split_c8s3, void* push_up, void* push_dn, int push_rows, void* stream);
 int cmfb200_cost_volume_concat_c8s3_padded(const float* L, const float* R, void* cost_c8s3, int B, int C, int h, int w,
                                            int D, int pad, void* stream);
 /* K1 written directly as C8S3 (cmfsm.py:667-682): cost [B][2C/8][3][D][h][w][8] bf16; the three terms of an element
