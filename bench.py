@@ -444,7 +444,10 @@ def run_ours(args, rank, world, local_rank):
         model.enable_cuda_graph(False)
         del model
         torch.cuda.empty_cache()
-        sharded = sharded_legs(args, rank, world, dev, barrier)
+        try:
+            sharded = sharded_legs(args, rank, world, dev, barrier)
+        except Exception as e:  # keep the headline line even if a sharded leg fails (it is reported, not hidden)
+            sharded = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
     if rank == 0:
         hbm_peak, tpeak, peak_src = peaks()

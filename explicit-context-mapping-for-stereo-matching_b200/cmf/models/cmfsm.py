@@ -862,6 +862,8 @@ class cmfsm(nn.Module):
     # -------------------------------------------------------------------------------- forward
     def forward(self, left, right):
         self._check(left, right, self.maxdisp)
+        if self.conv_engine not in ("tc3", "ffma"):
+            raise ValueError("conv_engine must be 'tc3' or 'ffma', got %r" % (self.conv_engine,))
         if self._graphs is not None and not torch.is_grad_enabled():
             with torch.cuda.device(left.device):
                 return self._forward_graphed(left, right)
