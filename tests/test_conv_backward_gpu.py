@@ -26,7 +26,11 @@ def _autograd(fn, x, w):
 
 
 @pytest.mark.parametrize("B,Cin,Cout,D,H,W,stride", [(1, 32, 32, 4, 10, 40, 1), (2, 64, 32, 3, 9, 33, 1), (1, 64, 64, 4, 8, 20, 1),
-                                                    (1, 32, 64, 4, 12, 36, 2), (2, 64, 64, 6, 8, 20, 2)])
+                                                    (1, 32, 64, 4, 12, 36, 2), (2, 64, 64, 6, 8, 20, 2),
+                                                    # row pitches that are multiples of 16 bytes: the TMA-staged wgrad
+                                                    # (the third one walks the four-deep ring twice per CTA)
+                                                    (1, 32, 64, 4, 12, 40, 2), (1, 64, 32, 5, 7, 72, 1),
+                                                    (2, 32, 32, 12, 24, 128, 1)])
 def test_conv3d_backward(B, Cin, Cout, D, H, W, stride):
     from cmf_b200 import ops
 
@@ -38,7 +42,7 @@ def test_conv3d_backward(B, Cin, Cout, D, H, W, stride):
     assert _rel(got_dx, dx) < 1e-5 and _rel(got_dw, dw) < 1e-5, (_rel(got_dx, dx), _rel(got_dw, dw))
 
 
-@pytest.mark.parametrize("B,Cin,Cout,D,H,W", [(1, 64, 64, 2, 5, 18), (2, 64, 32, 3, 6, 10)])
+@pytest.mark.parametrize("B,Cin,Cout,D,H,W", [(1, 64, 64, 2, 5, 18), (2, 64, 32, 3, 6, 10), (1, 64, 32, 3, 6, 20)])
 def test_deconv3d_backward(B, Cin, Cout, D, H, W):
     from cmf_b200 import ops
 
@@ -53,7 +57,10 @@ def test_deconv3d_backward(B, Cin, Cout, D, H, W):
 @pytest.mark.parametrize("B,Cin,Cout,H,W,k,stride,dil", [
     (2, 32, 32, 20, 44, 3, 1, 1), (1, 64, 128, 9, 33, 3, 1, 1), (1, 128, 128, 12, 20, 3, 1, 2), (1, 320, 128, 8, 16, 3, 1, 1),
     (2, 32, 32, 16, 40, 3, 2, 1), (1, 32, 64, 12, 36, 3, 2, 1), (1, 32, 64, 12, 36, 1, 2, 1), (1, 64, 128, 7, 19, 1, 1, 1),
-    (2, 128, 32, 5, 9, 1, 1, 1), (1, 3, 32, 18, 34, 3, 1, 1), (4, 128, 32, 1, 2, 1, 1, 1)])
+    (2, 128, 32, 5, 9, 1, 1, 1), (1, 3, 32, 18, 34, 3, 1, 1), (4, 128, 32, 1, 2, 1, 1, 1),
+    # 16-byte row pitches (TMA-staged wgrad): every kernel family, a 3-channel input, a ring that wraps
+    (1, 32, 64, 12, 40, 1, 2, 1), (1, 64, 128, 7, 24, 1, 1, 1), (1, 3, 32, 18, 36, 3, 1, 1), (1, 128, 128, 12, 40, 3, 1, 2),
+    (4, 32, 32, 128, 256, 3, 1, 1), (2, 32, 64, 64, 136, 3, 2, 1)])
 def test_conv2d_backward(B, Cin, Cout, H, W, k, stride, dil):
     from cmf_b200 import ops
 
