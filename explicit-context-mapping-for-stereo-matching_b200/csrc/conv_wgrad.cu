@@ -181,7 +181,7 @@ struct WgTmaCfg {
     static constexpr int TAIL_FLOATS = TAIL ? G::ROWS * 32 * 4 : 0;  // [kd][kh][ci][4]
     static constexpr int DY_FLOATS = 32 * G::P;                  // [co][P]
     static constexpr int STAGE_FLOATS = X_FLOATS + TAIL_FLOATS + DY_FLOATS;
-    static constexpr int SMEM_BYTES = kWgRing * STAGE_FLOATS * 4 + 128 + 64;
+    static constexpr int SMEM_BYTES = kWgRing * STAGE_FLOATS * 4 + 64;
     static_assert((X_FLOATS * 4) % 128 == 0 && (TAIL_FLOATS * 4) % 128 == 0 && (STAGE_FLOATS * 4) % 128 == 0,
                   "TMA destinations are 128-byte aligned");
     static_assert((BOX_H * 32 * kWgPitch * 4) % 128 == 0 && (BOX_H * 32 * 16) % 128 == 0, "per-row boxes stay aligned");
@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(kWgThreads, KD == 1 ? 2 : 1)  // 2-D tiles kee
                           const __grid_constant__ CUtensorMap tm_dy, float* __restrict__ dw, const WgDims dm) {
     using G = WgCfg<KD, KHW, STRIDE, DIL>;
     using T = WgTmaCfg<KD, KHW, STRIDE, DIL>;
-    extern __shared__ uint8_t smem_wg_raw[];
-    float* ring = reinterpret_cast<float*>(((uintptr_t)smem_wg_raw + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(128) float smem_wg_ring[];  // no static shared memory: the window starts 1 KB-aligned
+    float* ring = smem_wg_ring;
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + kWgRing * T::STAGE_FLOATS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ci_tiles = (dm.Cin + 31) / 32;
