@@ -321,7 +321,10 @@ static int launch_wgrad(const float* x, const float* dy, float* dw, WgDims dm, c
     CMF_CUDA(cudaGetDevice(&dev));
     CMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int tiles = (dm.Cout / 32) * (int)cdiv(dm.Cin, 32);
-    long long gx = (2LL * sms + tiles - 1) / tiles;  // ~2 waves of one-CTA-per-SM blocks over all (co, ci) tiles
+    // 2 * SMs blocks over all (co, ci) tiles, rounded DOWN: the 2-D TMA kernels run two CTAs per SM, so the grid is one
+    // full wave (a 19 x 16 grid on 296 slots left 8 blocks for a second wave and doubled the kernel time); the 3-D
+    // kernels (one CTA per SM) run it as two waves.
+    long long gx = 2LL * sms / tiles;
     if (gx > dm.stages) gx = dm.stages;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)tiles);
