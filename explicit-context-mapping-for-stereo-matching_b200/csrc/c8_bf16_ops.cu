@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) cost_volume_c8_bf16_kernel(const float* _
 }
 
 // GroupNorm apply on C8/bf16 (+ residual C8/bf16) (+ ReLU); one CTA column per (b, chunk)
-__global__ void __launch_bounds__(256) gn_apply_c8_bf16_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(256, 3) gn_apply_c8_bf16_kernel(const __nv_bfloat16* __restrict__ x,
                                                                const double* __restrict__ sums,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta,
@@ -112,37 +112,55 @@ __global__ void __launch_bounds__(256) gn_apply_c8_bf16_kernel(const __nv_bfloat
         sh[j] = sshift[j];
     }
     const size_t base = (size_t)blockIdx.y * spatial;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < spatial; i += (long long)gridDim.x * blockDim.x) {
-        uint4 raw = *reinterpret_cast<const uint4*>(x + (base + i) * 8);
-        const __nv_bfloat162* in = reinterpret_cast<const __nv_bfloat162*>(&raw);
-        uint4 rraw = make_uint4(0, 0, 0, 0);
-        if (residual) rraw = *reinterpret_cast<const uint4*>(residual + (base + i) * 8);
-        const __nv_bfloat162* rin = reinterpret_cast<const __nv_bfloat162*>(&rraw);
-        __nv_bfloat162 out[4];
+    // four independent 16-byte loads (+ residual) in flight per thread: the pass is pure HBM streaming
+    constexpr int U = 4;
+    const int stride = (int)(gridDim.x * blockDim.x), n_sp = (int)spatial;  // spatial < 2^31 (checked by the entry point)
+    const __nv_bfloat16* xb = x + base * 8;
+    const __nv_bfloat16* rb = residual ? residual + base * 8 : nullptr;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_sp; i0 += U * stride) {
+        uint4 raw[U], rraw[U];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float f0 = fmaf(__low2float(in[e]), sc[2 * e], sh[2 * e]);
-            float f1 = fmaf(__high2float(in[e]), sc[2 * e + 1], sh[2 * e + 1]);
-            if (residual) {
-                f0 += __low2float(rin[e]);
-                f1 += __high2float(rin[e]);
-            }
-            if (relu) {
-                f0 = fmaxf(f0, 0.f);
-                f1 = fmaxf(f1, 0.f);
-            }
-            out[e] = __floats2bfloat162_rn(f0, f1);
-            if (y_f32 != nullptr) {  // un-rounded fp32 [B][C][D][H][W] copy (input of the fp32 classifier tail)
-                y_f32[((size_t)b * C + chunk * 8 + 2 * e) * spatial + i] = f0;
-                y_f32[((size_t)b * C + chunk * 8 + 2 * e + 1) * spatial + i] = f1;
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * stride;
+            raw[u] = rraw[u] = make_uint4(0, 0, 0, 0);
+            if (i < n_sp) {
+                raw[u] = *reinterpret_cast<const uint4*>(xb + (size_t)i * 8);
+                if (rb) rraw[u] = *reinterpret_cast<const uint4*>(rb + (size_t)i * 8);
             }
         }
-        if (y != nullptr) *reinterpret_cast<uint4*>(y + (base + i) * 8) = *reinterpret_cast<const uint4*>(out);
-        if (y_split != nullptr) {  // parity-split copy for a stride-2 consumer: [B][8][C/8][D/2][H/2][W/2][8]
-            const int w = (int)(i % W), h = (int)((i / W) % H), d = (int)(i / ((long long)W * H));
-            const int par = ((d & 1) << 2) | ((h & 1) << 1) | (w & 1);
-            const size_t dst = (((((size_t)b * 8 + par) * nc + chunk) * (D >> 1) + (d >> 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
-            *reinterpret_cast<uint4*>(y_split + dst * 8) = *reinterpret_cast<const uint4*>(out);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * stride;
+            if (i >= n_sp) break;
+            const __nv_bfloat162* in = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+            const __nv_bfloat162* rin = reinterpret_cast<const __nv_bfloat162*>(&rraw[u]);
+            __nv_bfloat162 out[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float f0 = fmaf(__low2float(in[e]), sc[2 * e], sh[2 * e]);
+                float f1 = fmaf(__high2float(in[e]), sc[2 * e + 1], sh[2 * e + 1]);
+                if (residual) {
+                    f0 += __low2float(rin[e]);
+                    f1 += __high2float(rin[e]);
+                }
+                if (relu) {
+                    f0 = fmaxf(f0, 0.f);
+                    f1 = fmaxf(f1, 0.f);
+                }
+                out[e] = __floats2bfloat162_rn(f0, f1);
+                if (y_f32 != nullptr) {  // un-rounded fp32 [B][C][D][H][W] copy (input of the fp32 classifier tail)
+                    y_f32[((size_t)b * C + chunk * 8 + 2 * e) * spatial + i] = f0;
+                    y_f32[((size_t)b * C + chunk * 8 + 2 * e + 1) * spatial + i] = f1;
+                }
+            }
+            if (y != nullptr) *reinterpret_cast<uint4*>(y + (base + i) * 8) = *reinterpret_cast<const uint4*>(out);
+            if (y_split != nullptr) {  // parity-split copy for a stride-2 consumer: [B][8][C/8][D/2][H/2][W/2][8]
+                const int w = i % W, h = (i / W) % H, d = i / (W * H);
+                const int par = ((d & 1) << 2) | ((h & 1) << 1) | (w & 1);
+                const size_t dst =
+                    (((((size_t)b * 8 + par) * nc + chunk) * (D >> 1) + (d >> 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+                *reinterpret_cast<uint4*>(y_split + dst * 8) = *reinterpret_cast<const uint4*>(out);
+            }
         }
     }
 }
@@ -226,8 +244,12 @@ extern "C" int cmfb200_gn_apply_c8_bf16(const void* x_c8, const double* gn_sums,
     CMF_REQUIRE(y_split_c8 == nullptr || ((D % 2 == 0) && (H % 2 == 0) && (W % 2 == 0)),
                 "gn_apply_c8_bf16: the parity-split copy needs even D,H,W (got %d,%d,%d)", D, H, W);
     const long long spatial = (long long)D * H * W;
+    CMF_REQUIRE(spatial < (1LL << 31) - 4LL * 256 * kNumSMs * 3, "gn_apply_c8_bf16: volume too large for 32-bit positions");
     CMF_REQUIRE((long long)B * (C / 8) <= 65535, "gn_apply_c8_bf16: B*C/8 exceeds grid limit");
-    dim3 grid((unsigned)min((long long)kNumSMs * 8, cdiv(spatial, 256)), (unsigned)(B * (C / 8)));
+    // three CTAs per SM (one wave) over all (b, chunk) columns, each thread walking four positions per iteration
+    const long long cols = (long long)B * (C / 8);
+    const long long gx = std::max(1LL, std::min(cdiv(spatial, 256 * 4), cdiv((long long)kNumSMs * 3, cols)));
+    dim3 grid((unsigned)gx, (unsigned)cols);
     gn_apply_c8_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x_c8), gn_sums, gamma, beta,
         reinterpret_cast<const __nv_bfloat16*>(residual_c8), reinterpret_cast<__nv_bfloat16*>(y_c8),
