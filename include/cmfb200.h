@@ -311,7 +311,9 @@ int cmfb200_masked_smooth_l1_bwd(const float* out1, const float* out2, const flo
  * o = (i - 1)/stride + 1 per axis; dw: [Cout][Cin][KD][k][k], MUST BE ZERO on entry (partial sums are added with fp32
  * atomics).  Cout % 32 == 0.  Supported: 3x3x3 s1/s2; 3x3 s1 d1/d2, 3x3 s2, 1x1 s1/s2.
  * Transposed conv (weight [Cin_t][Cout_t][27], k3 s2 p1 op1): call with x := grad of the OUTPUT, dy := the layer INPUT,
- * Cin := Cout_t, Cout := Cin_t, stride 2 -- the result has the ConvTranspose3d weight layout. */
+ * Cin := Cout_t, Cout := Cin_t, stride 2 -- the result has the ConvTranspose3d weight layout.
+ * Stages are fetched by TMA when W and Wo are multiples of 4 and x, dy are 16-byte aligned (every layer of the SceneFlow /
+ * KITTI-padded shapes down to 1/8 resolution); otherwise by 4-byte cp.async -- same arithmetic, same result layout. */
 int cmfb200_conv_wgrad(const float* x, const float* dy, float* dw, int B, int Cin, int Cout, int D, int H, int W, int KD,
                        int KHW, int stride, int dilation, void* stream);
 
