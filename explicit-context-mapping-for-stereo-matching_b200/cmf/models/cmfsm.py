@@ -604,7 +604,8 @@ class cmfsm(nn.Module):
             par.fill_row_halo_(out[0], P, P, P, dim=out[0].dim() - 3)
         return out
 
-    def _tc_band(self, block, x_s3, full_rows, res_s3=None, res_nchw=None, relu=False, want_s3=True, want_nchw=False):
+    def _tc_band(self, block, x_s3, full_rows, res_s3=None, res_nchw=None, relu=False, want_s3=True, want_nchw=False,
+                 nchw_pad=False):
         """Stride-1 conv (2-D or 3-D) + GroupNorm on a row band.  `x_s3` (and `res_s3`, and the C8S3 result) carry
         _BAND_PAD spare rows on both sides: the halo rows are received straight into them and the row-window conv_tc3
         reads the padded tensor -- no copy of the activation."""
@@ -617,7 +618,7 @@ class cmfsm(nn.Module):
         y, sums = ops.conv_tc3(x_s3, self._pack_tc3(conv), conv.dilation[0], True, row_off=P, out_rows=rows)
         sums = self._band_sums(sums, rows, full_rows)
         return self._band_apply(y, sums, gn.weight, gn.bias, True, res_s3=res_s3, res_nchw=res_nchw, relu=relu,
-                                want_s3=want_s3, want_nchw=want_nchw)
+                                want_s3=want_s3, want_nchw=want_nchw, nchw_pad=nchw_pad)
 
     def _ffma2_band_to_s3(self, block, x_nchw, full_rows, relu=False):
         y, sums = self._conv2_band(block[0], x_nchw, True)
@@ -701,9 +702,12 @@ class cmfsm(nn.Module):
         return o_s3, o_split, pre, post
 
     def _classify_band_tc3(self, head, x_s3, rows):
-        _, t = self._tc_band(head[0], x_s3, rows, relu=True, want_s3=False, want_nchw=True)
-        ext = par.exchange_row_halo(t, 1, 1, dim=3)
-        y, _ = ops.conv3d_k3_rows(ext, self._pack(head[2]), t.shape[3], stride=1, row_offset=1, want_stats=False)
+        """classifN on a band: the fp32 NCDHW activation is produced with the spare rows already in place, the halo rows
+        are received into them, and the row-window 32->1 kernel reads the padded tensor (no torch.cat of the volume)."""
+        P = self._BAND_PAD
+        _, t = self._tc_band(head[0], x_s3, rows, relu=True, want_s3=False, want_nchw=True, nchw_pad=True)
+        par.fill_row_halo_(t, P, 1, 1, dim=3)
+        y, _ = ops.conv3d_k3_rows(t, self._pack(head[2]), t.shape[3] - 2 * P, stride=1, row_offset=P, want_stats=False)
         return y[:, 0]
 
     def _aggregate_band_tc3(self, lband, rband, D, h):

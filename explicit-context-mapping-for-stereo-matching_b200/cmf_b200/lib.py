@@ -60,10 +60,12 @@ SIGNATURES = {
     "cmfb200_softargmin_ctxmap_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_cost_volume_concat_c8s3": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_cost_volume_corr_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "cmfb200_copy_2d": [_P, _LL, _P, _LL, _LL, _LL, _P],
     "cmfb200_masked_smooth_l1_fwd": [_P, _P, _P, _P, _P, _LL, _F, _P],
     "cmfb200_masked_smooth_l1_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _F, _P],
     "cmfb200_conv_wgrad": [_P, _P, _P] + [_I] * 10 + [_P],
-    "cmfb200_gn_apply_tc3_padded": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _F, _I, _I, _I, _I, _P, _P, _P, _I, _P],
+    "cmfb200_gn_apply_tc3_padded": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _F, _I, _I, _I, _I, _P, _P, _P, _I, _I,
+                                    _P],
     "cmfb200_conv_tc3_s2_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_deconv_tc3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_conv_tc3_s2_rows_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -91,6 +91,48 @@ def cost_volume_concat(L, R, D):
     return cost
 
 
+def pitched_2d(t):
+    """(height, width, pitch) in elements when `t` is `height` contiguous blocks of `width` elements `pitch` apart (a dense
+    tensor, or rows narrowed out of a contiguous one); None for any other striding."""
+    dims = [(n, st) for n, st in zip(t.shape, t.stride()) if n != 1]
+    width, i = 1, len(dims) - 1
+    while i >= 0 and dims[i][1] == width:
+        width *= dims[i][0]
+        i -= 1
+    if i < 0:
+        return 1, width, width
+    pitch, height = dims[i][1], dims[i][0]
+    expect = pitch * height
+    for n, st in reversed(dims[:i]):
+        if st != expect:
+            return None
+        height *= n
+        expect *= n
+    return height, width, pitch
+
+
+def copy_rows(dst, src):
+    """dst.copy_(src) for the boundary rows of band activations (row-band halo exchange): both sides are blocks of
+    contiguous rows at a fixed pitch (or dense), moved 16 bytes per thread by `cmfb200_copy_2d`; either side may live in a
+    peer GPU's mailbox.  Any other layout, dtype pair or alignment goes through ATen's copy_."""
+    if dst.is_cuda and src.is_cuda and dst.dtype == src.dtype and dst.shape == src.shape and dst.numel() > 0:
+        a, b = pitched_2d(dst), pitched_2d(src)
+        if a is not None and b is not None:
+            es = dst.element_size()
+            if a[0] == 1 and b[0] > 1:      # dense side: cut it into the other side's blocks
+                a = (b[0], b[1], b[1])
+            elif b[0] == 1 and a[0] > 1:
+                b = (a[0], a[1], a[1])
+            ok = a[0] == b[0] and a[1] == b[1]
+            vals = (dst.data_ptr(), src.data_ptr(), a[2] * es, b[2] * es, a[1] * es)
+            if ok and all(v % 16 == 0 for v in vals):
+                with torch.cuda.device(dst.device), _timed("copy_2d"):
+                    _lib.check(_lib.load().cmfb200_copy_2d(_p(dst), a[2] * es, _p(src), b[2] * es, a[1] * es, a[0], _stream()),
+                               "copy_2d")
+                return dst
+    return dst.copy_(src)
+
+
 def cost_volume_corr(L, R, D, normalize=False):
     """Correlation cost volume [B,D,h,w]: mean over channels of L[x] * R[x-d] (cosine similarity with `normalize`)."""
     _req(L, R)
@@ -790,12 +832,13 @@ def deconv_tc3(x_s3, packed, Cout, want_stats=True, pad=0):
 
 
 def gn_apply_tc3(raw, sums, gamma, beta, raw_c8f, res_s3=None, res_nchw=None, relu=False, want_s3=True, want_nchw=False,
-                 groups=GN_GROUPS, eps=GN_EPS, pad=0, want_split=False, push=None):
+                 groups=GN_GROUPS, eps=GN_EPS, pad=0, want_split=False, push=None, nchw_pad=False):
     """GroupNorm (+residual) (+ReLU) of the tc3 pipeline.  raw: C8F (raw_c8f) or NCHW/NCDHW fp32; the result is returned
     as (C8S3 or None, NCHW fp32 or None).  sums=None: layout conversion / three-term split only.
     Row bands: with `pad` the C8S3 result (and `res_s3`) carry `pad` halo rows above and below (left un-written);
     `push` = (up, dn, rows): bf16 landing buffers IN THE NEIGHBOUR RANKS' memory (or None) that receive the first / last
-    `rows` rows of the C8S3 result -- the next conv's halo exchange fused into this kernel."""
+    `rows` rows of the C8S3 result -- the next conv's halo exchange fused into this kernel.  `nchw_pad`: the NCHW result
+    carries the same `pad` rows (un-written)."""
     _req(raw, res_nchw)
     _req(res_s3, dtype=BF16)
     if sums is not None:
@@ -814,7 +857,8 @@ def gn_apply_tc3(raw, sums, gamma, beta, raw_c8f, res_s3=None, res_nchw=None, re
     if res_s3 is not None and tuple(res_s3.shape) != (B, C // 8, 3) + psp + (8,):
         raise ValueError("gn_apply_tc3: residual %s does not match %s (pad %d)" % (tuple(res_s3.shape), (B, C // 8, 3) + psp, pad))
     y_s3 = torch.empty((B, C // 8, 3) + psp + (8,), device=raw.device, dtype=BF16) if want_s3 else None
-    y_nchw = torch.empty((B, C) + sp, device=raw.device, dtype=torch.float32) if want_nchw else None
+    y_nchw = (torch.empty((B, C) + (psp if nchw_pad else sp), device=raw.device, dtype=torch.float32)
+              if want_nchw else None)
     csp = tuple(v // 2 for v in sp)
     y_split = (torch.empty((B, 8, C // 8, 3) + csp[:-2] + (csp[-2] + 2 * pad, csp[-1]) + (8,), device=raw.device, dtype=BF16)
                if want_split else None)
@@ -825,7 +869,7 @@ def gn_apply_tc3(raw, sums, gamma, beta, raw_c8f, res_s3=None, res_nchw=None, re
                                                            _p(y_s3), _p(y_nchw), B, C, groups, spatial, eps, int(relu), pad,
                                                            sp[-2], sp[-1], _p(y_split), _p(push[0]) if push else None,
                                                            _p(push[1]) if push else None, push[2] if push else 0,
-                                                           _stream()), "gn_apply_tc3")
+                                                           int(bool(nchw_pad and pad)), _stream()), "gn_apply_tc3")
     if want_split:
         return y_s3, y_nchw, y_split
     return y_s3, y_nchw

@@ -19,6 +19,14 @@ import torch
 import torch.distributed as dist
 
 
+def _copy_rows(dst, src):
+    """Boundary-row copy of the halo exchange: the pitched 16-byte kernel on CUDA tensors, copy_ on CPU (gloo tests)."""
+    if dst.is_cuda:
+        from . import ops
+        return ops.copy_rows(dst, src)
+    return dst.copy_(src)
+
+
 def world(group=None):
     """Number of ranks of `group` (default: the whole job); 1 when torch.distributed is not initialised."""
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -265,9 +273,9 @@ def _exchange(x, dim, pad_lo, n_up, n_dn, top, bottom, group):
     if mb is not None:
         off, ch = mb.slot()
         if up is not None and r > 0:
-            mb.mine(off, up).copy_(up)
+            _copy_rows(mb.mine(off, up), up)
         if dn is not None and r < n - 1:
-            mb.mine(off + nb_up, dn).copy_(dn)
+            _copy_rows(mb.mine(off + nb_up, dn), dn)
         mb.barrier(ch)
         if top and r > 0:
             got_t = mb.peer(r - 1, off + nb_up, dn)   # the previous rank's "down" region (same shape as my own)
@@ -342,17 +350,17 @@ def fill_row_halo_(x, pad, top, bottom, dim=-3, group=None):
             mb.barrier(push.ch)
             like = x.narrow(dim, 0, pad)
             lo, hi = x.narrow(dim, 0, pad), x.narrow(dim, pad + rows, pad)
-            lo.copy_(mb.mine(push.off, like)) if r > 0 else lo.zero_()             # from the previous rank's bottom rows
-            hi.copy_(mb.mine(push.off + push.nb, like)) if r < n - 1 else hi.zero_()  # from the next rank's top rows
+            _copy_rows(lo, mb.mine(push.off, like)) if r > 0 else lo.zero_()             # the previous rank's bottom rows
+            _copy_rows(hi, mb.mine(push.off + push.nb, like)) if r < n - 1 else hi.zero_()  # the next rank's top rows
             push.done = True
         return x
     got_t, got_b = _exchange(x, dim, pad, pad + rows, 0, top, bottom, group)
     if top:
         dst = x.narrow(dim, pad - top, top)
-        dst.copy_(got_t) if got_t is not None else dst.zero_()
+        _copy_rows(dst, got_t) if got_t is not None else dst.zero_()
     if bottom:
         dst = x.narrow(dim, pad + rows, bottom)
-        dst.copy_(got_b) if got_b is not None else dst.zero_()
+        _copy_rows(dst, got_b) if got_b is not None else dst.zero_()
     return x
 
 

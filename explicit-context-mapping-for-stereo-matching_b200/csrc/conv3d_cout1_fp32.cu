@@ -23,7 +23,7 @@ constexpr int kQNS = 4;
 
 __global__ void __launch_bounds__(kQThreads, 3)
     conv3d_cout1_fp32_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ wp,
-                             float* __restrict__ y, int Cin, int D, int H, int W, int tiles_w, int tiles_h) {
+                             float* __restrict__ y, int Cin, int D, int H, int W, int tiles_w, int tiles_h, int hoff) {
     extern __shared__ uint8_t q1_raw[];
     float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(q1_raw) + 127) & ~uintptr_t(127));
     float* sIn = smem;                                   // [NS][kQStage]
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kQThreads, 3)
     if (tid == 0) {
         for (int s = 0; s < kQNS && s < Cin; ++s) {
             mbar_arrive_expect_tx(full + s, kQPatch * 4);
-            tma_load_5d(sIn + s * kQStage, &tmap_x, full + s, w0 - 4, h0 - 1, d0 - 1, b * Cin + s, 0);
+            tma_load_5d(sIn + s * kQStage, &tmap_x, full + s, w0 - 4, h0 - 1 + hoff, d0 - 1, b * Cin + s, 0);
         }
     }
 
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kQThreads, 3)
         __syncthreads();  // every thread is done with stage s
         if (tid == 0 && ci + kQNS < Cin) {
             mbar_arrive_expect_tx(full + s, kQPatch * 4);
-            tma_load_5d(sIn + s * kQStage, &tmap_x, full + s, w0 - 4, h0 - 1, d0 - 1, b * Cin + ci + kQNS, 0);
+            tma_load_5d(sIn + s * kQStage, &tmap_x, full + s, w0 - 4, h0 - 1 + hoff, d0 - 1, b * Cin + ci + kQNS, 0);
         }
     }
 
@@ -108,15 +108,16 @@ __global__ void __launch_bounds__(kQThreads, 3)
     }
 }
 
-// used by cmfb200_conv3d_k3_fwd for Cout == 1; returns -1 when the shape does not qualify (caller falls back)
-int conv3d_cout1_fp32_dispatch(const float* x, const float* wp, float* y, int B, int Cin, int D, int H, int W,
-                               cudaStream_t st) {
+// used by cmfb200_conv3d_k3_fwd / _rows_fwd for Cout == 1; returns -1 when the shape does not qualify (caller falls back).
+// Row window (row bands): x has H_in rows, the H output rows read input rows m - 1 + hoff + kh (rows outside x are zero).
+int conv3d_cout1_fp32_dispatch(const float* x, const float* wp, float* y, int B, int Cin, int D, int H_in, int W, int hoff,
+                               int H, cudaStream_t st) {
     if ((W & 3) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0 || Cin > 64 || B > 65535)
         return -1;
     CUtensorMap tmap;
-    const cuuint64_t gdim[5] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * Cin, 1};
-    const cuuint64_t gstr[4] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)D * H * W * 4,
-                                (cuuint64_t)B * Cin * D * H * W * 4};
+    const cuuint64_t gdim[5] = {(cuuint64_t)W, (cuuint64_t)H_in, (cuuint64_t)D, (cuuint64_t)B * Cin, 1};
+    const cuuint64_t gstr[4] = {(cuuint64_t)W * 4, (cuuint64_t)H_in * W * 4, (cuuint64_t)D * H_in * W * 4,
+                                (cuuint64_t)B * Cin * D * H_in * W * 4};
     const cuuint32_t box[5] = {kQPW, kQPH, kQPD, 1, 1};
     if (int rc = encode_tmap_5d(&tmap, x, gdim, gstr, box, "conv3d_cout1_fp32", CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return rc;
     const size_t smem = (size_t)kQNS * kQStage * 4 + (size_t)Cin * 28 * 4 + kQNS * 8 + 128;
@@ -124,7 +125,7 @@ int conv3d_cout1_fp32_dispatch(const float* x, const float* wp, float* y, int B,
     const int tiles_w = (int)cdiv(W, kQTW), tiles_h = (int)cdiv(H, kQTH);
     dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)cdiv(D, kQTD), (unsigned)B);
     CMF_REQUIRE(grid.y <= 65535, "conv3d_cout1_fp32: depth too large");
-    conv3d_cout1_fp32_kernel<<<grid, kQThreads, smem, st>>>(tmap, wp, y, Cin, D, H, W, tiles_w, tiles_h);
+    conv3d_cout1_fp32_kernel<<<grid, kQThreads, smem, st>>>(tmap, wp, y, Cin, D, H, W, tiles_w, tiles_h, hoff);
     CMF_LAUNCH_CHECK("conv3d_cout1_fp32_kernel");
     return CMFB200_OK;
 }

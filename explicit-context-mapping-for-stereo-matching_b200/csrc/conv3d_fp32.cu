@@ -675,8 +675,8 @@ static int launch_deconv(const float* x, const float* wp, float* y, double* gn, 
     return CMFB200_OK;
 }
 
-int conv3d_cout1_fp32_dispatch(const float* x, const float* wp, float* y, int B, int Cin, int D, int H, int W,
-                               cudaStream_t st);  // conv3d_cout1_fp32.cu
+int conv3d_cout1_fp32_dispatch(const float* x, const float* wp, float* y, int B, int Cin, int D, int H_in, int W, int hoff,
+                               int H_out, cudaStream_t st);  // conv3d_cout1_fp32.cu
 
 }  // namespace cmfb200
 
@@ -700,8 +700,9 @@ static int conv3d_k3_dispatch(const float* x, const float* packed_w, float* y, d
     if (Cout == 32 && stride == 2) return launch_conv<32, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
     if (Cout == 64 && stride == 2) return launch_conv<64, 8, 2, 2, 32>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);
     if (Cout == 1 && stride == 1) {
-        if (gn_sums == nullptr && rw.Ho < 0) {  // classifier tail: TMA-staged 4x4-outputs-per-thread kernel
-            const int rc = conv3d_cout1_fp32_dispatch(x, packed_w, y, B, Cin, D, H, W, st);
+        if (gn_sums == nullptr) {  // classifier tail: TMA-staged 4x4-outputs-per-thread kernel (also on a row window)
+            const int rc = rw.Ho < 0 ? conv3d_cout1_fp32_dispatch(x, packed_w, y, B, Cin, D, H, W, 0, H, st)
+                                     : conv3d_cout1_fp32_dispatch(x, packed_w, y, B, Cin, D, H, W, rw.hoff, rw.Ho, st);
             if (rc >= 0) return rc;
         }
         return launch_conv_best<1, 1, 1, 4>(x, packed_w, y, gn_sums, B, Cin, D, H, W, st, rw);

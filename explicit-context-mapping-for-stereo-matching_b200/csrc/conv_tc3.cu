@@ -337,6 +337,7 @@ struct GnTc3Args {
     float eps;
     int relu, raw_c8f;
     int pad, H, W;  // row bands: y_s3 / res_s3 carry `pad` extra rows above and below the H rows (0 = dense)
+    int nchw_padded;  // row bands: y_nchw carries the same `pad` rows (the 32->1 tail reads its halo rows in place)
     // row bands, fused halo push: the first / last `push_rows` rows of the C8S3 result are ALSO stored into the neighbour
     // ranks' landing buffers (peer-mapped memory over NVLink), dense [B*C/8][3][D][push_rows][W][8]; either may be null
     __nv_bfloat16* push_up;
@@ -487,7 +488,9 @@ __global__ void __launch_bounds__(256, 4) gn_apply_tc3_kernel(const GnTc3Args a)
             }
             if (a.y_nchw != nullptr) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) a.y_nchw[((size_t)b * a.C + g * 8 + e) * S + p] = v[u][e];
+                for (int e = 0; e < 8; ++e)
+                    a.y_nchw[a.nchw_padded ? ((size_t)b * a.C + g * 8 + e) * Sp + pp[u] : ((size_t)b * a.C + g * 8 + e) * S + p] =
+                        v[u][e];
             }
         }
     }
@@ -630,7 +633,7 @@ extern "C" int cmfb200_gn_apply_tc3_padded(const float* raw, int raw_is_c8f, con
                                            const float* beta, const void* residual_c8s3, const float* residual_nchw,
                                            void* y_c8s3, float* y_nchw, int B, int C, int groups, long long spatial,
                                            float eps, int relu, int pad, int H, int W, void* y_split_c8s3, void* push_up,
-                                           void* push_dn, int push_rows, void* stream) {
+                                           void* push_dn, int push_rows, int nchw_padded, void* stream) {
     CMF_REQUIRE(raw && (y_c8s3 || y_nchw || y_split_c8s3), "gn_apply_tc3: null pointer");
     CMF_REQUIRE(push_rows >= 0 && (push_rows == 0 || (y_c8s3 && H >= push_rows && W > 0)),
                 "gn_apply_tc3: the halo push needs the C8S3 output and push_rows <= H");
@@ -650,7 +653,7 @@ extern "C" int cmfb200_gn_apply_tc3_padded(const float* raw, int raw_is_c8f, con
     a.push_up = reinterpret_cast<__nv_bfloat16*>(push_up), a.push_dn = reinterpret_cast<__nv_bfloat16*>(push_dn);
     a.push_rows = (push_up || push_dn) ? push_rows : 0;
     a.C = C, a.cpg = gn_sums ? C / groups : 1, a.spatial = spatial, a.eps = eps, a.relu = relu, a.raw_c8f = raw_is_c8f;
-    a.pad = pad, a.H = H, a.W = W;
+    a.pad = pad, a.H = H, a.W = W, a.nchw_padded = (nchw_padded && pad > 0) ? 1 : 0;
     long long bx = cdiv(spatial, 256 * 4);  // 4 positions per thread, all loads of an iteration in flight together
     if (bx > 8192) bx = 8192;
     dim3 grid((unsigned)bx, (unsigned)(B * (C / 8)));
@@ -667,7 +670,7 @@ extern "C" int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const doub
                                     void* y_c8s3, float* y_nchw, int B, int C, int groups, long long spatial, float eps,
                                     int relu, void* stream) {
     return cmfb200_gn_apply_tc3_padded(raw, raw_is_c8f, gn_sums, gamma, beta, residual_c8s3, residual_nchw, y_c8s3, y_nchw, B,
-                                       C, groups, spatial, eps, relu, 0, 0, 0, nullptr, nullptr, nullptr, 0, stream);
+                                       C, groups, spatial, eps, relu, 0, 0, 0, nullptr, nullptr, nullptr, 0, 0, stream);
 }
 
 extern "C" int cmfb200_cost_volume_concat_c8s3_padded(const float* L, const float* R, void* cost_c8s3, int B, int C, int h,

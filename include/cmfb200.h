@@ -275,11 +275,13 @@ int cmfb200_gn_apply_tc3(const float* raw, int raw_is_c8f, const double* gn_sums
  * tensor-core conv reads (D, H, W even; H and W must then be passed).
  * Row-band forms: y_c8s3 / residual_c8s3 (and the K1 output) carry `pad` extra rows above and below the H rows of every
  * depth plane ([...][D][H + 2 pad][W][8]); the kernels fill the H interior rows, the halo rows are filled by the halo
- * exchange -- no re-copy of the activation to attach them.  pad = 0 is the dense form. */
+ * exchange -- no re-copy of the activation to attach them.  pad = 0 is the dense form.  nchw_padded != 0: y_nchw
+ * carries the same `pad` rows ([B][C][D][H + 2 pad][W]; the row-window 32->1 tail reads its halo rows in place). */
 int cmfb200_gn_apply_tc3_padded(const float* raw, int raw_is_c8f, const double* gn_sums, const float* gamma,
                                 const float* beta, const void* residual_c8s3, const float* residual_nchw, void* y_c8s3,
                                 float* y_nchw, int B, int C, int groups, long long spatial, float eps, int relu, int pad,
-                                int H, int W, void* y_split_c8s3, void* push_up, void* push_dn, int push_rows, void* stream);
+                                int H, int W, void* y_split_c8s3, void* push_up, void* push_dn, int push_rows,
+                                int nchw_padded, void* stream);
 int cmfb200_cost_volume_concat_c8s3_padded(const float* L, const float* R, void* cost_c8s3, int B, int C, int h, int w,
                                            int D, int pad, void* stream);
 /* K1 written directly as C8S3 (cmfsm.py:667-682): cost [B][2C/8][3][D][h][w][8] bf16; the three terms of an element
@@ -304,6 +306,12 @@ int cmfb200_masked_smooth_l1_fwd(const float* out1, const float* out2, const flo
 int cmfb200_masked_smooth_l1_bwd(const float* out1, const float* out2, const float* out3, const float* disp,
                                  const float* scale3, float* g1, float* g2, float* g3, long long n, float maxdisp,
                                  void* stream);
+
+/* ---- pitched block copy for the row-band halo exchange (cmf_b200/parallel.py) ---------------------------
+ * `height` blocks of `width` contiguous bytes, dst_pitch / src_pitch bytes apart; everything a multiple of 16 bytes.
+ * dst or src may be a peer GPU's memory mapped through the symmetric-memory mailbox (NVLink loads / stores). */
+int cmfb200_copy_2d(void* dst, long long dst_pitch, const void* src, long long src_pitch, long long width, long long height,
+                    void* stream);
 
 /* ---- weight gradient of every convolution (training backward; replaces aten::convolution_backward) ------------------
  * dW[co][ci][kd][kh][kw] = sum_{b,o} dy[b][co][o] * x[b][ci][o*stride - pad + k*dilation], "same" padding (dilation*(k/2),

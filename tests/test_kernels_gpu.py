@@ -633,3 +633,27 @@ def test_masked_smooth_l1_fused_vs_reference_statement(B, H, W):
     assert abs(float(got.detach()) - float(want.detach())) < 1e-5 * abs(float(want.detach()))
     for a, b in zip(ours_in, ref_in):
         torch.testing.assert_close(a.grad.cpu().double(), 3.0 * b.grad, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_copy_rows_pitched(dtype):
+    """cmfb200_copy_2d (halo rows of band activations): strided rows <- dense, dense <- strided rows, odd layouts fall
+    back to copy_; bit-exact, nothing outside the rows is touched."""
+    from cmf_b200 import lib, ops
+
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 4, 3, 6, 10, 12, 8, generator=g).to(DEV).to(dtype)
+    src = torch.randn(1, 4, 3, 6, 2, 12, 8, generator=g).to(DEV).to(dtype)
+    want = x.clone()
+    want.narrow(4, 8, 2).copy_(src)
+    n0 = lib.launch_count()
+    ops.copy_rows(x.narrow(4, 8, 2), src)
+    assert lib.launch_count() == n0 + 1 and torch.equal(x, want)
+    dense = torch.empty_like(src)
+    ops.copy_rows(dense, x.narrow(4, 0, 2))
+    assert lib.launch_count() == n0 + 2 and torch.equal(dense, x.narrow(4, 0, 2))
+    # 4-byte-aligned only (one fp32 column): ATen path, same result
+    y = torch.randn(2, 5, 7, generator=g).to(DEV)
+    col = torch.randn(2, 5, 1, generator=g).to(DEV)
+    ops.copy_rows(y.narrow(2, 3, 1), col)
+    assert lib.launch_count() == n0 + 2 and torch.equal(y[:, :, 3:4], col)

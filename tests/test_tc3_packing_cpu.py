@@ -60,3 +60,20 @@ def test_transposed_decomposition_over_output_parity_classes():
                         ti += 1
     assert ti == taps.shape[0] == 27 * (Cin // 16)
     torch.testing.assert_close(out, F.conv_transpose3d(x, wgt, None, 2, 1, 1), rtol=1e-5, atol=1e-5)
+
+
+def test_pitched_2d_views():
+    """ops.pitched_2d: the (height, width, pitch) description of band boundary rows that cmfb200_copy_2d moves."""
+    import torch
+    from cmf_b200 import ops
+
+    x = torch.zeros(1, 4, 3, 6, 10, 12, 8)
+    assert ops.pitched_2d(x) == (1, x.numel(), x.numel())
+    rows = x.narrow(4, 2, 3)                      # 3 of the 10 rows: blocks of 3*12*8 elements, 10*12*8 apart
+    assert ops.pitched_2d(rows) == (4 * 3 * 6, 3 * 12 * 8, 10 * 12 * 8)
+    assert ops.pitched_2d(x.narrow(4, 0, 10)) == (1, x.numel(), x.numel())
+    assert ops.pitched_2d(x[..., ::2, :]) == (4 * 3 * 6 * 10 * 6, 8, 16)  # every other column: 8-element blocks
+    assert ops.pitched_2d(x.transpose(3, 4)) is None                      # permuted dims: not a pitched block copy
+    assert ops.pitched_2d(x.narrow(4, 2, 3).narrow(3, 1, 2)) is None   # two narrowed dims do not collapse
+    y = torch.zeros(2, 32, 5, 7)
+    assert ops.pitched_2d(y.narrow(2, 1, 2)) == (64, 14, 35)

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay the band forward as one CUDA graph per rank")
+    ap.add_argument("--torch-profile", action="store_true", help="rank 0: kernel table of one band forward (torch.profiler)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -56,6 +57,30 @@ def main():
         dist.all_gather(gathered, ms)
         per_rank = [float(t) for t in gathered]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if args.torch_profile:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            model.forward_row_bands(left, right)
+            torch.cuda.synchronize()
+        if rank == 0:
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70))
+            # idle time on the device: gaps between consecutive kernels / copies of the replayed forward
+            ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
+                         if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda t: t[0])
+            busy = sum(b - a for a, b, _ in ev)
+            gaps, t_end = [], ev[0][1]
+            for i in range(1, len(ev)):
+                if ev[i][0] > t_end:
+                    gaps.append((ev[i][0] - t_end, ev[i - 1][2][:60], ev[i][2][:60]))
+                t_end = max(t_end, ev[i][1])
+            print("device span %.2f ms, busy %.2f ms, %d gaps totalling %.2f ms" %
+                  ((t_end - ev[0][0]) / 1e3, busy / 1e3, len(gaps), sum(g[0] for g in gaps) / 1e3))
+            by_next = {}
+            for g, prev, nxt in gaps:
+                k = (prev[:40], nxt[:40])
+                by_next[k] = (by_next.get(k, (0, 0))[0] + g, by_next.get(k, (0, 0))[1] + 1)
+            for k, (g, n) in sorted(by_next.items(), key=lambda kv: -kv[1][0])[:12]:
+                print("   %8.1f us in %4d gaps   %s  ->  %s" % (g, n, k[0], k[1]))
     if args.profile:  # where does a band forward spend its time?  (our kernels by event pairs vs the elapsed time)
         from cmf_b200 import ops
         ops.enable_event_timing(True)
