@@ -578,7 +578,7 @@ class cmfsm(nn.Module):
     def _band_sums(sums, band_rows, full_rows):
         """All-reduce the band's GroupNorm sums and rescale them so that gn_apply (which derives mean / var from the
         sums and the element count of THIS tensor) reproduces the statistics of the whole volume."""
-        return par.allreduce_gn_sums(sums) * (float(band_rows) / float(full_rows))
+        return par.allreduce_gn_sums(sums, scale=float(band_rows) / float(full_rows))
 
     _BAND_PAD = 2  # spare rows above / below every C8S3 band activation (largest halo: dilation 2)
 

@@ -16,6 +16,7 @@ _P = _c.c_void_p
 _I = _c.c_int
 _LL = _c.c_longlong
 _F = _c.c_float
+_D = _c.c_double
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/cmfb200.h one to one
 SIGNATURES = {
@@ -61,6 +62,7 @@ SIGNATURES = {
     "cmfb200_cost_volume_concat_c8s3": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cmfb200_cost_volume_corr_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cmfb200_copy_2d": [_P, _LL, _P, _LL, _LL, _LL, _P],
+    "cmfb200_sum_peers_f64": [_P, _P, _I, _I, _D, _P],
     "cmfb200_masked_smooth_l1_fwd": [_P, _P, _P, _P, _P, _LL, _F, _P],
     "cmfb200_masked_smooth_l1_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _F, _P],
     "cmfb200_conv_wgrad": [_P, _P, _P] + [_I] * 10 + [_P],

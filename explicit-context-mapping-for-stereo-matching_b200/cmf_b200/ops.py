@@ -133,6 +133,21 @@ def copy_rows(dst, src):
     return dst.copy_(src)
 
 
+def sum_peers(dst, peers, scale=1.0):
+    """dst = scale * (peers[0] + peers[1] + ...) over double tensors of dst's shape (the ranks' mailbox views of the band
+    GroupNorm sums), summed in list order by ONE kernel."""
+    n = dst.numel()
+    for t in peers:
+        if t.dtype != torch.float64 or t.numel() != n or not t.is_contiguous() or not t.is_cuda:
+            raise _lib.CmfB200Error("sum_peers: every peer buffer must be a contiguous CUDA double tensor of dst's size")
+    if dst.dtype != torch.float64 or not dst.is_contiguous():
+        raise _lib.CmfB200Error("sum_peers: dst must be a contiguous double tensor")
+    ptrs = (ctypes.c_void_p * len(peers))(*[t.data_ptr() for t in peers])
+    with torch.cuda.device(dst.device), _timed("sum_peers"):
+        _lib.check(_lib.load().cmfb200_sum_peers_f64(_p(dst), ptrs, len(peers), n, float(scale), _stream()), "sum_peers_f64")
+    return dst
+
+
 def cost_volume_corr(L, R, D, normalize=False):
     """Correlation cost volume [B,D,h,w]: mean over channels of L[x] * R[x-d] (cosine similarity with `normalize`)."""
     _req(L, R)

@@ -364,24 +364,27 @@ def fill_row_halo_(x, pad, top, bottom, dim=-3, group=None):
     return x
 
 
-def allreduce_gn_sums(sums, group=None):
-    """Sum per-band GroupNorm statistics ([B,C,2] double: sum, sum of squares) over all bands, in place.  Peer-memory
-    path: every rank publishes its sums, one barrier, every rank adds the n buffers in rank order (identical result on
-    every rank); otherwise one all-reduce."""
+def allreduce_gn_sums(sums, group=None, scale=1.0):
+    """Sum per-band GroupNorm statistics ([B,C,2] double: sum, sum of squares) over all bands, in place, times `scale`.
+    Peer-memory path: every rank publishes its sums, one barrier, ONE kernel adds the n buffers in rank order (identical
+    result on every rank); otherwise one all-reduce."""
     n = world(group)
     if n == 1:
-        return sums
+        return sums if scale == 1.0 else sums.mul_(scale)
     mb = _mailbox(group, sums.device, _align(sums.numel() * sums.element_size())) if sums.is_cuda else None
     if mb is None:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-        return sums
+        return sums if scale == 1.0 else sums.mul_(scale)
     off, ch = mb.slot()
     mb.mine(off, sums).copy_(sums)
     mb.barrier(ch)
+    if n <= 16 and sums.is_contiguous():
+        from . import ops
+        return ops.sum_peers(sums, [mb.peer(r, off, sums) for r in range(n)], scale)
     sums.copy_(mb.peer(0, off, sums))
     for r in range(1, n):
         sums.add_(mb.peer(r, off, sums))
-    return sums
+    return sums if scale == 1.0 else sums.mul_(scale)
 
 
 def gather_bands(x, dim=-2, group=None):

@@ -312,6 +312,9 @@ int cmfb200_masked_smooth_l1_bwd(const float* out1, const float* out2, const flo
  * dst or src may be a peer GPU's memory mapped through the symmetric-memory mailbox (NVLink loads / stores). */
 int cmfb200_copy_2d(void* dst, long long dst_pitch, const void* src, long long src_pitch, long long width, long long height,
                     void* stream);
+/* GroupNorm statistics of a row-band forward: dst[i] = scale * sum_r srcs[r][i] (doubles), r = 0..n-1 in rank order on every
+ * rank; srcs = HOST array of n <= 16 device pointers (the ranks' mailbox buffers, peer-mapped). */
+int cmfb200_sum_peers_f64(double* dst, const void* const* srcs, int n, int count, double scale, void* stream);
 
 /* ---- weight gradient of every convolution (training backward; replaces aten::convolution_backward) ------------------
  * dW[co][ci][kd][kh][kw] = sum_{b,o} dy[b][co][o] * x[b][ci][o*stride - pad + k*dilation], "same" padding (dilation*(k/2),
