@@ -99,6 +99,10 @@ def _worker(rank, world, port, h_total):
     par.allreduce_gn_sums(sums)
     full_sums = torch.stack([yfull.sum((2, 3, 4)), (yfull * yfull).sum((2, 3, 4))], -1)
     torch.testing.assert_close(sums, full_sums)
+    # the scaled form the band forward uses (sums * band_rows / full_rows, so that gn_apply's own element count fits)
+    part = torch.stack([yb.sum((2, 3, 4)), (yb * yb).sum((2, 3, 4))], -1)
+    scaled = par.allreduce_gn_sums(part, scale=float(r1 - r0) / h_total)
+    torch.testing.assert_close(scaled, full_sums * (float(r1 - r0) / h_total))
     # normalise with the GLOBAL statistics (n = full volume), then gather the bands
     B_, C_ = yb.shape[:2]
     n_full = (C_ // 8) * yfull[0, 0].numel()
